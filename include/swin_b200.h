@@ -1,0 +1,156 @@
+/*
+ * swin_b200 — C ABI of the B200 (sm_100a) kernels behind the Swin backbone's shifted-window
+ * attention path.  This is the drop-in boundary: plain pointers and sizes, no torch types.
+ *
+ * The reference (an mmdetection 2.11 fork) is pure Python and ships no native interface; the
+ * "FFI" for this path is the set of torch calls made by
+ *     mmdet/models/backbones/swin_transformer.py            (cited below as REF:line)
+ * Each entry point names the reference lines it replaces.  The Python package `swin_b200`
+ * binds these with ctypes (swin_b200/_lib.py); INTEGRATION.md shows the stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every function ENQUEUES work on `stream` (a cudaStream_t passed as void*) and returns:
+ *       0 on success, a negative errno-style code (-EINVAL bad shape/alignment/dtype,
+ *       -ENOTSUP device is not sm_100) or a positive cudaError_t.  Nothing throws, allocates
+ *       device memory or synchronises.  swin_last_error() returns a thread-local message.
+ *   - all device pointers must be 16-byte aligned, tensors contiguous unless a leading
+ *     dimension is given.  Entry points are re-entrant (forward runs on the Python main
+ *     thread, backward on autograd's worker thread).
+ *   - dtypes: SWIN_F32 = 0, SWIN_BF16 = 1.  "bf16" kernels take bf16 operands, accumulate and
+ *     normalise in fp32.  The residual stream and LayerNorm statistics are always fp32.
+ *   - geometry: B images, H x W tokens per image (token-major (B, H*W, C)), window size ws,
+ *     shift in {0, ws/2}; Hp, Wp = H, W rounded up to a multiple of ws; nW = Hp/ws * Wp/ws;
+ *     N = ws*ws; window slots are (B*nW, N, C).
+ */
+#ifndef SWIN_B200_H_
+#define SWIN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWIN_B200_VERSION 100 /* 0.1.0 */
+
+enum { SWIN_F32 = 0, SWIN_BF16 = 1 };
+
+int swin_version(void);
+const char* swin_last_error(void);
+/* 0 if `device` is compute capability 10.x, else -ENOTSUP. */
+int swin_device_check(int device);
+
+/* ---------------------------------------------------------------- index ops (bit-exact) */
+
+/* window_partition, REF:41-53.  x (B,Hp,Wp,C) -> win (B*nW, ws, ws, C); elem_bytes in {2,4}. */
+int swin_window_partition(const void* x, void* win, int B, int Hp, int Wp, int C, int ws, int elem_bytes, void* stream);
+/* window_reverse, REF:56-70.  win (B*nW, ws, ws, C) -> x (B,Hp,Wp,C). */
+int swin_window_reverse(const void* win, void* x, int B, int Hp, int Wp, int C, int ws, int elem_bytes, void* stream);
+/* F.pad + torch.roll(-shift) + window_partition, REF:214-231.  x (B,H*W,C) -> xw (B*nW, N, C); pad slots = 0. */
+int swin_window_gather(const void* x, void* xw, int B, int H, int W, int C, int ws, int shift, int elem_bytes, void* stream);
+/* window_reverse + torch.roll(+shift) + crop, REF:236-249.  xw (B*nW,N,C) -> x (B,H*W,C). */
+int swin_window_scatter(const void* xw, void* x, int B, int H, int W, int C, int ws, int shift, int elem_bytes, void* stream);
+/* SW-MSA mask of BasicLayer.forward, REF:370-389.  mask (nW,N,N) fp32 in {0,-100}. */
+int swin_shift_mask(float* mask, int H, int W, int ws, int shift, void* stream);
+/* relative_position_bias gather, REF:135-137: table ((2ws-1)^2, nH) -> bias (nH,N,N) fp32. */
+int swin_rel_bias_expand(const float* table, float* bias, int nH, int ws, void* stream);
+/* its transpose (index_put accumulate of the autograd backward): dtable += scatter(dbias). */
+int swin_rel_bias_reduce(const float* dbias, float* dtable, int nH, int ws, void* stream);
+
+/* ---------------------------------------------------------------- LayerNorm family
+ * mode 0: plain rows           x (rows, C)                       -> y (rows, C)        REF:253 norm2, :620
+ * mode 1: LN + pad/roll/partition  x (B,H*W,C)                   -> y (B*nW, N, C)     REF:211-231
+ * mode 2: PatchMerging 2x2 gather + LN(4C)  x (B,H*W,C)          -> y (B*H2*W2, 4C)    REF:281-295
+ * x is fp32; y has dtype y_dtype.  mean/rstd: fp32 per LN row (mode 0/1: B*H*W, mode 2: B*H2*W2).
+ */
+typedef struct swin_ln_args {
+  int mode;
+  int B, H, W, C;      /* mode 0: rows = B*H*W with C = row width                                  */
+  int ws, shift;       /* mode 1 only                                                              */
+  float eps;
+  int y_dtype;         /* SWIN_F32 / SWIN_BF16 for y (fwd) and dy (bwd)                            */
+  const float* x;      /* fp32 input rows                                                          */
+  const float* gamma;  /* (C) or (4C)                                                              */
+  const float* beta;
+  void* y;             /* fwd out                                                                  */
+  float* mean;         /* fwd out / bwd in                                                         */
+  float* rstd;
+  const void* dy;      /* bwd in, same layout as y                                                 */
+  const float* dres;   /* bwd in, optional (may be NULL): gradient already flowing on x, added     */
+  float* dx;           /* bwd out fp32, same layout as x                                           */
+  float* dgamma;       /* bwd out, ACCUMULATED (+=) with atomics: caller zero-fills               */
+  float* dbeta;
+} swin_ln_args;
+int swin_ln_fwd(const swin_ln_args* a, void* stream);
+int swin_ln_bwd(const swin_ln_args* a, void* stream);
+
+/* ---------------------------------------------------------------- GEMM with fused epilogues
+ * acc[m,n] = sum_k A[m,k] * B[n,k]
+ *   a_trans = 0: A stored (M,K) row-major, leading dim lda.   a_trans = 1: A stored (K,M) row-major.
+ *   b_trans = 0: B stored (N,K) row-major (an nn.Linear weight).  b_trans = 1: B stored (K,N) row-major.
+ * dtype SWIN_F32: A,B fp32, FFMA path (the <=1e-4 parity mode).  SWIN_BF16: A,B bf16, tcgen05.mma
+ * (TMA-fed, fp32 accumulation in TMEM).
+ */
+enum {
+  SWIN_EPI_STORE = 0,            /* D = acc (+bias)                              qkv REF:129, reduction REF:296, dX  */
+  SWIN_EPI_GELU = 1,             /* D2 = u = acc+bias ; D = gelu_erf(u)          fc1 + act, REF:33-34                */
+  SWIN_EPI_RESIDUAL = 2,         /* D(fp32) = aux + row_scale[b] * (acc+bias)    fc2 + drop_path + residual REF:253  */
+  SWIN_EPI_SCATTER_RESIDUAL = 3, /* same, rows are window slots scattered through the REF:236-252 inverse map        */
+  SWIN_EPI_DGELU = 4,            /* D = acc * gelu'(aux)  (aux = saved u)        backward of REF:34                  */
+  SWIN_EPI_ATOMIC_ADD = 5        /* D(fp32) += acc   (split-K weight gradients)                                      */
+};
+typedef struct swin_gemm_args {
+  int dtype;            /* operand dtype: SWIN_F32 or SWIN_BF16 */
+  int M, N, K;
+  const void* A; int a_trans; int64_t lda;
+  const void* B; int b_trans; int64_t ldb;
+  int epilogue;
+  const float* bias;    /* (N) fp32 or NULL */
+  void* D; int d_dtype; int64_t ldd;
+  void* D2;             /* GELU: pre-activation output, same dtype/ld as D */
+  const void* aux;      /* RESIDUAL / SCATTER_RESIDUAL: fp32 residual (same layout as D); DGELU: u (dtype d_dtype, ld ldd) */
+  const float* row_scale; /* per-image drop-path multiplier (B) or NULL                                 */
+  int rows_per_image;   /* RESIDUAL: H*W ; SCATTER_RESIDUAL: nW*N                                      */
+  int H, W, ws, shift;  /* SCATTER_RESIDUAL geometry                                                   */
+} swin_gemm_args;
+int swin_gemm(const swin_gemm_args* a, void* stream);
+
+/* colsum[n] += sum_m X[m,n]  (bias gradients); X (M,N) ld, dtype; colsum fp32, caller zero-fills. */
+int swin_colsum(const void* X, int M, int N, int64_t ld, int dtype, float* colsum, void* stream);
+
+/* y = row_scale[b] * x, fp32 -> dtype; mode 0 rows 1:1, mode 1 gathered into window slots (pad slots 0)
+ * (the backward of the residual/scatter epilogues: dY for fc2 / proj). */
+int swin_scale_cast(const float* x, void* y, const float* row_scale, int mode, int B, int H, int W, int C, int ws,
+                    int shift, int y_dtype, void* stream);
+/* fp32 -> bf16 copy (weights shadow copies), n elements */
+int swin_cast_bf16(const float* x, void* y, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------- window attention core, REF:129-150
+ * qkv (B_, N, 3C): columns [q|k|v] x [head] x [32].  bias (nH,N,N) fp32 (swin_rel_bias_expand).
+ * mask (nW,N,N) fp32 or NULL; window w uses mask[w % nW] (REF:141-143).
+ * out (B_, N, C) heads concatenated (REF:150).  lse (B_, nH, N) fp32 row log-sum-exp (saved for backward).
+ * head_dim must be 32.  dtype SWIN_BF16 -> tcgen05 kernel (two 64-row padded windows per 128-row tile).
+ */
+typedef struct swin_attn_args {
+  int dtype;
+  int B_, nH, ws, nW;
+  float scale;
+  const void* qkv;
+  const float* bias;
+  const float* mask;
+  void* out;
+  float* lse;
+  /* backward */
+  const void* dout;   /* (B_,N,C) */
+  void* dqkv;         /* (B_,N,3C) */
+  float* dbias;       /* (nH,N,N) fp32, ACCUMULATED with atomics: caller zero-fills */
+} swin_attn_args;
+int swin_window_attn_fwd(const swin_attn_args* a, void* stream);
+int swin_window_attn_bwd(const swin_attn_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWIN_B200_H_ */

@@ -1,0 +1,180 @@
+// fp32 window attention core (FFMA): the <=1e-4 parity mode.  One CTA per (window, head),
+// one thread per query row; S/P live in shared memory.  REF:129-150 forward, SURVEY App. E backward.
+#include "common.cuh"
+
+namespace swin {
+
+struct AttnSimtParams {
+  int B_, nH, N, nW, C;
+  float scale;
+  const float* qkv; const float* bias; const float* mask;
+  float* out; float* lse;
+  const float* dout; float* dqkv; float* dbias;
+};
+
+constexpr int HD = 32;
+
+__global__ void attn_simt_fwd_kernel(AttnSimtParams p) {
+  extern __shared__ float sm[];
+  const int N = p.N, b = blockIdx.x / p.nH, h = blockIdx.x % p.nH;
+  float* sk = sm;                 // [N][33]
+  float* sv = sk + N * 33;        // [N][33]
+  const float* base = p.qkv + (size_t)b * N * 3 * p.C + h * HD;
+  for (int e = threadIdx.x; e < N * HD; e += blockDim.x) {
+    int j = e / HD, d = e % HD;
+    sk[j * 33 + d] = base[(size_t)j * 3 * p.C + p.C + d];
+    sv[j * 33 + d] = base[(size_t)j * 3 * p.C + 2 * p.C + d];
+  }
+  __syncthreads();
+  const int i = threadIdx.x;
+  if (i >= N) return;
+  float q[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) q[d] = base[(size_t)i * 3 * p.C + d] * p.scale;
+  const float* brow = p.bias + ((size_t)h * N + i) * N;
+  const float* mrow = p.mask ? p.mask + ((size_t)(b % p.nW) * N + i) * N : nullptr;
+  float mx = -INFINITY;
+  for (int j = 0; j < N; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) s = fmaf(q[d], sk[j * 33 + d], s);
+    s += brow[j];
+    if (mrow) s += mrow[j];
+    mx = fmaxf(mx, s);
+  }
+  float o[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) o[d] = 0.f;
+  float sum = 0.f;
+  for (int j = 0; j < N; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) s = fmaf(q[d], sk[j * 33 + d], s);
+    s += brow[j];
+    if (mrow) s += mrow[j];
+    float e = expf(s - mx);
+    sum += e;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = fmaf(e, sv[j * 33 + d], o[d]);
+  }
+  const float inv = 1.0f / sum;
+  float* orow = p.out + ((size_t)b * N + i) * p.C + h * HD;
+#pragma unroll
+  for (int d = 0; d < HD; ++d) orow[d] = o[d] * inv;
+  p.lse[((size_t)b * p.nH + h) * N + i] = mx + logf(sum);
+}
+
+__global__ void attn_simt_bwd_kernel(AttnSimtParams p) {
+  extern __shared__ float sm[];
+  const int N = p.N, b = blockIdx.x / p.nH, h = blockIdx.x % p.nH;
+  float* sq = sm;                  // [N][33]  (unscaled q)
+  float* sk = sq + N * 33;
+  float* sv = sk + N * 33;
+  float* sdo = sv + N * 33;
+  float* sp = sdo + N * 33;        // [N][N+1]
+  float* sds = sp + N * (N + 1);   // [N][N+1]
+  const float* base = p.qkv + (size_t)b * N * 3 * p.C + h * HD;
+  const float* dobase = p.dout + (size_t)b * N * p.C + h * HD;
+  for (int e = threadIdx.x; e < N * HD; e += blockDim.x) {
+    int j = e / HD, d = e % HD;
+    sq[j * 33 + d] = base[(size_t)j * 3 * p.C + d];
+    sk[j * 33 + d] = base[(size_t)j * 3 * p.C + p.C + d];
+    sv[j * 33 + d] = base[(size_t)j * 3 * p.C + 2 * p.C + d];
+    sdo[j * 33 + d] = dobase[(size_t)j * p.C + d];
+  }
+  __syncthreads();
+  const int i = threadIdx.x;
+  if (i < N) {
+    const float* brow = p.bias + ((size_t)h * N + i) * N;
+    const float* mrow = p.mask ? p.mask + ((size_t)(b % p.nW) * N + i) * N : nullptr;
+    const float l = p.lse[((size_t)b * p.nH + h) * N + i];
+    float delta = 0.f;
+    for (int j = 0; j < N; ++j) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) {
+        s = fmaf(sq[i * 33 + d] * p.scale, sk[j * 33 + d], s);
+        dp = fmaf(sdo[i * 33 + d], sv[j * 33 + d], dp);
+      }
+      s += brow[j];
+      if (mrow) s += mrow[j];
+      float pr = expf(s - l);
+      sp[i * (N + 1) + j] = pr;
+      sds[i * (N + 1) + j] = dp;       // temporarily dP
+      delta = fmaf(pr, dp, delta);
+    }
+    float dq[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) dq[d] = 0.f;
+    for (int j = 0; j < N; ++j) {
+      float ds = sp[i * (N + 1) + j] * (sds[i * (N + 1) + j] - delta);
+      sds[i * (N + 1) + j] = ds;
+      atomicAdd(p.dbias + ((size_t)h * N + i) * N + j, ds);
+#pragma unroll
+      for (int d = 0; d < HD; ++d) dq[d] = fmaf(ds, sk[j * 33 + d], dq[d]);
+    }
+    float* dqrow = p.dqkv + ((size_t)b * N + i) * 3 * p.C + h * HD;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) dqrow[d] = dq[d] * p.scale;
+  }
+  __syncthreads();
+  if (i < N) {
+    const int j = i;
+    float dk[HD], dv[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
+    for (int r = 0; r < N; ++r) {
+      float ds = sds[r * (N + 1) + j], pr = sp[r * (N + 1) + j];
+#pragma unroll
+      for (int d = 0; d < HD; ++d) {
+        dk[d] = fmaf(ds, sq[r * 33 + d], dk[d]);
+        dv[d] = fmaf(pr, sdo[r * 33 + d], dv[d]);
+      }
+    }
+    float* row = p.dqkv + ((size_t)b * N + j) * 3 * p.C + h * HD;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) { row[p.C + d] = dk[d] * p.scale; row[2 * p.C + d] = dv[d]; }
+  }
+}
+
+static int attn_simt_common(const swin_attn_args* a, AttnSimtParams* out, bool bwd) {
+  SWIN_REQUIRE(a->B_ >= 0 && a->nH > 0 && a->ws > 0, "attn: bad shape");
+  SWIN_REQUIRE(a->qkv && a->bias && a->lse, "attn: null pointer");
+  SWIN_REQUIRE(a->mask == nullptr || (a->nW > 0 && a->B_ % a->nW == 0), "attn: B_ must be a multiple of nW when a mask is given");
+  if (bwd) SWIN_REQUIRE(a->dout && a->dqkv && a->dbias, "attn_bwd: null pointer");
+  else SWIN_REQUIRE(a->out != nullptr, "attn_fwd: null out");
+  AttnSimtParams p;
+  p.B_ = a->B_; p.nH = a->nH; p.N = a->ws * a->ws; p.nW = a->nW > 0 ? a->nW : 1; p.C = a->nH * HD; p.scale = a->scale;
+  p.qkv = (const float*)a->qkv; p.bias = a->bias; p.mask = a->mask; p.out = (float*)a->out; p.lse = a->lse;
+  p.dout = (const float*)a->dout; p.dqkv = (float*)a->dqkv; p.dbias = a->dbias;
+  *out = p;
+  return 0;
+}
+
+int attn_simt_fwd(const swin_attn_args* a, cudaStream_t st) {
+  AttnSimtParams p;
+  int rc = attn_simt_common(a, &p, false);
+  if (rc) return rc;
+  if (p.B_ == 0) return 0;
+  size_t smem = (size_t)2 * p.N * 33 * sizeof(float);
+  int threads = ceil_div(p.N, 32) * 32;
+  cudaFuncSetAttribute(attn_simt_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  attn_simt_fwd_kernel<<<p.B_ * p.nH, threads, smem, st>>>(p);
+  SWIN_LAUNCH_CHECK();
+  return 0;
+}
+int attn_simt_bwd(const swin_attn_args* a, cudaStream_t st) {
+  AttnSimtParams p;
+  int rc = attn_simt_common(a, &p, true);
+  if (rc) return rc;
+  if (p.B_ == 0) return 0;
+  size_t smem = ((size_t)4 * p.N * 33 + (size_t)2 * p.N * (p.N + 1)) * sizeof(float);
+  SWIN_REQUIRE(smem <= 200 * 1024, "attn_bwd(fp32): window too large for shared memory");
+  int threads = ceil_div(p.N, 32) * 32;
+  cudaFuncSetAttribute(attn_simt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  attn_simt_bwd_kernel<<<p.B_ * p.nH, threads, smem, st>>>(p);
+  SWIN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace swin

@@ -1,0 +1,50 @@
+// C-ABI front door: version / error reporting / device check and dtype dispatch.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace swin {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace swin
+
+using namespace swin;
+
+extern "C" int swin_version(void) { return SWIN_B200_VERSION; }
+extern "C" const char* swin_last_error(void) { return g_err; }
+
+extern "C" int swin_device_check(int device) {
+  int major = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (e != cudaSuccess) { set_error("cudaDeviceGetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  if (major != 10) { set_error("device %d has compute capability %d.x; these kernels are sm_100a only", device, major); return -ENOTSUP; }
+  return 0;
+}
+
+extern "C" int swin_gemm(const swin_gemm_args* a, void* stream) {
+  if (!a) { set_error("gemm: null args"); return -EINVAL; }
+  if (a->dtype == SWIN_F32) return gemm_simt(a, (cudaStream_t)stream);
+  if (a->dtype == SWIN_BF16) return gemm_tc(a, (cudaStream_t)stream);
+  set_error("gemm: bad dtype %d", a->dtype);
+  return -EINVAL;
+}
+extern "C" int swin_window_attn_fwd(const swin_attn_args* a, void* stream) {
+  if (!a) { set_error("attn: null args"); return -EINVAL; }
+  if (a->dtype == SWIN_F32) return attn_simt_fwd(a, (cudaStream_t)stream);
+  if (a->dtype == SWIN_BF16) return attn_tc_fwd(a, (cudaStream_t)stream);
+  set_error("attn: bad dtype %d", a->dtype);
+  return -EINVAL;
+}
+extern "C" int swin_window_attn_bwd(const swin_attn_args* a, void* stream) {
+  if (!a) { set_error("attn: null args"); return -EINVAL; }
+  if (a->dtype == SWIN_F32) return attn_simt_bwd(a, (cudaStream_t)stream);
+  if (a->dtype == SWIN_BF16) return attn_tc_bwd(a, (cudaStream_t)stream);
+  set_error("attn: bad dtype %d", a->dtype);
+  return -EINVAL;
+}

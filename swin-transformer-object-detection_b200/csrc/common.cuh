@@ -1,0 +1,105 @@
+// Shared host/device helpers for the swin_b200 kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/swin_b200.h"
+
+namespace swin {
+
+constexpr int kNumSMs = 148;
+
+void set_error(const char* fmt, ...);
+
+#define SWIN_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::swin::set_error(__VA_ARGS__);  \
+      return -EINVAL;                  \
+    }                                  \
+  } while (0)
+
+#define SWIN_LAUNCH_CHECK()                                                    \
+  do {                                                                         \
+    cudaError_t e__ = cudaGetLastError();                                      \
+    if (e__ != cudaSuccess) {                                                  \
+      ::swin::set_error("%s:%d launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return (int)e__;                                                         \
+    }                                                                          \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Geometry of one stage's window grid (REF:214-231 / :371-372).
+struct WinGeom {
+  int B, H, W, C, ws, shift;
+  int Hp, Wp, nwh, nww, nW, N;
+};
+inline WinGeom make_geom(int B, int H, int W, int C, int ws, int shift) {
+  WinGeom g;
+  g.B = B; g.H = H; g.W = W; g.C = C; g.ws = ws; g.shift = shift;
+  g.nwh = (H + ws - 1) / ws; g.nww = (W + ws - 1) / ws;
+  g.Hp = g.nwh * ws; g.Wp = g.nww * ws;
+  g.nW = g.nwh * g.nww; g.N = ws * ws;
+  return g;
+}
+
+// slot (window-token index inside ONE image, [0, nW*N)) -> source token h*W+w, or -1 for zero padding.
+__host__ __device__ __forceinline__ int slot_to_token(const WinGeom& g, int slot) {
+  int w = slot / g.N, t = slot - w * g.N;
+  int wh = w / g.nww, ww = w - wh * g.nww;
+  int i = t / g.ws, j = t - i * g.ws;
+  int hs = wh * g.ws + i + g.shift; if (hs >= g.Hp) hs -= g.Hp;
+  int wsrc = ww * g.ws + j + g.shift; if (wsrc >= g.Wp) wsrc -= g.Wp;
+  return (hs < g.H && wsrc < g.W) ? hs * g.W + wsrc : -1;
+}
+// token (h*W+w) -> slot inside the image (inverse of the above on valid tokens).
+__host__ __device__ __forceinline__ int token_to_slot(const WinGeom& g, int tok) {
+  int h = tok / g.W, w = tok - h * g.W;
+  int hh = h - g.shift; if (hh < 0) hh += g.Hp;
+  int wq = w - g.shift; if (wq < 0) wq += g.Wp;
+  int wh = hh / g.ws, i = hh - wh * g.ws;
+  int ww = wq / g.ws, j = wq - ww * g.ws;
+  return (wh * g.nww + ww) * g.N + i * g.ws + j;
+}
+
+__device__ __forceinline__ float gelu_erf(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f)); }
+__device__ __forceinline__ float dgelu_erf(float u) {
+  // d/du [u * Phi(u)] = Phi(u) + u * phi(u)
+  float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752440f));
+  float pdf = 0.39894228040143267794f * __expf(-0.5f * u * u);
+  return cdf + u * pdf;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// internal entry points implemented per translation unit
+int gemm_simt(const swin_gemm_args* a, cudaStream_t st);
+int gemm_tc(const swin_gemm_args* a, cudaStream_t st);
+int attn_simt_fwd(const swin_attn_args* a, cudaStream_t st);
+int attn_simt_bwd(const swin_attn_args* a, cudaStream_t st);
+int attn_tc_fwd(const swin_attn_args* a, cudaStream_t st);
+int attn_tc_bwd(const swin_attn_args* a, cudaStream_t st);
+
+}  // namespace swin

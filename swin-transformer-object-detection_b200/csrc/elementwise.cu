@@ -1,0 +1,563 @@
+// HBM-bound kernels of the Swin path: bit-exact index ops (shift / partition / reverse / mask),
+// the LayerNorm family (plain, fused with pad+roll+partition, fused with the PatchMerging gather),
+// casts, column sums and the relative-position-bias expand / reduce.
+// All accesses are 128-bit and coalesced per row; index arithmetic is done once per row.
+#include "common.cuh"
+
+namespace swin {
+
+// ------------------------------------------------------------------------------------------
+// Row copy machinery: a group of L lanes (L = power of two <= 32 dividing the row's 16-byte
+// vector count) moves one row; a warp therefore moves 32/L rows at a time.
+// ------------------------------------------------------------------------------------------
+static inline int lanes_per_row(int vecs_per_row) {
+  int l = 1;
+  while (l < 32 && (vecs_per_row % (l * 2)) == 0) l *= 2;
+  return l;
+}
+
+enum { MAP_PARTITION = 0, MAP_REVERSE = 1, MAP_GATHER = 2, MAP_SCATTER = 3 };
+
+// One launch covers `rows` destination rows; src row index (or -1 => zeros) comes from the map.
+template <int MAP>
+__global__ void __launch_bounds__(256) row_map_copy_kernel(const int4* __restrict__ src, int4* __restrict__ dst,
+                                                           WinGeom g, int vpr, int L, long long rows) {
+  const int groups_per_block = blockDim.x / L;
+  const int gl = threadIdx.x % L;
+  long long row = (long long)blockIdx.x * groups_per_block + threadIdx.x / L;
+  const long long stride = (long long)gridDim.x * groups_per_block;
+  const int per_img_slots = g.nW * g.N;
+  const int per_img_tok = g.H * g.W;
+  for (; row < rows; row += stride) {
+    long long srow;
+    if (MAP == MAP_GATHER) {            // dst = window slots, src = tokens
+      int b = (int)(row / per_img_slots);
+      int t = slot_to_token(g, (int)(row - (long long)b * per_img_slots));
+      srow = t < 0 ? -1 : (long long)b * per_img_tok + t;
+    } else if (MAP == MAP_SCATTER) {    // dst = tokens, src = window slots (always valid)
+      int b = (int)(row / per_img_tok);
+      srow = (long long)b * per_img_slots + token_to_slot(g, (int)(row - (long long)b * per_img_tok));
+    } else if (MAP == MAP_PARTITION) {  // H,W already padded (H==Hp), shift 0
+      int b = (int)(row / per_img_slots);
+      srow = (long long)b * per_img_tok + slot_to_token(g, (int)(row - (long long)b * per_img_slots));
+    } else {                            // MAP_REVERSE
+      int b = (int)(row / per_img_tok);
+      srow = (long long)b * per_img_slots + token_to_slot(g, (int)(row - (long long)b * per_img_tok));
+    }
+    int4* d = dst + row * vpr;
+    if (srow < 0) {
+      for (int v = gl; v < vpr; v += L) d[v] = make_int4(0, 0, 0, 0);
+    } else {
+      const int4* s = src + srow * vpr;
+      for (int v = gl; v < vpr; v += L) d[v] = __ldg(s + v);
+    }
+  }
+}
+
+template <int MAP>
+static int launch_row_map(const void* src, void* dst, const WinGeom& g, int elem_bytes, long long rows, cudaStream_t st) {
+  SWIN_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "elem_bytes must be 2 or 4");
+  SWIN_REQUIRE(((long long)g.C * elem_bytes) % 16 == 0, "row bytes (C*elem) must be a multiple of 16");
+  SWIN_REQUIRE(aligned16(src) && aligned16(dst), "pointers must be 16-byte aligned");
+  SWIN_REQUIRE(g.B > 0 && g.H > 0 && g.W > 0 && g.ws > 0 && g.shift >= 0 && g.shift < g.ws, "bad geometry");
+  if (rows == 0) return 0;
+  int vpr = g.C * elem_bytes / 16;
+  int L = lanes_per_row(vpr);
+  int gpb = 256 / L;
+  long long blocks = (rows + gpb - 1) / gpb;
+  int grid = (int)(blocks < (long long)kNumSMs * 16 ? blocks : (long long)kNumSMs * 16);
+  row_map_copy_kernel<MAP><<<grid, 256, 0, st>>>((const int4*)src, (int4*)dst, g, vpr, L, rows);
+  SWIN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// shift mask (REF:370-389): region ids on the padded grid, in window-frame coordinates.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int region1d(int p, int P, int ws, int shift) { return (p >= P - ws) + (p >= P - shift); }
+
+__global__ void shift_mask_kernel(float* __restrict__ mask, WinGeom g) {
+  long long total = (long long)g.nW * g.N * g.N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int q = (int)(i % g.N);
+    int p = (int)((i / g.N) % g.N);
+    int w = (int)(i / ((long long)g.N * g.N));
+    int wh = w / g.nww, ww = w - wh * g.nww;
+    int rp = 3 * region1d(wh * g.ws + p / g.ws, g.Hp, g.ws, g.shift) + region1d(ww * g.ws + p % g.ws, g.Wp, g.ws, g.shift);
+    int rq = 3 * region1d(wh * g.ws + q / g.ws, g.Hp, g.ws, g.shift) + region1d(ww * g.ws + q % g.ws, g.Wp, g.ws, g.shift);
+    mask[i] = (rp == rq) ? 0.0f : -100.0f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// relative position bias: table ((2ws-1)^2, nH) <-> dense (nH, N, N)   (REF:101-111, :135-137)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int rel_index(int i, int j, int ws) {
+  return (i / ws - j / ws + ws - 1) * (2 * ws - 1) + (i % ws - j % ws + ws - 1);
+}
+__global__ void rel_bias_expand_kernel(const float* __restrict__ table, float* __restrict__ bias, int nH, int ws) {
+  int N = ws * ws;
+  int total = nH * N * N;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    int j = e % N, i = (e / N) % N, h = e / (N * N);
+    bias[e] = table[rel_index(i, j, ws) * nH + h];
+  }
+}
+// one thread per table entry: deterministic gather-sum of every (i,j) that maps to it
+__global__ void rel_bias_reduce_kernel(const float* __restrict__ dbias, float* __restrict__ dtable, int nH, int ws) {
+  int R = 2 * ws - 1;
+  int total = R * R * nH;
+  int N = ws * ws;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    int h = e % nH, r = e / nH;
+    int dr = r / R - (ws - 1), dc = r % R - (ws - 1);   // ri - rj, ci - cj
+    float s = 0.f;
+    for (int rj = 0; rj < ws; ++rj) {
+      int ri = rj + dr;
+      if (ri < 0 || ri >= ws) continue;
+      for (int cj = 0; cj < ws; ++cj) {
+        int ci = cj + dc;
+        if (ci < 0 || ci >= ws) continue;
+        s += dbias[((size_t)h * N + (ri * ws + ci)) * N + (rj * ws + cj)];
+      }
+    }
+    dtable[e] += s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm family.  One warp per LN row; the row is NSEG gathered segments of C floats
+// (NSEG = 1 for plain / window mode, 4 for PatchMerging).  VPL = float4 vectors held per lane.
+// ------------------------------------------------------------------------------------------
+struct LnGeom {
+  WinGeom g;       // window mode
+  int mode;        // 0 plain, 1 window, 2 merge
+  int C;           // segment width
+  int nseg;        // 1 or 4
+  int H2, W2;      // merge
+  long long rows;  // iteration rows (see kernels)
+  float eps;
+};
+
+// merged row (b, oh, ow) segment q -> source token row or -1   (REF:288-292 order (0,0),(1,0),(0,1),(1,1))
+__device__ __forceinline__ long long merge_src(const LnGeom& lg, long long row, int q) {
+  int per = lg.H2 * lg.W2;
+  int b = (int)(row / per), r = (int)(row - (long long)b * per);
+  int oh = r / lg.W2, ow = r - oh * lg.W2;
+  int h = 2 * oh + (q & 1), w = 2 * ow + (q >> 1);
+  return (h < lg.g.H && w < lg.g.W) ? ((long long)b * lg.g.H + h) * lg.g.W + w : -1;
+}
+
+template <typename T> struct Vec4IO;
+template <> struct Vec4IO<float> {
+  static __device__ __forceinline__ float4 ld(const float* p, long long v) { return __ldg(reinterpret_cast<const float4*>(p) + v); }
+  static __device__ __forceinline__ void st(float* p, long long v, float4 x) { reinterpret_cast<float4*>(p)[v] = x; }
+};
+template <> struct Vec4IO<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 ld(const __nv_bfloat16* p, long long v) {
+    uint2 u = __ldg(reinterpret_cast<const uint2*>(p) + v);
+    return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, long long v, float4 x) {
+    reinterpret_cast<uint2*>(p)[v] = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+  }
+};
+
+// Forward.  Iteration rows: mode 0 -> LN rows; mode 1 -> window SLOTS (pad slots get zeros);
+// mode 2 -> merged rows.
+template <int VPL, typename YT>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, YT* __restrict__ y,
+                                                     float* __restrict__ mean, float* __restrict__ rstd, LnGeom lg) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int vps = lg.C >> 2;                 // float4 per segment
+  const int vrow = vps * lg.nseg;            // float4 per LN row
+  const float inv_n = 1.0f / (float)(lg.C * lg.nseg);
+  const int per_img_slots = lg.g.nW * lg.g.N, per_img_tok = lg.g.H * lg.g.W;
+  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < lg.rows; row += (long long)gridDim.x * wpb) {
+    long long stat_row = row;
+    long long src0 = row;
+    if (lg.mode == 1) {
+      int b = (int)(row / per_img_slots);
+      int t = slot_to_token(lg.g, (int)(row - (long long)b * per_img_slots));
+      if (t < 0) {                           // zero padding AFTER the norm (REF:211 then :218)
+        for (int v = lane; v < vrow; v += 32) Vec4IO<YT>::st(y, row * vrow + v, make_float4(0.f, 0.f, 0.f, 0.f));
+        continue;
+      }
+      src0 = (long long)b * per_img_tok + t;
+      stat_row = src0;
+    }
+    float4 r[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      int v = lane + 32 * k;
+      r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v < vrow) {
+        long long srow = src0;
+        int off = v;
+        if (lg.mode == 2) { int q = v / vps; off = v - q * vps; srow = merge_src(lg, row, q); }
+        if (srow >= 0) r[k] = Vec4IO<float>::ld(x, srow * vps + off);
+        s += r[k].x + r[k].y + r[k].z + r[k].w;
+      }
+    }
+    const float mu = warp_sum(s) * inv_n;
+    float q2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      if (lane + 32 * k < vrow) {
+        float a = r[k].x - mu, b2 = r[k].y - mu, c = r[k].z - mu, d = r[k].w - mu;
+        q2 += a * a + b2 * b2 + c * c + d * d;
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q2) * inv_n + lg.eps);
+    if (lane == 0) { mean[stat_row] = mu; rstd[stat_row] = rs; }
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      int v = lane + 32 * k;
+      if (v < vrow) {
+        float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + v);
+        float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + v);
+        float4 o;
+        o.x = (r[k].x - mu) * rs * gm.x + bt.x;
+        o.y = (r[k].y - mu) * rs * gm.y + bt.y;
+        o.z = (r[k].z - mu) * rs * gm.z + bt.z;
+        o.w = (r[k].w - mu) * rs * gm.w + bt.w;
+        Vec4IO<YT>::st(y, row * vrow + v, o);
+      }
+    }
+  }
+}
+
+// Backward.  Iteration rows: mode 0 -> LN rows; mode 1 -> TOKENS (dy read through token->slot);
+// mode 2 -> merged rows (dx scattered to the 4 source tokens; pad segments dropped).
+// dx = (dres) + rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += dy*xhat; dbeta += dy.
+template <int VPL, typename YT>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const YT* __restrict__ dy, const float* __restrict__ x,
+                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, const float* __restrict__ dres,
+                                                     float* __restrict__ dx, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, LnGeom lg) {
+  extern __shared__ float sred[];            // [2][vrow*4] block partials
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int vps = lg.C >> 2;
+  const int vrow = vps * lg.nseg;
+  const int width = vrow * 4;
+  const float inv_n = 1.0f / (float)width;
+  const int per_img_slots = lg.g.nW * lg.g.N, per_img_tok = lg.g.H * lg.g.W;
+  for (int i = threadIdx.x; i < 2 * width; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  float4 ag[VPL], ab[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) { ag[k] = make_float4(0.f, 0.f, 0.f, 0.f); ab[k] = ag[k]; }
+  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < lg.rows; row += (long long)gridDim.x * wpb) {
+    long long dyrow = row;
+    if (lg.mode == 1) {
+      int b = (int)(row / per_img_tok);
+      dyrow = (long long)b * per_img_slots + token_to_slot(lg.g, (int)(row - (long long)b * per_img_tok));
+    }
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[VPL], gd[VPL];
+    long long srow_k[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      int v = lane + 32 * k;
+      xh[k] = make_float4(0.f, 0.f, 0.f, 0.f); gd[k] = xh[k]; srow_k[k] = -1;
+      if (v < vrow) {
+        long long srow = row; int off = v;
+        if (lg.mode == 2) { int q = v / vps; off = v - q * vps; srow = merge_src(lg, row, q); }
+        srow_k[k] = srow < 0 ? -1 : srow * vps + off;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (srow >= 0) xv = Vec4IO<float>::ld(x, srow * vps + off);
+        float4 d = Vec4IO<YT>::ld(dy, dyrow * vrow + v);
+        float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + v);
+        xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        gd[k] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        s1 += gd[k].x + gd[k].y + gd[k].z + gd[k].w;
+        s2 += gd[k].x * xh[k].x + gd[k].y * xh[k].y + gd[k].z * xh[k].z + gd[k].w * xh[k].w;
+        ag[k].x += d.x * xh[k].x; ag[k].y += d.y * xh[k].y; ag[k].z += d.z * xh[k].z; ag[k].w += d.w * xh[k].w;
+        ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
+      }
+    }
+    const float m1 = warp_sum(s1) * inv_n, m2 = warp_sum(s2) * inv_n;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      if (srow_k[k] >= 0) {
+        float4 o;
+        o.x = rs * (gd[k].x - m1 - xh[k].x * m2);
+        o.y = rs * (gd[k].y - m1 - xh[k].y * m2);
+        o.z = rs * (gd[k].z - m1 - xh[k].z * m2);
+        o.w = rs * (gd[k].w - m1 - xh[k].w * m2);
+        if (dres != nullptr) {
+          float4 rr = Vec4IO<float>::ld(dres, srow_k[k]);
+          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        }
+        Vec4IO<float>::st(dx, srow_k[k], o);
+      }
+    }
+  }
+  // block reduce of dgamma / dbeta partials, then one atomic per column per block
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    int v = lane + 32 * k;
+    if (v < vrow) {
+      atomicAdd(&sred[v * 4 + 0], ag[k].x); atomicAdd(&sred[v * 4 + 1], ag[k].y);
+      atomicAdd(&sred[v * 4 + 2], ag[k].z); atomicAdd(&sred[v * 4 + 3], ag[k].w);
+      atomicAdd(&sred[width + v * 4 + 0], ab[k].x); atomicAdd(&sred[width + v * 4 + 1], ab[k].y);
+      atomicAdd(&sred[width + v * 4 + 2], ab[k].z); atomicAdd(&sred[width + v * 4 + 3], ab[k].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < width; i += blockDim.x) {
+    atomicAdd(dgamma + i, sred[i]);
+    atomicAdd(dbeta + i, sred[width + i]);
+  }
+}
+
+static int ln_geom(const swin_ln_args* a, bool bwd, LnGeom* out) {
+  LnGeom lg;
+  SWIN_REQUIRE(a->mode >= 0 && a->mode <= 2, "ln: bad mode %d", a->mode);
+  SWIN_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0 && a->C > 0 && a->C % 4 == 0, "ln: bad shape");
+  int ws = a->mode == 1 ? a->ws : 1, shift = a->mode == 1 ? a->shift : 0;
+  SWIN_REQUIRE(ws > 0 && shift >= 0 && shift < ws, "ln: bad window geometry");
+  lg.g = make_geom(a->B, a->H, a->W, a->C, ws, shift);
+  lg.mode = a->mode; lg.C = a->C; lg.nseg = a->mode == 2 ? 4 : 1;
+  lg.H2 = (a->H + 1) / 2; lg.W2 = (a->W + 1) / 2;
+  lg.eps = a->eps;
+  long long tokens = (long long)a->B * a->H * a->W;
+  if (a->mode == 0) lg.rows = tokens;
+  else if (a->mode == 1) lg.rows = bwd ? tokens : (long long)a->B * lg.g.nW * lg.g.N;
+  else lg.rows = (long long)a->B * lg.H2 * lg.W2;
+  SWIN_REQUIRE(a->y_dtype == SWIN_F32 || (a->y_dtype == SWIN_BF16), "ln: bad y dtype");
+  *out = lg;
+  return 0;
+}
+
+template <typename YT>
+static int ln_fwd_dispatch(const swin_ln_args* a, const LnGeom& lg, cudaStream_t st) {
+  int vrow = lg.C / 4 * lg.nseg;
+  int vpl = ceil_div(vrow, 32);
+  long long blocks = ceil_div64(lg.rows, 8);
+  int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
+#define LN_FWD_CASE(V)                                                                                         \
+  if (vpl <= V) {                                                                                              \
+    ln_fwd_kernel<V, YT><<<grid, 256, 0, st>>>(a->x, a->gamma, a->beta, (YT*)a->y, a->mean, a->rstd, lg);      \
+    SWIN_LAUNCH_CHECK();                                                                                       \
+    return 0;                                                                                                  \
+  }
+  LN_FWD_CASE(1) LN_FWD_CASE(2) LN_FWD_CASE(3) LN_FWD_CASE(4) LN_FWD_CASE(6) LN_FWD_CASE(8)
+  LN_FWD_CASE(12) LN_FWD_CASE(16) LN_FWD_CASE(24) LN_FWD_CASE(32)
+#undef LN_FWD_CASE
+  set_error("ln: row width %d too large", vrow * 4);
+  return -EINVAL;
+}
+
+template <typename YT>
+static int ln_bwd_dispatch(const swin_ln_args* a, const LnGeom& lg, cudaStream_t st) {
+  int vrow = lg.C / 4 * lg.nseg;
+  int vpl = ceil_div(vrow, 32);
+  long long blocks = ceil_div64(lg.rows, 8 * 16);   // each warp walks >= 16 rows so the atomics amortise
+  int grid = (int)(blocks < (long long)kNumSMs * 4 ? blocks : (long long)kNumSMs * 4);
+  if (grid < 1) grid = 1;
+  size_t smem = (size_t)2 * vrow * 4 * sizeof(float);
+#define LN_BWD_CASE(V)                                                                                         \
+  if (vpl <= V) {                                                                                              \
+    ln_bwd_kernel<V, YT><<<grid, 256, smem, st>>>((const YT*)a->dy, a->x, a->gamma, a->mean, a->rstd, a->dres, \
+                                                  a->dx, a->dgamma, a->dbeta, lg);                             \
+    SWIN_LAUNCH_CHECK();                                                                                       \
+    return 0;                                                                                                  \
+  }
+  LN_BWD_CASE(1) LN_BWD_CASE(2) LN_BWD_CASE(3) LN_BWD_CASE(4) LN_BWD_CASE(6) LN_BWD_CASE(8)
+  LN_BWD_CASE(12) LN_BWD_CASE(16) LN_BWD_CASE(24) LN_BWD_CASE(32)
+#undef LN_BWD_CASE
+  set_error("ln: row width %d too large", vrow * 4);
+  return -EINVAL;
+}
+
+// ------------------------------------------------------------------------------------------
+// scale + cast (+ optional gather into window slots): dY of the residual epilogues.
+// ------------------------------------------------------------------------------------------
+template <typename YT>
+__global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict__ x, YT* __restrict__ y,
+                                                         const float* __restrict__ row_scale, int mode, WinGeom g,
+                                                         long long rows) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int vrow = g.C >> 2;
+  const int per_img_slots = g.nW * g.N, per_img_tok = g.H * g.W;
+  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+    long long srow = row;
+    int b;
+    if (mode == 1) {
+      b = (int)(row / per_img_slots);
+      int t = slot_to_token(g, (int)(row - (long long)b * per_img_slots));
+      srow = t < 0 ? -1 : (long long)b * per_img_tok + t;
+    } else {
+      b = (int)(row / per_img_tok);
+    }
+    if (srow < 0) {
+      for (int v = lane; v < vrow; v += 32) Vec4IO<YT>::st(y, row * vrow + v, make_float4(0.f, 0.f, 0.f, 0.f));
+      continue;
+    }
+    const float sc = row_scale ? row_scale[b] : 1.0f;
+    for (int v = lane; v < vrow; v += 32) {
+      float4 t = Vec4IO<float>::ld(x, srow * vrow + v);
+      Vec4IO<YT>::st(y, row * vrow + v, make_float4(t.x * sc, t.y * sc, t.z * sc, t.w * sc));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4,
+                                                        long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long v = i; v < n4; v += stride) Vec4IO<__nv_bfloat16>::st(y, v, Vec4IO<float>::ld(x, v));
+  for (long long e = n4 * 4 + i; e < n; e += stride) y[e] = __float2bfloat16(x[e]);
+}
+
+// ------------------------------------------------------------------------------------------
+// column sums (bias gradients): block = 256 threads = 8 row-lanes x 32 column-vectors(4 wide)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, int M, int N, long long ld, float* __restrict__ out,
+                                                     int rows_per_block) {
+  __shared__ float4 part[8][32];
+  const int cv = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + cv) * 4;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < N) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      float4 v = Vec4IO<T>::ld(X + (long long)r * ld + col, 0);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  part[rl][cv] = acc;
+  __syncthreads();
+  if (rl == 0 && col < N) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { float4 v = part[k][cv]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    atomicAdd(out + col + 0, acc.x); atomicAdd(out + col + 1, acc.y);
+    atomicAdd(out + col + 2, acc.z); atomicAdd(out + col + 3, acc.w);
+  }
+}
+
+}  // namespace swin
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace swin;
+
+extern "C" int swin_window_partition(const void* x, void* win, int B, int Hp, int Wp, int C, int ws, int elem_bytes, void* stream) {
+  SWIN_REQUIRE(ws > 0 && Hp % ws == 0 && Wp % ws == 0, "window_partition: Hp,Wp must be multiples of ws");
+  WinGeom g = make_geom(B, Hp, Wp, C, ws, 0);
+  return launch_row_map<MAP_PARTITION>(x, win, g, elem_bytes, (long long)B * g.nW * g.N, (cudaStream_t)stream);
+}
+extern "C" int swin_window_reverse(const void* win, void* x, int B, int Hp, int Wp, int C, int ws, int elem_bytes, void* stream) {
+  SWIN_REQUIRE(ws > 0 && Hp % ws == 0 && Wp % ws == 0, "window_reverse: Hp,Wp must be multiples of ws");
+  WinGeom g = make_geom(B, Hp, Wp, C, ws, 0);
+  return launch_row_map<MAP_REVERSE>(win, x, g, elem_bytes, (long long)B * Hp * Wp, (cudaStream_t)stream);
+}
+extern "C" int swin_window_gather(const void* x, void* xw, int B, int H, int W, int C, int ws, int shift, int elem_bytes, void* stream) {
+  SWIN_REQUIRE(ws > 0 && shift >= 0 && shift < ws, "window_gather: bad ws/shift");
+  WinGeom g = make_geom(B, H, W, C, ws, shift);
+  return launch_row_map<MAP_GATHER>(x, xw, g, elem_bytes, (long long)B * g.nW * g.N, (cudaStream_t)stream);
+}
+extern "C" int swin_window_scatter(const void* xw, void* x, int B, int H, int W, int C, int ws, int shift, int elem_bytes, void* stream) {
+  SWIN_REQUIRE(ws > 0 && shift >= 0 && shift < ws, "window_scatter: bad ws/shift");
+  WinGeom g = make_geom(B, H, W, C, ws, shift);
+  return launch_row_map<MAP_SCATTER>(xw, x, g, elem_bytes, (long long)B * H * W, (cudaStream_t)stream);
+}
+extern "C" int swin_shift_mask(float* mask, int H, int W, int ws, int shift, void* stream) {
+  SWIN_REQUIRE(H > 0 && W > 0 && ws > 0 && shift >= 0 && shift < ws, "shift_mask: bad geometry");
+  WinGeom g = make_geom(1, H, W, 1, ws, shift);
+  long long total = (long long)g.nW * g.N * g.N;
+  int grid = (int)((total + 255) / 256 < kNumSMs * 8 ? (total + 255) / 256 : kNumSMs * 8);
+  shift_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mask, g);
+  SWIN_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int swin_rel_bias_expand(const float* table, float* bias, int nH, int ws, void* stream) {
+  SWIN_REQUIRE(nH > 0 && ws > 0, "rel_bias_expand: bad shape");
+  int total = nH * ws * ws * ws * ws;
+  rel_bias_expand_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(table, bias, nH, ws);
+  SWIN_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int swin_rel_bias_reduce(const float* dbias, float* dtable, int nH, int ws, void* stream) {
+  SWIN_REQUIRE(nH > 0 && ws > 0, "rel_bias_reduce: bad shape");
+  int total = (2 * ws - 1) * (2 * ws - 1) * nH;
+  rel_bias_reduce_kernel<<<ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(dbias, dtable, nH, ws);
+  SWIN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int swin_ln_fwd(const swin_ln_args* a, void* stream) {
+  LnGeom lg;
+  int rc = ln_geom(a, false, &lg);
+  if (rc) return rc;
+  SWIN_REQUIRE(a->x && a->gamma && a->beta && a->y && a->mean && a->rstd, "ln_fwd: null pointer");
+  SWIN_REQUIRE(aligned16(a->x) && aligned16(a->y) && aligned16(a->gamma) && aligned16(a->beta), "ln_fwd: alignment");
+  if (lg.rows == 0) return 0;
+  if (a->y_dtype == SWIN_F32) return ln_fwd_dispatch<float>(a, lg, (cudaStream_t)stream);
+  return ln_fwd_dispatch<__nv_bfloat16>(a, lg, (cudaStream_t)stream);
+}
+extern "C" int swin_ln_bwd(const swin_ln_args* a, void* stream) {
+  LnGeom lg;
+  int rc = ln_geom(a, true, &lg);
+  if (rc) return rc;
+  SWIN_REQUIRE(a->x && a->gamma && a->dy && a->mean && a->rstd && a->dx && a->dgamma && a->dbeta, "ln_bwd: null pointer");
+  SWIN_REQUIRE(aligned16(a->x) && aligned16(a->dy) && aligned16(a->dx) && aligned16(a->gamma), "ln_bwd: alignment");
+  SWIN_REQUIRE(a->dres == nullptr || aligned16(a->dres), "ln_bwd: alignment");
+  if (lg.rows == 0) return 0;
+  if (a->y_dtype == SWIN_F32) return ln_bwd_dispatch<float>(a, lg, (cudaStream_t)stream);
+  return ln_bwd_dispatch<__nv_bfloat16>(a, lg, (cudaStream_t)stream);
+}
+
+extern "C" int swin_scale_cast(const float* x, void* y, const float* row_scale, int mode, int B, int H, int W, int C, int ws,
+                               int shift, int y_dtype, void* stream) {
+  SWIN_REQUIRE(mode == 0 || mode == 1, "scale_cast: bad mode");
+  SWIN_REQUIRE(C % 4 == 0 && B > 0 && H > 0 && W > 0, "scale_cast: bad shape");
+  SWIN_REQUIRE(aligned16(x) && aligned16(y), "scale_cast: alignment");
+  if (mode == 0) { ws = 1; shift = 0; }
+  SWIN_REQUIRE(ws > 0 && shift >= 0 && shift < ws, "scale_cast: bad window geometry");
+  WinGeom g = make_geom(B, H, W, C, ws, shift);
+  long long rows = mode == 1 ? (long long)B * g.nW * g.N : (long long)B * H * W;
+  long long blocks = ceil_div64(rows, 8);
+  int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
+  if (y_dtype == SWIN_F32) scale_cast_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (float*)y, row_scale, mode, g, rows);
+  else if (y_dtype == SWIN_BF16) scale_cast_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, row_scale, mode, g, rows);
+  else { set_error("scale_cast: bad dtype"); return -EINVAL; }
+  SWIN_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int swin_cast_bf16(const float* x, void* y, int64_t n, void* stream) {
+  SWIN_REQUIRE(n >= 0 && aligned16(x) && aligned16(y), "cast_bf16: alignment");
+  if (n == 0) return 0;
+  long long n4 = n / 4;
+  long long blocks = ceil_div64(n4 > 0 ? n4 : 1, 256);
+  int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
+  cast_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n4, n);
+  SWIN_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int swin_colsum(const void* X, int M, int N, int64_t ld, int dtype, float* colsum, void* stream) {
+  SWIN_REQUIRE(M >= 0 && N > 0 && N % 4 == 0 && ld >= N && ld % 4 == 0, "colsum: bad shape");
+  SWIN_REQUIRE(aligned16(X) && aligned16(colsum), "colsum: alignment");
+  if (M == 0) return 0;
+  int gx = ceil_div(N, 128);
+  int target_y = ceil_div(kNumSMs * 4, gx);
+  int rpb = ceil_div(M, target_y);
+  if (rpb < 64) rpb = 64;
+  dim3 grid(gx, ceil_div(M, rpb));
+  if (dtype == SWIN_F32) colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)X, M, N, ld, colsum, rpb);
+  else if (dtype == SWIN_BF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)X, M, N, ld, colsum, rpb);
+  else { set_error("colsum: bad dtype"); return -EINVAL; }
+  SWIN_LAUNCH_CHECK();
+  return 0;
+}

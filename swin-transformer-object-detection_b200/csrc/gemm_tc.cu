@@ -1,0 +1,222 @@
+// bf16 GEMM on the 5th-generation tensor cores: persistent, warp-specialised
+//   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring)
+//   warp 1      MMA issuer     (one thread, tcgen05.mma kind::f16, fp32 accumulators in TMEM)
+//   warps 2..5  epilogue       (tcgen05.ld -> fused epilogue -> global), overlapped with the next
+//                               tile's main loop through two TMEM accumulator stages.
+// Operands may be K-major or MN-major ("transposed") so forward (X W^T), dX (dY W) and the
+// split-K weight gradient (dY^T X) all run on the same kernel.
+#include "epilogue.cuh"
+#include "ptx.cuh"
+#include "tma_host.cuh"
+
+namespace swin {
+
+constexpr int TBM = 128, TBK = 64;
+constexpr int kGemmThreads = 192;
+constexpr int kMaxStages = 8;
+
+struct GemmTcParams {
+  int block_n;            // MMA N (multiple of 32, <= 256)
+  int n_tiles, m_tiles, splits, kb_total, kb_per_split;
+  int stages;
+  uint32_t a_bytes, b_bytes;   // per stage
+  EpiParams epi;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmB, GemmTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  // 1024-byte aligned operand ring
+  uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&bars[kMaxStages + s]); };
+  auto tfull_bar = [&](int s) { return smem_u32(&bars[2 * kMaxStages + s]); };
+  auto tempty_bar = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 2 + s]); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_slot), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int total_units = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int ks = unit % p.splits;
+        const int tile = unit / p.splits;
+        const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int m0 = m_blk * TBM, n0 = n_blk * p.block_n;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), stage_bytes);
+          const uint32_t sa = smem0 + s * stage_bytes, sb = sa + p.a_bytes;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, full_bar(s), kb * TBK, m0);
+          } else {
+            tma_load_2d(sa, &tmA, full_bar(s), m0, kb * TBK);
+            tma_load_2d(sa + 8192, &tmA, full_bar(s), m0 + 64, kb * TBK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, full_bar(s), kb * TBK, n0);
+          } else {
+            for (uint32_t b = 0; b * 8192 < p.b_bytes; ++b) tma_load_2d(sb + b * 8192, &tmB, full_bar(s), n0 + 64 * b, kb * TBK);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(p.block_n, A_MN, B_MN);
+      uint32_t it = 0, u = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++u) {
+        const int ks = unit % p.splits;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const uint32_t acc = u & 1, acc_ph = (u >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem0 + s * stage_bytes, sb = sa + p.a_bytes;
+#pragma unroll
+          for (int k = 0; k < TBK / 16; ++k) {
+            const uint64_t ad = A_MN ? umma_desc(sa + k * 2048, 8192, 1024, kSw128) : umma_desc(sa + k * 32, 16, 1024, kSw128);
+            const uint64_t bd = B_MN ? umma_desc(sb + k * 2048, 8192, 1024, kSw128) : umma_desc(sb + k * 32, 16, 1024, kSw128);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));          // smem slot reusable once these MMAs retire
+        }
+        umma_commit(tfull_bar(acc));          // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue (4 warps = 128 TMEM lanes)
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    uint32_t u = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++u) {
+      const int tile = unit / p.splits;
+      const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
+      const int row = m_blk * TBM + q * 32 + lane;
+      const int n0 = n_blk * p.block_n;
+      const uint32_t acc = u & 1, acc_ph = (u >> 1) & 1;
+      long long drow = 0; float scale = 1.f;
+      const bool live = epi_row_setup(p.epi, row, &drow, &scale);
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+      for (int c = 0; c < p.block_n; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        if (live) epilogue_cols<32>(p.epi, row, drow, scale, n0 + c, reinterpret_cast<const float*>(v));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+static int pick_block_n(int N) {
+  const int cand[] = {256, 192, 128, 96, 64, 32};
+  for (int c : cand) if (N % c == 0) return c;
+  return 0;
+}
+
+int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
+  EpiParams ep;
+  int rc = make_epi_params(a, &ep);
+  if (rc) return rc;
+  SWIN_REQUIRE(a->A && a->B, "gemm: null operand");
+  SWIN_REQUIRE(a->N % 32 == 0, "gemm(bf16): N must be a multiple of 32 (got %d)", a->N);
+  SWIN_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "gemm(bf16): lda/ldb must be multiples of 8");
+  if (a->M == 0) return 0;
+  const bool a_mn = a->a_trans != 0, b_mn = a->b_trans != 0;
+  GemmTcParams p;
+  p.epi = ep;
+  p.block_n = pick_block_n(a->N);
+  SWIN_REQUIRE(p.block_n > 0, "gemm(bf16): unsupported N %d", a->N);
+  p.m_tiles = ceil_div(a->M, TBM);
+  p.n_tiles = a->N / p.block_n;
+  p.kb_total = ceil_div(a->K, TBK);
+  p.splits = 1;
+  if (a->epilogue == SWIN_EPI_ATOMIC_ADD) {
+    int tiles = p.m_tiles * p.n_tiles;
+    p.splits = ceil_div(2 * kNumSMs, tiles);
+    int maxs = ceil_div(p.kb_total, 4);
+    if (p.splits > maxs) p.splits = maxs;
+    if (p.splits < 1) p.splits = 1;
+  }
+  p.kb_per_split = ceil_div(p.kb_total, p.splits);
+  p.splits = ceil_div(p.kb_total, p.kb_per_split);
+  p.a_bytes = TBM * TBK * 2;
+  const int bn_rows = b_mn ? ceil_div(p.block_n, 64) * 64 : p.block_n;
+  p.b_bytes = (uint32_t)bn_rows * TBK * 2;
+  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+  const uint32_t budget = 200 * 1024;
+  p.stages = (int)(budget / stage_bytes);
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  SWIN_REQUIRE(p.stages >= 2, "gemm(bf16): tile does not fit in shared memory");
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+
+  CUtensorMap tmA, tmB;
+  if (!a_mn) rc = make_tmap_bf16_2d(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, TBK, TBM, CU_TENSOR_MAP_SWIZZLE_128B);
+  else       rc = make_tmap_bf16_2d(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda * 2, 64, TBK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  if (!b_mn) rc = make_tmap_bf16_2d(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb * 2, TBK, (uint32_t)p.block_n, CU_TENSOR_MAP_SWIZZLE_128B);
+  else       rc = make_tmap_bf16_2d(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, 64, TBK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+
+  const int total_units = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = total_units < kNumSMs ? total_units : kNumSMs;
+#define LAUNCH_TC(AM, BM)                                                                                         \
+  do {                                                                                                            \
+    static bool attr_done = false;                                                                                \
+    if (!attr_done) {                                                                                             \
+      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AM, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); \
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }      \
+      attr_done = true;                                                                                           \
+    }                                                                                                             \
+    gemm_tc_kernel<AM, BM><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);                                        \
+  } while (0)
+  if (!a_mn && !b_mn) LAUNCH_TC(false, false);
+  else if (!a_mn && b_mn) LAUNCH_TC(false, true);
+  else if (a_mn && b_mn) LAUNCH_TC(true, true);
+  else LAUNCH_TC(true, false);
+#undef LAUNCH_TC
+  SWIN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace swin

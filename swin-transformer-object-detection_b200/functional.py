@@ -1,0 +1,174 @@
+"""autograd.Functions that chain the sm_100a kernels into the reference's operators.
+
+Each Function is one reference operator (forward + hand-written backward):
+  SwinBlockFn        SwinTransformerBlock.forward   mmdet/models/backbones/swin_transformer.py:198-255
+  WindowAttentionFn  WindowAttention.forward        :121-153
+  PatchMergingFn     PatchMerging.forward           :271-298
+Gradients of parameters are RETURNED (not accumulated in place) so AccumulateGrad hooks — and
+therefore the bucketed NCCL all-reduce in ddp.py — fire per parameter during backward.
+
+Precision modes (``dt``): F32 = everything fp32 on the FFMA kernels (<=1e-4 parity mode);
+BF16 = bf16 GEMM/attention operands on tcgen05 with fp32 accumulation, fp32 residual stream,
+fp32 LayerNorm / softmax statistics and fp32 master weights (the reference's AMP semantics).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+_W16 = {}
+
+
+def _w(param: torch.Tensor, dt: int) -> torch.Tensor:
+    """Operand copy of a weight in the compute dtype; bf16 shadow copies are cached per parameter version."""
+    if dt == L.F32:
+        return param.detach()
+    key = (param.data_ptr(), tuple(param.shape))
+    hit = _W16.get(key)
+    ver = param._version
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    w16 = ops.cast_bf16(param.detach().contiguous())
+    _W16[key] = (ver, w16)
+    return w16
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class SwinBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, table, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b, mask, s1, s2,
+                H, W, ws, shift, nH, scale, dt, eps):
+        B, Lx, Cc = x.shape
+        x = _f32c(x)
+        geom = (H, W, ws, shift)
+        hid = fc1w.shape[0]
+        T = B * Lx
+        # attention branch: LN1 + pad/roll/partition -> qkv -> window attention -> proj + reverse/roll/crop + residual
+        xw, mean1, rstd1 = ops.ln_fwd(1, x, n1w.detach(), n1b.detach(), B, H, W, Cc, ws, shift, eps, dt)
+        Tp = xw.shape[0] * xw.shape[1]
+        qkv = ops.gemm(xw, _w(qkvw, dt), Tp, 3 * Cc, Cc, bias=None if qkvb is None else qkvb.detach())
+        bias = ops.rel_bias_expand(table.detach().contiguous(), ws)
+        o, lse = ops.window_attn_fwd(qkv.view(-1, ws * ws, 3 * Cc), bias, mask, Tp // (ws * ws), nH, ws, scale)
+        x1 = torch.empty_like(x)
+        ops.gemm(o, _w(projw, dt), Tp, Cc, Cc, bias=projb.detach(), epilogue=L.EPI_SCATTER_RESIDUAL, out=x1, aux=x,
+                 row_scale=s1, geom=geom)
+        # MLP branch: LN2 -> fc1 + GELU -> fc2 + residual
+        xn, mean2, rstd2 = ops.ln_fwd(0, x1, n2w.detach(), n2b.detach(), B, H, W, Cc, 1, 0, eps, dt)
+        u = torch.empty((T, hid), dtype=xn.dtype, device=x.device)
+        h = ops.gemm(xn, _w(fc1w, dt), T, hid, Cc, bias=fc1b.detach(), epilogue=L.EPI_GELU, out2=u)
+        x2 = torch.empty_like(x)
+        ops.gemm(h, _w(fc2w, dt), T, Cc, hid, bias=fc2b.detach(), epilogue=L.EPI_RESIDUAL, out=x2, aux=x1, row_scale=s2,
+                 rows_per_image=Lx)
+        ctx.save_for_backward(x, n1w, table, qkvw, projw, n2w, fc1w, fc2w, mask, s1, s2,
+                              xw, mean1, rstd1, qkv, bias, o, lse, x1, xn, mean2, rstd2, u, h)
+        ctx.cfg = (B, H, W, Cc, ws, shift, nH, scale, dt, hid, qkvb is not None)
+        return x2
+
+    @staticmethod
+    def backward(ctx, dx2):
+        (x, n1w, table, qkvw, projw, n2w, fc1w, fc2w, mask, s1, s2,
+         xw, mean1, rstd1, qkv, bias, o, lse, x1, xn, mean2, rstd2, u, h) = ctx.saved_tensors
+        B, H, W, Cc, ws, shift, nH, scale, dt, hid, has_qkvb = ctx.cfg
+        T = B * H * W
+        N = ws * ws
+        Tp = xw.shape[0] * N
+        dx2 = _f32c(dx2)
+        # ---- MLP branch
+        dy2 = ops.scale_cast(dx2, s2, 0, B, H, W, Cc, 1, 0, dt)                         # (T, C)
+        dfc2b = ops.colsum(dy2)
+        dfc2w = torch.zeros_like(fc2w, dtype=torch.float32)
+        ops.gemm(dy2, h, Cc, hid, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc2w)
+        du = ops.gemm(dy2, _w(fc2w, dt), T, hid, Cc, b_trans=True, epilogue=L.EPI_DGELU, aux=u)
+        dfc1b = ops.colsum(du)
+        dfc1w = torch.zeros_like(fc1w, dtype=torch.float32)
+        ops.gemm(du, xn, hid, Cc, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc1w)
+        dxn = ops.gemm(du, _w(fc1w, dt), T, Cc, hid, b_trans=True)
+        dx1, dn2w, dn2b = ops.ln_bwd(0, dxn, x1, n2w.detach(), mean2, rstd2, dx2, B, H, W, Cc, 1, 0)
+        # ---- attention branch
+        dy1 = ops.scale_cast(dx1, s1, 1, B, H, W, Cc, ws, shift, dt)                    # (Tp, C), pad slots 0
+        dprojb = ops.colsum(dy1)
+        dprojw = torch.zeros_like(projw, dtype=torch.float32)
+        ops.gemm(dy1, o, Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dprojw)
+        do = ops.gemm(dy1, _w(projw, dt), Tp, Cc, Cc, b_trans=True)
+        dqkv, dbias = ops.window_attn_bwd(qkv.view(-1, N, 3 * Cc), o, do.view(-1, N, Cc), lse, bias, mask, Tp // N, nH, ws, scale)
+        dtable = ops.rel_bias_reduce(dbias, ws)
+        dqkvb = ops.colsum(dqkv) if has_qkvb else None
+        dqkvw = torch.zeros_like(qkvw, dtype=torch.float32)
+        ops.gemm(dqkv, xw, 3 * Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dqkvw)
+        dxw = ops.gemm(dqkv.view(Tp, 3 * Cc), _w(qkvw, dt), Tp, Cc, 3 * Cc, b_trans=True)
+        dx, dn1w, dn1b = ops.ln_bwd(1, dxw, x, n1w.detach(), mean1, rstd1, dx1, B, H, W, Cc, ws, shift)
+        return (dx, dn1w, dn1b, dtable, dqkvw, dqkvb, dprojw, dprojb, dn2w, dn2b, dfc1w, dfc1b, dfc2w, dfc2b,
+                None, None, None, None, None, None, None, None, None, None, None)
+
+
+class WindowAttentionFn(torch.autograd.Function):
+    """x_windows (B_, N, C) -> (B_, N, C): qkv Linear, attention core, proj Linear."""
+
+    @staticmethod
+    def forward(ctx, xwin, table, qkvw, qkvb, projw, projb, mask, ws, nH, scale, dt):
+        B_, N, Cc = xwin.shape
+        rows = B_ * N
+        xin = _f32c(xwin)
+        xw = xin if dt == L.F32 else ops.scale_cast(xin, None, 0, 1, rows, 1, Cc, 1, 0, dt)
+        xw = xw.view(rows, Cc)
+        qkv = ops.gemm(xw, _w(qkvw, dt), rows, 3 * Cc, Cc, bias=None if qkvb is None else qkvb.detach())
+        bias = ops.rel_bias_expand(table.detach().contiguous(), ws)
+        o, lse = ops.window_attn_fwd(qkv.view(B_, N, 3 * Cc), bias, mask, B_, nH, ws, scale)
+        y = ops.gemm(o.view(rows, Cc), _w(projw, dt), rows, Cc, Cc, bias=projb.detach(), out_dtype=L.F32)
+        ctx.save_for_backward(table, qkvw, projw, mask, xw, qkv, bias, o, lse)
+        ctx.cfg = (B_, N, Cc, ws, nH, scale, dt, qkvb is not None, xwin.dtype)
+        return y.view(B_, N, Cc).to(xwin.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        table, qkvw, projw, mask, xw, qkv, bias, o, lse = ctx.saved_tensors
+        B_, N, Cc, ws, nH, scale, dt, has_qkvb, in_dtype = ctx.cfg
+        rows = B_ * N
+        dyf = _f32c(dy)
+        dy1 = dyf.view(rows, Cc) if dt == L.F32 else ops.scale_cast(dyf, None, 0, 1, rows, 1, Cc, 1, 0, dt)
+        dprojb = ops.colsum(dy1)
+        dprojw = torch.zeros_like(projw, dtype=torch.float32)
+        ops.gemm(dy1, o.view(rows, Cc), Cc, Cc, rows, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dprojw)
+        do = ops.gemm(dy1, _w(projw, dt), rows, Cc, Cc, b_trans=True)
+        dqkv, dbias = ops.window_attn_bwd(qkv.view(B_, N, 3 * Cc), o, do.view(B_, N, Cc), lse, bias, mask, B_, nH, ws, scale)
+        dtable = ops.rel_bias_reduce(dbias, ws)
+        dqkvb = ops.colsum(dqkv) if has_qkvb else None
+        dqkvw = torch.zeros_like(qkvw, dtype=torch.float32)
+        ops.gemm(dqkv.view(rows, 3 * Cc), xw, 3 * Cc, Cc, rows, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dqkvw)
+        dx = ops.gemm(dqkv.view(rows, 3 * Cc), _w(qkvw, dt), rows, Cc, 3 * Cc, b_trans=True, out_dtype=L.F32)
+        return dx.view(B_, N, Cc).to(in_dtype), dtable, dqkvw, dqkvb, dprojw, dprojb, None, None, None, None, None
+
+
+class PatchMergingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, nw, nb, redw, H, W, dt, eps):
+        B, Lx, Cc = x.shape
+        x = _f32c(x)
+        g, mean, rstd = ops.ln_fwd(2, x, nw.detach(), nb.detach(), B, H, W, Cc, 1, 0, eps, dt)
+        T2 = g.shape[0] * g.shape[1]
+        y = ops.gemm(g.view(T2, 4 * Cc), _w(redw, dt), T2, 2 * Cc, 4 * Cc, out_dtype=L.F32)
+        ctx.save_for_backward(x, nw, redw, g, mean, rstd)
+        ctx.cfg = (B, H, W, Cc, dt, T2)
+        return y.view(B, g.shape[1], 2 * Cc)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, nw, redw, g, mean, rstd = ctx.saved_tensors
+        B, H, W, Cc, dt, T2 = ctx.cfg
+        dyf = _f32c(dy).view(T2, 2 * Cc)
+        dy1 = dyf if dt == L.F32 else ops.scale_cast(dyf, None, 0, 1, T2, 1, 2 * Cc, 1, 0, dt)
+        dredw = torch.zeros_like(redw, dtype=torch.float32)
+        ops.gemm(dy1, g.view(T2, 4 * Cc), 2 * Cc, 4 * Cc, T2, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dredw)
+        dg = ops.gemm(dy1, _w(redw, dt), T2, 4 * Cc, 2 * Cc, b_trans=True)
+        dx, dnw, dnb = ops.ln_bwd(2, dg, x, nw.detach(), mean, rstd, None, B, H, W, Cc, 1, 0)
+        return dx, dnw, dnb, dredw, None, None, None, None

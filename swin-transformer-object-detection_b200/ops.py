@@ -1,0 +1,254 @@
+"""Tensor-level wrappers over the C ABI (device pointers in, device pointers out).
+
+PyTorch is plumbing here: it owns the buffers (caching allocator) and the stream; every
+arithmetic step is a kernel from libswin_b200.so.  All wrappers raise RuntimeError on failure
+and refuse non-CUDA tensors — there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+
+# ------------------------------------------------------------------ instrumentation (bench.py)
+LAUNCHES = 0          # kernels of libswin_b200.so enqueued by this process
+_TIMER = None         # optional object with .begin(kind, flops, bytes) / .end()
+
+
+def set_kernel_timer(timer) -> None:
+    """bench.py installs a CUDA-event timer around the dominant kernel class; None disables."""
+    global _TIMER
+    _TIMER = timer
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("swin_b200 ops need CUDA tensors (no CPU fallback exists)")
+        if not t.is_contiguous():
+            raise RuntimeError("swin_b200 ops need contiguous tensors")
+
+
+def torch_dtype(code: int) -> torch.dtype:
+    return torch.float32 if code == L.F32 else torch.bfloat16
+
+
+def padded_hw(H: int, W: int, ws: int) -> Tuple[int, int]:
+    return -(-H // ws) * ws, -(-W // ws) * ws
+
+
+# ------------------------------------------------------------------ index ops (a1-a5)
+def window_partition(x: torch.Tensor, ws: int) -> torch.Tensor:
+    _chk(x)
+    B, Hp, Wp, Cc = x.shape
+    out = torch.empty((B * (Hp // ws) * (Wp // ws), ws, ws, Cc), dtype=x.dtype, device=x.device)
+    _count()
+    L.check(L.lib().swin_window_partition(_p(x), _p(out), B, Hp, Wp, Cc, ws, x.element_size(), _stream()), "window_partition")
+    return out
+
+
+def window_reverse(win: torch.Tensor, ws: int, Hp: int, Wp: int) -> torch.Tensor:
+    _chk(win)
+    Cc = win.shape[-1]
+    nW = (Hp // ws) * (Wp // ws)
+    B = win.shape[0] // nW
+    out = torch.empty((B, Hp, Wp, Cc), dtype=win.dtype, device=win.device)
+    _count()
+    L.check(L.lib().swin_window_reverse(_p(win), _p(out), B, Hp, Wp, Cc, ws, win.element_size(), _stream()), "window_reverse")
+    return out
+
+
+def window_gather(x: torch.Tensor, H: int, W: int, ws: int, shift: int) -> torch.Tensor:
+    """(B, H*W, C) -> (B*nW, ws*ws, C): pad + roll(-shift) + partition."""
+    _chk(x)
+    B, Lx, Cc = x.shape
+    assert Lx == H * W
+    Hp, Wp = padded_hw(H, W, ws)
+    out = torch.empty((B * (Hp // ws) * (Wp // ws), ws * ws, Cc), dtype=x.dtype, device=x.device)
+    _count()
+    L.check(L.lib().swin_window_gather(_p(x), _p(out), B, H, W, Cc, ws, shift, x.element_size(), _stream()), "window_gather")
+    return out
+
+
+def window_scatter(xw: torch.Tensor, B: int, H: int, W: int, ws: int, shift: int) -> torch.Tensor:
+    """(B*nW, ws*ws, C) -> (B, H*W, C): reverse + roll(+shift) + crop."""
+    _chk(xw)
+    Cc = xw.shape[-1]
+    out = torch.empty((B, H * W, Cc), dtype=xw.dtype, device=xw.device)
+    _count()
+    L.check(L.lib().swin_window_scatter(_p(xw), _p(out), B, H, W, Cc, ws, shift, xw.element_size(), _stream()), "window_scatter")
+    return out
+
+
+def shift_mask(H: int, W: int, ws: int, shift: int, device) -> torch.Tensor:
+    Hp, Wp = padded_hw(H, W, ws)
+    nW, N = (Hp // ws) * (Wp // ws), ws * ws
+    out = torch.empty((nW, N, N), dtype=torch.float32, device=device)
+    _count()
+    L.check(L.lib().swin_shift_mask(_p(out), H, W, ws, shift, _stream()), "shift_mask")
+    return out
+
+
+def rel_bias_expand(table: torch.Tensor, ws: int) -> torch.Tensor:
+    _chk(table)
+    nH = table.shape[1]
+    out = torch.empty((nH, ws * ws, ws * ws), dtype=torch.float32, device=table.device)
+    _count()
+    L.check(L.lib().swin_rel_bias_expand(_p(table), _p(out), nH, ws, _stream()), "rel_bias_expand")
+    return out
+
+
+def rel_bias_reduce(dbias: torch.Tensor, ws: int) -> torch.Tensor:
+    _chk(dbias)
+    nH = dbias.shape[0]
+    out = torch.zeros(((2 * ws - 1) ** 2, nH), dtype=torch.float32, device=dbias.device)
+    _count()
+    L.check(L.lib().swin_rel_bias_reduce(_p(dbias), _p(out), nH, ws, _stream()), "rel_bias_reduce")
+    return out
+
+
+# ------------------------------------------------------------------ LayerNorm family
+def ln_fwd(mode: int, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, B: int, H: int, W: int, Cc: int,
+           ws: int, shift: int, eps: float, y_dtype: int):
+    """Returns (y, mean, rstd).  mode 0 plain (rows=B*H*W), 1 LN+window gather, 2 PatchMerging gather+LN(4C)."""
+    _chk(x, gamma, beta)
+    assert x.dtype == torch.float32 and gamma.dtype == torch.float32
+    dev = x.device
+    if mode == 0:
+        yshape, nstat = (B * H * W, Cc), B * H * W
+    elif mode == 1:
+        Hp, Wp = padded_hw(H, W, ws)
+        yshape, nstat = (B * (Hp // ws) * (Wp // ws), ws * ws, Cc), B * H * W
+    else:
+        H2, W2 = (H + 1) // 2, (W + 1) // 2
+        yshape, nstat = (B, H2 * W2, 4 * Cc), B * H2 * W2
+    y = torch.empty(yshape, dtype=torch_dtype(y_dtype), device=dev)
+    mean = torch.empty((nstat,), dtype=torch.float32, device=dev)
+    rstd = torch.empty((nstat,), dtype=torch.float32, device=dev)
+    a = L.LnArgs(mode=mode, B=B, H=H, W=W, C=Cc, ws=ws, shift=shift, eps=eps, y_dtype=y_dtype, x=_p(x), gamma=_p(gamma),
+                 beta=_p(beta), y=_p(y), mean=_p(mean), rstd=_p(rstd))
+    _count()
+    L.check(L.lib().swin_ln_fwd(C.byref(a), _stream()), "ln_fwd")
+    return y, mean, rstd
+
+
+def ln_bwd(mode: int, dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor,
+           dres: Optional[torch.Tensor], B: int, H: int, W: int, Cc: int, ws: int, shift: int):
+    """Returns (dx fp32 like x, dgamma, dbeta)."""
+    _chk(dy, x, gamma, mean, rstd, dres)
+    dx = torch.empty_like(x)
+    width = Cc * (4 if mode == 2 else 1)
+    dgb = torch.zeros((2, width), dtype=torch.float32, device=x.device)
+    a = L.LnArgs(mode=mode, B=B, H=H, W=W, C=Cc, ws=ws, shift=shift, eps=0.0, y_dtype=_DT[dy.dtype], x=_p(x), gamma=_p(gamma),
+                 mean=_p(mean), rstd=_p(rstd), dy=_p(dy), dres=_p(dres), dx=_p(dx), dgamma=_p(dgb[0]), dbeta=_p(dgb[1]))
+    _count()
+    L.check(L.lib().swin_ln_bwd(C.byref(a), _stream()), "ln_bwd")
+    return dx, dgb[0], dgb[1]
+
+
+# ------------------------------------------------------------------ GEMM
+def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_trans: bool = False, b_trans: bool = False,
+         epilogue: int = L.EPI_STORE, bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         out_dtype: Optional[int] = None, out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
+         row_scale: Optional[torch.Tensor] = None, rows_per_image: int = 0, geom=(0, 0, 0, 0),
+         out_rows: Optional[int] = None) -> torch.Tensor:
+    """acc = A(M,K) . B(N,K)^T with a fused epilogue; see include/swin_b200.h."""
+    _chk(A, Bm, bias, out, out2, aux, row_scale)
+    dt = _DT[A.dtype]
+    assert Bm.dtype == A.dtype
+    if out is None:
+        od = dt if out_dtype is None else out_dtype
+        out = torch.empty((M if out_rows is None else out_rows, N), dtype=torch_dtype(od), device=A.device)
+    a = L.GemmArgs(dtype=dt, M=M, N=N, K=K, A=_p(A), a_trans=int(a_trans), lda=A.stride(-2) if A.dim() >= 2 else K,
+                   B=_p(Bm), b_trans=int(b_trans), ldb=Bm.stride(-2), epilogue=epilogue, bias=_p(bias), D=_p(out),
+                   d_dtype=_DT[out.dtype], ldd=N, D2=_p(out2), aux=_p(aux), row_scale=_p(row_scale),
+                   rows_per_image=rows_per_image, H=geom[0], W=geom[1], ws=geom[2], shift=geom[3])
+    _count()
+    if _TIMER is not None and dt == L.BF16:
+        _TIMER.begin("gemm_tc", 2.0 * M * N * K)
+        L.check(L.lib().swin_gemm(C.byref(a), _stream()), "gemm")
+        _TIMER.end()
+    else:
+        L.check(L.lib().swin_gemm(C.byref(a), _stream()), "gemm")
+    return out
+
+
+def colsum(X: torch.Tensor) -> torch.Tensor:
+    _chk(X)
+    X2 = X.reshape(-1, X.shape[-1])
+    out = torch.zeros((X2.shape[1],), dtype=torch.float32, device=X.device)
+    _count()
+    L.check(L.lib().swin_colsum(_p(X2), X2.shape[0], X2.shape[1], X2.shape[1], _DT[X.dtype], _p(out), _stream()), "colsum")
+    return out
+
+
+def scale_cast(x: torch.Tensor, row_scale: Optional[torch.Tensor], mode: int, B: int, H: int, W: int, Cc: int, ws: int,
+               shift: int, y_dtype: int) -> torch.Tensor:
+    _chk(x, row_scale)
+    assert x.dtype == torch.float32
+    if mode == 1:
+        Hp, Wp = padded_hw(H, W, ws)
+        rows = B * (Hp // ws) * (Wp // ws) * ws * ws
+    else:
+        rows = B * H * W
+    y = torch.empty((rows, Cc), dtype=torch_dtype(y_dtype), device=x.device)
+    _count()
+    L.check(L.lib().swin_scale_cast(_p(x), _p(y), _p(row_scale), mode, B, H, W, Cc, ws, shift, y_dtype, _stream()), "scale_cast")
+    return y
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _chk(x)
+    assert x.dtype == torch.float32
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _count()
+    L.check(L.lib().swin_cast_bf16(_p(x), _p(y), x.numel(), _stream()), "cast_bf16")
+    return y
+
+
+# ------------------------------------------------------------------ window attention core
+def window_attn_fwd(qkv: torch.Tensor, bias: torch.Tensor, mask: Optional[torch.Tensor], B_: int, nH: int, ws: int,
+                    scale: float):
+    _chk(qkv, bias, mask)
+    N, Cc = ws * ws, nH * 32
+    out = torch.empty((B_, N, Cc), dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty((B_, nH, N), dtype=torch.float32, device=qkv.device)
+    a = L.AttnArgs(dtype=_DT[qkv.dtype], B_=B_, nH=nH, ws=ws, nW=0 if mask is None else mask.shape[0], scale=scale,
+                   qkv=_p(qkv), bias=_p(bias), mask=_p(mask), out=_p(out), lse=_p(lse))
+    _count()
+    L.check(L.lib().swin_window_attn_fwd(C.byref(a), _stream()), "window_attn_fwd")
+    return out, lse
+
+
+def window_attn_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, bias: torch.Tensor,
+                    mask: Optional[torch.Tensor], B_: int, nH: int, ws: int, scale: float):
+    _chk(qkv, out, dout, lse, bias, mask)
+    N = ws * ws
+    dqkv = torch.empty_like(qkv)
+    dbias = torch.zeros((nH, N, N), dtype=torch.float32, device=qkv.device)
+    a = L.AttnArgs(dtype=_DT[qkv.dtype], B_=B_, nH=nH, ws=ws, nW=0 if mask is None else mask.shape[0], scale=scale,
+                   qkv=_p(qkv), bias=_p(bias), mask=_p(mask), out=_p(out), lse=_p(lse), dout=_p(dout), dqkv=_p(dqkv),
+                   dbias=_p(dbias))
+    _count()
+    L.check(L.lib().swin_window_attn_bwd(C.byref(a), _stream()), "window_attn_bwd")
+    return dqkv, dbias

@@ -1,0 +1,359 @@
+"""Host-side mirror of the reference's Swin backbone interface, running on the sm_100a kernels.
+
+Same class names, constructor arguments, ``forward`` signatures, sub-module names and
+``state_dict`` keys as ``mmdet/models/backbones/swin_transformer.py`` (cited as REF:line), so
+reference checkpoints load unchanged and every ``configs/swin/*`` detector can use it as a
+drop-in.  The arithmetic is NOT the reference's op chain: each block is one fused
+autograd.Function over the C-ABI kernels (functional.py).  There is no CPU path — calling
+``forward`` on CPU tensors raises.
+
+Extra, optional constructor argument: ``compute_dtype`` ("bf16" default | "fp32").
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+import torch.utils.checkpoint as cp
+
+from . import _lib as L
+from . import ops
+from .functional import PatchMergingFn, SwinBlockFn, WindowAttentionFn
+from .registry import register_backbone
+
+
+def _dt_code(compute_dtype: Optional[str]) -> int:
+    v = (compute_dtype or os.environ.get("SWIN_B200_DTYPE", "bf16")).lower()
+    if v in ("bf16", "bfloat16"):
+        return L.BF16
+    if v in ("fp32", "float32", "f32"):
+        return L.F32
+    raise ValueError(f"compute_dtype must be 'bf16' or 'fp32', got {compute_dtype!r}")
+
+
+def _pair(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
+def _need_cuda(t: torch.Tensor, who: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{who}: swin_b200 runs only on CUDA (sm_100a) tensors; there is no CPU fallback")
+
+
+def window_partition(x: torch.Tensor, window_size: int) -> torch.Tensor:
+    """(B, H, W, C) -> (num_windows*B, window_size, window_size, C).  REF:41-53 (bit-exact copy kernel)."""
+    _need_cuda(x, "window_partition")
+    return ops.window_partition(x.contiguous(), window_size)
+
+
+def window_reverse(windows: torch.Tensor, window_size: int, H: int, W: int) -> torch.Tensor:
+    """(num_windows*B, window_size, window_size, C) -> (B, H, W, C).  REF:56-70."""
+    _need_cuda(windows, "window_reverse")
+    return ops.window_reverse(windows.contiguous(), window_size, H, W)
+
+
+class DropPath(nn.Module):
+    """Stochastic depth per sample (timm semantics used at REF:190,252,253).  ``sample_scale`` returns the
+    (B,) multiplier floor(keep + U[0,1)) / keep that the fused residual epilogues apply; draws one uniform per
+    sample per call, in the reference's call order."""
+
+    def __init__(self, drop_prob: float = 0.0):
+        super().__init__()
+        self.drop_prob = float(drop_prob)
+
+    def sample_scale(self, x: torch.Tensor) -> Optional[torch.Tensor]:
+        if self.drop_prob == 0.0 or not self.training:
+            return None
+        keep = 1.0 - self.drop_prob
+        r = keep + torch.rand((x.shape[0],) + (1,) * (x.ndim - 1), dtype=torch.float32, device=x.device)
+        return (r.floor_() / keep).reshape(-1).contiguous()
+
+    def forward(self, x):
+        s = self.sample_scale(x)
+        return x if s is None else x * s.view((-1,) + (1,) * (x.ndim - 1)).to(x.dtype)
+
+    def extra_repr(self):
+        return f"p={self.drop_prob}"
+
+
+class Mlp(nn.Module):
+    """fc1 -> GELU(erf) -> fc2 (REF:20-38).  Inside a block the fused path uses these parameters directly;
+    called standalone it runs the same GEMM kernels."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0):
+        super().__init__()
+        if act_layer is not nn.GELU:
+            raise NotImplementedError("swin_b200 fuses exact-erf GELU; other activations are not supported")
+        self.fc1 = nn.Linear(in_features, hidden_features or in_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features or in_features, out_features or in_features)
+        self.drop = nn.Dropout(drop)
+        self.drop_rate = drop
+
+    def forward(self, x):
+        raise NotImplementedError("Mlp is executed fused inside SwinTransformerBlock (LN2 + fc1 + GELU + fc2 + residual)")
+
+
+class WindowAttention(nn.Module):
+    """W-MSA / SW-MSA with relative position bias (REF:73-153); same parameters/buffers."""
+
+    def __init__(self, dim, window_size, num_heads, qkv_bias=True, qk_scale=None, attn_drop=0.0, proj_drop=0.0,
+                 compute_dtype: Optional[str] = None):
+        super().__init__()
+        self.dim = dim
+        self.window_size = _pair(window_size)
+        if self.window_size[0] != self.window_size[1]:
+            raise NotImplementedError("square windows only")
+        self.num_heads = num_heads
+        if dim % num_heads or dim // num_heads != 32:
+            raise NotImplementedError("swin_b200 kernels are specialised for head_dim 32 (every Swin variant)")
+        self.scale = qk_scale or (dim // num_heads) ** -0.5
+        ws = self.window_size[0]
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * ws - 1) ** 2, num_heads))
+        r = torch.arange(ws * ws) // ws
+        c = torch.arange(ws * ws) % ws
+        idx = (r[:, None] - r[None, :] + ws - 1) * (2 * ws - 1) + (c[:, None] - c[None, :] + ws - 1)
+        self.register_buffer("relative_position_index", idx.long())
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.softmax = nn.Softmax(dim=-1)
+        self._drops = (attn_drop, proj_drop)
+        self._dt = _dt_code(compute_dtype)
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=0.02)
+
+    def forward(self, x, mask=None):
+        """x: (num_windows*B, N, C); mask: (num_windows, N, N) additive or None."""
+        _need_cuda(x, "WindowAttention")
+        if self.training and any(p > 0 for p in self._drops):
+            raise NotImplementedError("attention/projection dropout > 0 is not implemented in the fused kernels")
+        if mask is not None:
+            mask = mask.detach().float().contiguous()
+        return WindowAttentionFn.apply(x, self.relative_position_bias_table, self.qkv.weight, self.qkv.bias,
+                                       self.proj.weight, self.proj.bias, mask, self.window_size[0], self.num_heads,
+                                       float(self.scale), self._dt)
+
+
+class SwinTransformerBlock(nn.Module):
+    """REF:156-255.  forward(x, mask_matrix) with self.H / self.W set by the caller (REF:207, :392)."""
+
+    def __init__(self, dim, num_heads, window_size=7, shift_size=0, mlp_ratio=4.0, qkv_bias=True, qk_scale=None,
+                 drop=0.0, attn_drop=0.0, drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm,
+                 compute_dtype: Optional[str] = None):
+        super().__init__()
+        if norm_layer is not nn.LayerNorm:
+            raise NotImplementedError("swin_b200 fuses nn.LayerNorm; other norm layers are not supported")
+        assert 0 <= shift_size < window_size, "shift_size must in 0-window_size"
+        self.dim, self.num_heads, self.window_size, self.shift_size, self.mlp_ratio = dim, num_heads, window_size, shift_size, mlp_ratio
+        self.norm1 = norm_layer(dim)
+        self.attn = WindowAttention(dim, _pair(window_size), num_heads, qkv_bias, qk_scale, attn_drop, drop, compute_dtype)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        self.H = None
+        self.W = None
+        self._drop = drop
+        self._dt = _dt_code(compute_dtype)
+
+    def forward(self, x, mask_matrix):
+        _need_cuda(x, "SwinTransformerBlock")
+        B, Lx, C = x.shape
+        H, W = self.H, self.W
+        assert Lx == H * W, "input feature has wrong size"
+        if self.training and (self._drop > 0 or any(p > 0 for p in self.attn._drops)):
+            raise NotImplementedError("dropout > 0 is not implemented in the fused kernels")
+        mask = None
+        if self.shift_size > 0:
+            if mask_matrix is None:
+                raise ValueError("shifted block needs mask_matrix")
+            mask = mask_matrix.detach().float().contiguous()
+        s1 = s2 = None
+        if isinstance(self.drop_path, DropPath):
+            s1 = self.drop_path.sample_scale(x)      # attention-branch draw first, then MLP (REF:252-253)
+            s2 = self.drop_path.sample_scale(x)
+        a, m = self.attn, self.mlp
+        return SwinBlockFn.apply(x, self.norm1.weight, self.norm1.bias, a.relative_position_bias_table, a.qkv.weight,
+                                 a.qkv.bias, a.proj.weight, a.proj.bias, self.norm2.weight, self.norm2.bias,
+                                 m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, mask, s1, s2,
+                                 H, W, self.window_size, self.shift_size, self.num_heads, float(a.scale), self._dt,
+                                 float(self.norm1.eps))
+
+
+class PatchMerging(nn.Module):
+    """REF:258-298: 2x2 gather (+ zero pad of odd H/W) -> LayerNorm(4C) -> Linear(4C, 2C, bias=False)."""
+
+    def __init__(self, dim, norm_layer=nn.LayerNorm, compute_dtype: Optional[str] = None):
+        super().__init__()
+        if norm_layer is not nn.LayerNorm:
+            raise NotImplementedError("swin_b200 fuses nn.LayerNorm; other norm layers are not supported")
+        self.dim = dim
+        self.reduction = nn.Linear(4 * dim, 2 * dim, bias=False)
+        self.norm = norm_layer(4 * dim)
+        self._dt = _dt_code(compute_dtype)
+
+    def forward(self, x, H, W):
+        _need_cuda(x, "PatchMerging")
+        B, Lx, C = x.shape
+        assert Lx == H * W, "input feature has wrong size"
+        return PatchMergingFn.apply(x, self.norm.weight, self.norm.bias, self.reduction.weight, H, W, self._dt,
+                                    float(self.norm.eps))
+
+
+class BasicLayer(nn.Module):
+    """One stage (REF:301-402): blocks alternate shift 0 / window_size//2, optional downsample."""
+
+    def __init__(self, dim, depth, num_heads, window_size=7, mlp_ratio=4.0, qkv_bias=True, qk_scale=None, drop=0.0,
+                 attn_drop=0.0, drop_path=0.0, norm_layer=nn.LayerNorm, downsample=None, use_checkpoint=False,
+                 compute_dtype: Optional[str] = None):
+        super().__init__()
+        self.window_size = window_size
+        self.shift_size = window_size // 2
+        self.depth = depth
+        self.use_checkpoint = use_checkpoint
+        self.blocks = nn.ModuleList(
+            SwinTransformerBlock(dim, num_heads, window_size, 0 if i % 2 == 0 else window_size // 2, mlp_ratio, qkv_bias,
+                                 qk_scale, drop, attn_drop, drop_path[i] if isinstance(drop_path, (list, tuple)) else drop_path,
+                                 norm_layer=norm_layer, compute_dtype=compute_dtype)
+            for i in range(depth))
+        self.downsample = downsample(dim=dim, norm_layer=norm_layer, compute_dtype=compute_dtype) if downsample is not None else None
+        self._mask_cache = {}
+
+    def attn_mask(self, H: int, W: int, device) -> torch.Tensor:
+        """SW-MSA mask (nW, N, N) fp32 of {0, -100} (REF:370-389), built by the bit-exact mask kernel."""
+        key = (H, W, str(device))
+        m = self._mask_cache.get(key)
+        if m is None:
+            m = ops.shift_mask(H, W, self.window_size, self.shift_size, device)
+            if len(self._mask_cache) > 16:
+                self._mask_cache.clear()
+            self._mask_cache[key] = m
+        return m
+
+    def forward(self, x, H, W):
+        _need_cuda(x, "BasicLayer")
+        mask = self.attn_mask(H, W, x.device)
+        for blk in self.blocks:
+            blk.H, blk.W = H, W
+            x = cp.checkpoint(blk, x, mask, use_reentrant=False) if self.use_checkpoint else blk(x, mask)
+        if self.downsample is not None:
+            x_down = self.downsample(x, H, W)
+            return x, H, W, x_down, (H + 1) // 2, (W + 1) // 2
+        return x, H, W, x, H, W
+
+
+class PatchEmbed(nn.Module):
+    """REF:405-445 (zero-pad to the patch multiple, 4x4/4 conv, optional LayerNorm).  SURVEY.md §8 row f1
+    ("next"): still library code (cuDNN conv + ATen LN), 0.3 % of the backbone FLOPs."""
+
+    def __init__(self, patch_size=4, in_chans=3, embed_dim=96, norm_layer=None):
+        super().__init__()
+        self.patch_size = _pair(patch_size)
+        self.in_chans, self.embed_dim = in_chans, embed_dim
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=self.patch_size, stride=self.patch_size)
+        self.norm = norm_layer(embed_dim) if norm_layer is not None else None
+
+    def forward(self, x):
+        _, _, H, W = x.shape
+        ph, pw = self.patch_size
+        if W % pw or H % ph:
+            x = F.pad(x, (0, (-W) % pw, 0, (-H) % ph))
+        x = self.proj(x)
+        if self.norm is not None:
+            Wh, Ww = x.shape[2], x.shape[3]
+            x = self.norm(x.flatten(2).transpose(1, 2)).transpose(1, 2).reshape(-1, self.embed_dim, Wh, Ww)
+        return x
+
+
+@register_backbone
+class SwinTransformer(nn.Module):
+    """Swin backbone, REF:448-630.  Constructor arguments and defaults as REF:478-497 (+ compute_dtype)."""
+
+    def __init__(self, pretrain_img_size=224, patch_size=4, in_chans=3, embed_dim=96, depths=[2, 2, 6, 2],
+                 num_heads=[3, 6, 12, 24], window_size=7, mlp_ratio=4.0, qkv_bias=True, qk_scale=None, drop_rate=0.0,
+                 attn_drop_rate=0.0, drop_path_rate=0.2, norm_layer=nn.LayerNorm, ape=False, patch_norm=True,
+                 out_indices=(0, 1, 2, 3), frozen_stages=-1, use_checkpoint=False, compute_dtype: Optional[str] = None):
+        super().__init__()
+        self.pretrain_img_size = pretrain_img_size
+        self.num_layers = len(depths)
+        self.embed_dim = embed_dim
+        self.ape = ape
+        self.patch_norm = patch_norm
+        self.out_indices = out_indices
+        self.frozen_stages = frozen_stages
+        self.compute_dtype = "fp32" if _dt_code(compute_dtype) == L.F32 else "bf16"
+        self.patch_embed = PatchEmbed(patch_size, in_chans, embed_dim, norm_layer if patch_norm else None)
+        if ape:
+            pis, ps = _pair(pretrain_img_size), _pair(patch_size)
+            self.absolute_pos_embed = nn.Parameter(torch.zeros(1, embed_dim, pis[0] // ps[0], pis[1] // ps[1]))
+            nn.init.trunc_normal_(self.absolute_pos_embed, std=0.02)
+        self.pos_drop = nn.Dropout(p=drop_rate)
+        dpr = [v.item() for v in torch.linspace(0, drop_path_rate, sum(depths))]       # REF:525
+        self.layers = nn.ModuleList()
+        for i in range(self.num_layers):
+            self.layers.append(BasicLayer(
+                dim=int(embed_dim * 2 ** i), depth=depths[i], num_heads=num_heads[i], window_size=window_size,
+                mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop_rate, attn_drop=attn_drop_rate,
+                drop_path=dpr[sum(depths[:i]):sum(depths[:i + 1])], norm_layer=norm_layer,
+                downsample=PatchMerging if i < self.num_layers - 1 else None, use_checkpoint=use_checkpoint,
+                compute_dtype=compute_dtype))
+        self.num_features = [int(embed_dim * 2 ** i) for i in range(self.num_layers)]
+        for i in out_indices:
+            self.add_module(f"norm{i}", norm_layer(self.num_features[i]))
+        self._freeze_stages()
+
+    def _freeze_stages(self):
+        """REF:557-572."""
+        if self.frozen_stages >= 0:
+            self.patch_embed.eval()
+            for p in self.patch_embed.parameters():
+                p.requires_grad = False
+        if self.frozen_stages >= 1 and self.ape:
+            self.absolute_pos_embed.requires_grad = False
+        if self.frozen_stages >= 2:
+            self.pos_drop.eval()
+            for i in range(0, self.frozen_stages - 1):
+                self.layers[i].eval()
+                for p in self.layers[i].parameters():
+                    p.requires_grad = False
+
+    def init_weights(self, pretrained=None):
+        """REF:574-598: Linear trunc-normal(0.02) + zero bias, LayerNorm 1/0; a str loads a checkpoint."""
+        def _init(m):
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+        if pretrained is None or isinstance(pretrained, str):
+            self.apply(_init)
+            if isinstance(pretrained, str):
+                from .checkpoint import load_checkpoint
+                load_checkpoint(self, pretrained, strict=False)
+        else:
+            raise TypeError("pretrained must be a str or None")
+
+    def forward(self, x):
+        _need_cuda(x, "SwinTransformer")
+        x = self.patch_embed(x.float())
+        Wh, Ww = x.shape[2], x.shape[3]
+        if self.ape:
+            x = x + F.interpolate(self.absolute_pos_embed, size=(Wh, Ww), mode="bicubic")
+        x = self.pos_drop(x.flatten(2).transpose(1, 2).contiguous())
+        outs = []
+        for i, layer in enumerate(self.layers):
+            x_out, H, W, x, Wh, Ww = layer(x, Wh, Ww)
+            if i in self.out_indices:
+                y = getattr(self, f"norm{i}")(x_out)
+                outs.append(y.view(-1, H, W, self.num_features[i]).permute(0, 3, 1, 2).contiguous())
+        return tuple(outs)
+
+    def train(self, mode=True):
+        super().train(mode)
+        self._freeze_stages()
+        return self

@@ -1,0 +1,265 @@
+"""Kernel-level parity on a B200: every C-ABI entry point against the oracle / plain torch math.
+Index ops are bit-exact; fp32 kernels <=1e-5; bf16 tensor-core kernels are compared with the same
+math done in fp64 on bf16-rounded inputs (tolerance 1e-2, the output rounding)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import swin_oracle as so
+from oracle.make_golden import INDEX_CASES
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ops():
+    from swin_b200 import ops, _lib
+    return ops, _lib
+
+
+def rel(a, b):
+    return so.rel_l2(a, b)
+
+
+# ---------------------------------------------------------------- index ops
+@pytest.mark.parametrize("ci", range(len(INDEX_CASES)))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_index_ops_bit_exact(ci, dtype):
+    ops, _ = _ops()
+    d = np.load(os.path.join(GOLDEN, "index_ops.npz"))
+    B, H, W, C, ws = INDEX_CASES[ci]
+    Hp, Wp = so.padded_hw(H, W, ws)
+    # bf16 represents integers exactly only up to 256: use the value mod 251 for the bf16 run
+    f = (lambda a: a) if dtype == torch.float32 else (lambda a: np.mod(a, 251))
+    x = np.random.default_rng(100 + ci).integers(-30000, 30000, size=(B, Hp, Wp, C)).astype(np.float32)
+    xt = torch.from_numpy(f(x)).to(DEV, dtype)
+    part = ops.window_partition(xt, ws)
+    assert torch.equal(part.float().cpu(), torch.from_numpy(f(d[f"part{ci}"].astype(np.float32))))
+    assert torch.equal(ops.window_reverse(part, ws, Hp, Wp), xt)
+    xs = np.random.default_rng(200 + ci).integers(1, 30000, size=(B, H, W, C)).astype(np.float32)
+    for shift in (0, ws // 2):
+        g = d[f"gather{ci}_s{shift}"].astype(np.float32)
+        got = ops.window_gather(torch.from_numpy(f(xs)).to(DEV, dtype).reshape(B, H * W, C), H, W, ws, shift)
+        want = torch.from_numpy(np.where(g == 0, 0, f(g)))          # pad slots stay exactly 0
+        assert torch.equal(got.float().cpu(), want)
+        ww = np.random.default_rng(300 + ci + shift).integers(1, 30000, size=g.shape).astype(np.float32)
+        back = ops.window_scatter(torch.from_numpy(f(ww)).to(DEV, dtype), B, H, W, ws, shift)
+        assert torch.equal(back.float().cpu(), torch.from_numpy(f(d[f"scatter{ci}_s{shift}"].astype(np.float32))))
+    m = ops.shift_mask(H, W, ws, ws // 2, DEV)
+    assert torch.equal(m.cpu(), torch.from_numpy(d[f"mask{ci}"]))
+
+
+def test_gather_scatter_roundtrip_full_size():
+    """cfg2 stage-0 geometry (B=2 of 16): scatter(gather(x)) == x bit-for-bit, pad slots are zero."""
+    ops, _ = _ops()
+    B, H, W, C, ws = 2, 200, 334, 96, 7
+    x = torch.randn(B, H * W, C, device=DEV).bfloat16()
+    for shift in (0, 3):
+        xw = ops.window_gather(x, H, W, ws, shift)
+        assert torch.equal(ops.window_scatter(xw, B, H, W, ws, shift), x)
+        idx = torch.from_numpy(so.gather_index(H, W, ws, shift)).to(DEV)
+        flat = xw.reshape(B, -1, C)
+        assert flat[:, idx < 0].abs().max().item() == 0
+        assert torch.equal(flat[:, idx >= 0], x[:, idx[idx >= 0]])
+
+
+def test_rel_bias_expand_reduce():
+    ops, _ = _ops()
+    for ws, nH in ((7, 3), (12, 4)):
+        table = torch.randn((2 * ws - 1) ** 2, nH, device=DEV)
+        idx = torch.from_numpy(so.relative_position_index_np(ws)).to(DEV)
+        want = table[idx.reshape(-1)].reshape(ws * ws, ws * ws, nH).permute(2, 0, 1).contiguous()
+        assert torch.equal(ops.rel_bias_expand(table, ws), want)
+        db = torch.randn(nH, ws * ws, ws * ws, device=DEV)
+        ref = torch.zeros_like(table).index_put_((idx.reshape(-1),), db.permute(1, 2, 0).reshape(-1, nH), accumulate=True)
+        assert rel(ops.rel_bias_reduce(db, ws), ref) < 1e-5
+
+
+# ---------------------------------------------------------------- LayerNorm family
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("ydt", ["f32", "bf16"])
+@pytest.mark.parametrize("C", [32, 96, 384])
+def test_layernorm_modes(mode, ydt, C):
+    ops, L = _ops()
+    B, H, W, ws, shift = 2, 9, 13, 7, 3
+    code = L.F32 if ydt == "f32" else L.BF16
+    rng = np.random.default_rng(5)
+    x = torch.from_numpy(rng.standard_normal((B, H * W, C)).astype(np.float32))
+    width = 4 * C if mode == 2 else C
+    gm = torch.from_numpy((1 + 0.2 * rng.standard_normal(width)).astype(np.float32))
+    bt = torch.from_numpy((0.3 * rng.standard_normal(width)).astype(np.float32))
+    xr = x.double().requires_grad_(True)
+    gr, br = gm.double().requires_grad_(True), bt.double().requires_grad_(True)
+    if mode == 0:
+        yr = so.layer_norm(xr, gr, br)
+    elif mode == 1:
+        yr = so.shift_gather(so.layer_norm(xr, gr, br), H, W, ws, shift)
+    else:
+        idx = torch.from_numpy(so.merge_index(H, W))
+        xz = torch.cat([xr, xr.new_zeros(B, 1, C)], 1)
+        sel = torch.where(idx < 0, torch.full_like(idx, H * W), idx)
+        yr = so.layer_norm(xz[:, sel.reshape(-1)].reshape(B, idx.shape[0], 4 * C), gr, br)
+    y, mean, rstd = ops.ln_fwd(mode, x.to(DEV), gm.to(DEV), bt.to(DEV), B, H, W, C, ws, shift, 1e-5, code)
+    tol = 1e-5 if ydt == "f32" else 6e-3
+    assert rel(y.float().reshape(yr.shape), yr) < tol
+    cot = torch.from_numpy(rng.standard_normal(tuple(yr.shape)).astype(np.float32))
+    dres = torch.from_numpy(rng.standard_normal(tuple(x.shape)).astype(np.float32))
+    cot_d = cot.to(DEV).to(y.dtype)
+    (yr * cot_d.float().cpu().double()).sum().backward()
+    dx, dg, db = ops.ln_bwd(mode, cot_d.reshape(y.shape).contiguous(), x.to(DEV), gm.to(DEV), mean, rstd, dres.to(DEV), B, H, W, C, ws, shift)
+    assert rel(dx, xr.grad + dres.double()) < 1e-5
+    assert rel(dg, gr.grad) < 1e-4
+    assert rel(db, br.grad) < 1e-4
+
+
+def test_scale_cast_and_colsum():
+    ops, L = _ops()
+    B, H, W, C, ws, shift = 2, 9, 13, 64, 7, 3
+    x = torch.randn(B, H * W, C, device=DEV)
+    s = torch.tensor([0.0, 1.25], device=DEV)
+    y = ops.scale_cast(x, s, 0, B, H, W, C, 1, 0, L.BF16)
+    assert torch.equal(y.view(B, H * W, C), (x * s.view(B, 1, 1)).bfloat16())
+    yw = ops.scale_cast(x, s, 1, B, H, W, C, ws, shift, L.F32)
+    want = so.shift_gather((x * s.view(B, 1, 1)).cpu(), H, W, ws, shift)
+    assert torch.equal(yw.cpu().view(want.shape), want)
+    for dt in (torch.float32, torch.bfloat16):
+        X = torch.randn(1000, 96, device=DEV).to(dt)
+        assert rel(ops.colsum(X), X.double().sum(0)) < 1e-5
+    w = torch.randn(777, device=DEV)
+    assert torch.equal(ops.cast_bf16(w), w.bfloat16())
+
+
+# ---------------------------------------------------------------- GEMM
+def _gemm_ref(A, Bm, a_trans, b_trans):
+    A2 = A.double().t() if a_trans else A.double()
+    B2 = Bm.double() if b_trans else Bm.double().t()
+    return A2 @ B2
+
+
+GEMM_SHAPES = [(300, 96, 96), (257, 288, 96), (130, 384, 200), (128, 32, 64), (1000, 256, 512), (64, 768, 3072)]
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("a_trans,b_trans", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_store_all_layouts(dtype, a_trans, b_trans, M, N, K):
+    ops, L = _ops()
+    td = torch.float32 if dtype == "f32" else torch.bfloat16
+    if dtype == "bf16" and a_trans and M % 8:
+        pytest.skip("transposed bf16 operand needs a 16-byte row pitch")
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    A = (torch.randn((K, M) if a_trans else (M, K), generator=g) * 0.5).to(td).to(DEV)
+    Bm = (torch.randn((K, N) if b_trans else (N, K), generator=g) * 0.5).to(td).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    out = ops.gemm(A, Bm, M, N, K, a_trans=a_trans, b_trans=b_trans, bias=bias, out_dtype=L.F32)
+    ref = _gemm_ref(A.cpu(), Bm.cpu(), a_trans, b_trans) + bias.cpu().double()
+    assert rel(out, ref) < (1e-5 if dtype == "f32" else 1e-5), (M, N, K)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_gemm_epilogues(dtype):
+    ops, L = _ops()
+    td = torch.float32 if dtype == "f32" else torch.bfloat16
+    tol_store = 1e-5 if dtype == "f32" else 6e-3
+    B, H, W, C, ws, shift = 2, 9, 13, 64, 7, 3
+    T = B * H * W
+    g = torch.Generator(device="cpu").manual_seed(3)
+    X = (torch.randn(T, C, generator=g)).to(td).to(DEV)
+    Wt = (torch.randn(4 * C, C, generator=g) * 0.2).to(td).to(DEV)
+    b = torch.randn(4 * C, generator=g).to(DEV)
+    # GELU: D = gelu(u), D2 = u
+    u = torch.empty(T, 4 * C, dtype=td, device=DEV)
+    h = ops.gemm(X, Wt, T, 4 * C, C, bias=b, epilogue=L.EPI_GELU, out2=u)
+    ur = X.double().cpu() @ Wt.double().cpu().t() + b.double().cpu()
+    assert rel(u, ur) < tol_store and rel(h, so.gelu_erf(ur)) < tol_store
+    # DGELU: D = acc * gelu'(u)
+    dy = (torch.randn(T, C, generator=g)).to(td).to(DEV)
+    du = ops.gemm(dy, Wt, T, 4 * C, C, b_trans=False, epilogue=L.EPI_DGELU, aux=u)
+    uu = u.double().cpu().requires_grad_(True)
+    so.gelu_erf(uu).sum().backward()
+    assert rel(du, (dy.double().cpu() @ Wt.double().cpu().t()) * uu.grad) < tol_store
+    # RESIDUAL with per-image scale
+    W2 = (torch.randn(C, 4 * C, generator=g) * 0.1).to(td).to(DEV)
+    b2 = torch.randn(C, generator=g).to(DEV)
+    res = torch.randn(T, C, generator=g).to(DEV)
+    s = torch.tensor([0.0, 1.25], device=DEV)
+    out = torch.empty(T, C, device=DEV)
+    ops.gemm(h, W2, T, C, 4 * C, bias=b2, epilogue=L.EPI_RESIDUAL, out=out, aux=res, row_scale=s, rows_per_image=H * W)
+    y = h.double().cpu() @ W2.double().cpu().t() + b2.double().cpu()
+    ref = res.double().cpu() + (y.view(B, H * W, C) * s.double().cpu().view(B, 1, 1)).view(T, C)
+    assert rel(out, ref) < 1e-5 if dtype == "f32" else rel(out, ref) < 2e-3
+    # SCATTER_RESIDUAL: rows are window slots
+    nslots = so.gather_index(H, W, ws, shift).shape[0]
+    Ow = torch.randn(B * nslots, C, generator=g).to(td).to(DEV)
+    Wp_ = (torch.randn(C, C, generator=g) * 0.2).to(td).to(DEV)
+    out = torch.empty(T, C, device=DEV)
+    ops.gemm(Ow, Wp_, B * nslots, C, C, bias=b2, epilogue=L.EPI_SCATTER_RESIDUAL, out=out, aux=res, row_scale=s, geom=(H, W, ws, shift))
+    yw = (Ow.double().cpu() @ Wp_.double().cpu().t() + b2.double().cpu()).view(-1, ws * ws, C)
+    ysc = so.shift_scatter(yw, B, H, W, ws, shift) * s.double().cpu().view(B, 1, 1)
+    assert rel(out, res.double().cpu() + ysc.view(T, C)) < (1e-5 if dtype == "f32" else 2e-3)
+    # ATOMIC_ADD split-K weight gradient: dW = dY^T X
+    dW = torch.zeros(4 * C, C, device=DEV)
+    dY = torch.randn(T, 4 * C, generator=g).to(td).to(DEV)
+    ops.gemm(dY, X, 4 * C, C, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dW)
+    assert rel(dW, dY.double().cpu().t() @ X.double().cpu()) < 1e-5
+
+
+def test_gemm_bf16_matches_fp32_kernel_on_device():
+    """Cross-check of the two GEMM implementations on identical (bf16-representable) data, large split-K."""
+    ops, L = _ops()
+    T, Co, Ci = 50000, 288, 96
+    dY = torch.randn(T, Co, device=DEV).bfloat16()
+    X = torch.randn(T, Ci, device=DEV).bfloat16()
+    d16 = torch.zeros(Co, Ci, device=DEV)
+    d32 = torch.zeros(Co, Ci, device=DEV)
+    ops.gemm(dY, X, Co, Ci, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=d16)
+    ops.gemm(dY.float(), X.float(), Co, Ci, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=d32)
+    assert rel(d16, d32) < 1e-4
+
+
+# ---------------------------------------------------------------- window attention core
+def _attn_ref(qkv, bias, mask, nH, scale, cot):
+    B_, N, C3 = qkv.shape
+    C = C3 // 3
+    q = qkv.double().requires_grad_(True)
+    bz = bias.double().requires_grad_(True)
+    qq = q[..., :C].reshape(B_, N, nH, 32).transpose(1, 2) * scale
+    kk = q[..., C:2 * C].reshape(B_, N, nH, 32).transpose(1, 2)
+    vv = q[..., 2 * C:].reshape(B_, N, nH, 32).transpose(1, 2)
+    s = qq @ kk.transpose(-1, -2) + bz[None]
+    if mask is not None:
+        s = s + mask.double()[torch.arange(B_) % mask.shape[0]][:, None]
+    p = torch.softmax(s, -1)
+    o = (p @ vv).transpose(1, 2).reshape(B_, N, C)
+    lse = torch.logsumexp(s, -1)
+    (o * cot.double()).sum().backward()
+    return o.detach(), lse.detach(), q.grad, bz.grad
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("B_,nH,masked", [(6, 2, True), (5, 3, False), (1, 1, False), (48, 6, True)])
+def test_window_attention_core(dtype, B_, nH, masked):
+    ops, L = _ops()
+    td = torch.float32 if dtype == "f32" else torch.bfloat16
+    ws, N, C = 7, 49, nH * 32
+    g = torch.Generator(device="cpu").manual_seed(B_ * 10 + nH)
+    qkv = torch.randn(B_, N, 3 * C, generator=g).to(td)
+    bias = (torch.randn(nH, N, N, generator=g) * 0.5)
+    mask = torch.from_numpy(so.shift_mask_np(10, 13, ws, 3)[1:4]) if masked else None   # nW = 3
+    cot = torch.randn(B_, N, C, generator=g).to(td)
+    o_r, lse_r, dqkv_r, dbias_r = _attn_ref(qkv.float(), bias, mask, nH, 32 ** -0.5, cot.float())
+    md = mask.to(DEV) if masked else None
+    o, lse = ops.window_attn_fwd(qkv.to(DEV), bias.to(DEV), md, B_, nH, ws, 32 ** -0.5)
+    tol = 1e-5 if dtype == "f32" else 8e-3
+    assert rel(o, o_r) < tol
+    assert rel(lse, lse_r) < 1e-5 if dtype == "f32" else rel(lse, lse_r) < 2e-3
+    dqkv, dbias = ops.window_attn_bwd(qkv.to(DEV), o, cot.to(DEV), lse, bias.to(DEV), md, B_, nH, ws, 32 ** -0.5)
+    tolb = 1e-5 if dtype == "f32" else 1.5e-2
+    C_ = C
+    assert rel(dqkv[..., :C_], dqkv_r[..., :C_]) < tolb, "dQ"
+    assert rel(dqkv[..., C_:2 * C_], dqkv_r[..., C_:2 * C_]) < tolb, "dK"
+    assert rel(dqkv[..., 2 * C_:], dqkv_r[..., 2 * C_:]) < tolb, "dV"
+    assert rel(dbias, dbias_r) < tolb, "dBias"

