@@ -54,6 +54,8 @@ int swin_window_gather(const void* x, void* xw, int B, int H, int W, int C, int 
 int swin_window_scatter(const void* xw, void* x, int B, int H, int W, int C, int ws, int shift, int elem_bytes, void* stream);
 /* SW-MSA mask of BasicLayer.forward, REF:370-389.  mask (nW,N,N) fp32 in {0,-100}. */
 int swin_shift_mask(float* mask, int H, int W, int ws, int shift, void* stream);
+/* flags[w] = 1 if mask[w] (N x N) has any non-zero entry, else 0  (lets the attention kernels skip all-zero masks). */
+int swin_mask_nonzero(const float* mask, int32_t* flags, int nW, int N, void* stream);
 /* relative_position_bias gather, REF:135-137: table ((2ws-1)^2, nH) -> bias (nH,N,N) fp32. */
 int swin_rel_bias_expand(const float* table, float* bias, int nH, int ws, void* stream);
 /* its transpose (index_put accumulate of the autograd backward): dtable += scatter(dbias). */
@@ -85,6 +87,19 @@ typedef struct swin_ln_args {
 } swin_ln_args;
 int swin_ln_fwd(const swin_ln_args* a, void* stream);
 int swin_ln_bwd(const swin_ln_args* a, void* stream);
+
+/* output norm{i} + view/permute(0,3,1,2).contiguous(), REF:618-623: x (B,L,C) fp32 -> out (B,C,L) fp32 (NCHW), LN over C. */
+int swin_ln_nchw_fwd(const float* x, const float* gamma, const float* beta, float* out, float* mean, float* rstd, int B, int L,
+                     int C, float eps, void* stream);
+/* backward: dout (B,C,L) -> dx (B,L,C); dgamma/dbeta ACCUMULATED (caller zero-fills). */
+int swin_ln_nchw_bwd(const float* dout, const float* x, const float* gamma, const float* mean, const float* rstd, float* dx,
+                     float* dgamma, float* dbeta, int B, int L, int C, void* stream);
+
+/* ---------------------------------------------------------------- PatchEmbed unfold, REF:432-438
+ * img (B,Cin,Hi,Wi) fp32 -> cols (B*ceil(Hi/p)*ceil(Wi/p), Cin*p*p) in `dtype`, zero-padded right/bottom, column order
+ * [c][i][j] == proj.weight.view(C,-1); the conv is then swin_gemm(cols, weight).  scatter = its transpose (d img). */
+int swin_patch_gather(const float* img, void* cols, int B, int Cin, int Hi, int Wi, int patch, int dtype, void* stream);
+int swin_patch_scatter(const void* dcols, float* dimg, int B, int Cin, int Hi, int Wi, int patch, int dtype, void* stream);
 
 /* ---------------------------------------------------------------- GEMM with fused epilogues
  * acc[m,n] = sum_k A[m,k] * B[n,k]
@@ -140,6 +155,7 @@ typedef struct swin_attn_args {
   const void* qkv;
   const float* bias;
   const float* mask;
+  const int32_t* mask_nz; /* optional (nW): 0 where mask[w] is all zeros, so the kernel skips reading it; NULL = unknown */
   void* out;
   float* lse;
   /* backward */

@@ -38,7 +38,7 @@ class GemmArgs(C.Structure):
 
 class AttnArgs(C.Structure):
     _fields_ = [("dtype", c_int), ("B_", c_int), ("nH", c_int), ("ws", c_int), ("nW", c_int), ("scale", c_f32),
-                ("qkv", vp), ("bias", vp), ("mask", vp), ("out", vp), ("lse", vp),
+                ("qkv", vp), ("bias", vp), ("mask", vp), ("mask_nz", vp), ("out", vp), ("lse", vp),
                 ("dout", vp), ("dqkv", vp), ("dbias", vp)]
 
 
@@ -52,10 +52,15 @@ SYMBOLS = {
     "swin_window_gather": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, vp]),
     "swin_window_scatter": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, vp]),
     "swin_shift_mask": (c_int, [vp, c_int, c_int, c_int, c_int, vp]),
+    "swin_mask_nonzero": (c_int, [vp, vp, c_int, c_int, vp]),
     "swin_rel_bias_expand": (c_int, [vp, vp, c_int, c_int, vp]),
     "swin_rel_bias_reduce": (c_int, [vp, vp, c_int, c_int, vp]),
     "swin_ln_fwd": (c_int, [C.POINTER(LnArgs), vp]),
     "swin_ln_bwd": (c_int, [C.POINTER(LnArgs), vp]),
+    "swin_ln_nchw_fwd": (c_int, [vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_f32, vp]),
+    "swin_ln_nchw_bwd": (c_int, [vp, vp, vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, vp]),
+    "swin_patch_gather": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp]),
+    "swin_patch_scatter": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp]),
     "swin_gemm": (c_int, [C.POINTER(GemmArgs), vp]),
     "swin_colsum": (c_int, [vp, c_int, c_int, c_i64, c_int, vp, vp]),
     "swin_scale_cast": (c_int, [vp, vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, vp]),

@@ -76,6 +76,23 @@ __device__ __forceinline__ float dgelu_erf(float u) {
   return cdf + u * pdf;
 }
 
+// Fast GELU / GELU' for the bf16 tensor-core epilogues: erfc by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7),
+// one MUFU.RCP + one MUFU.EX2 and ~12 FMA-pipe ops; exp(-u^2/2) is shared by the cdf and the pdf.
+__device__ __forceinline__ void gelu_fast(float u, float* g, float* dg) {
+  const float x = fabsf(u) * 0.70710678118654752440f;
+  float t, E;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, x, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E) : "f"(-0.72134752044448170368f * u * u));   // exp(-u^2/2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float half_erfc = 0.5f * poly * t * E;               // 0.5 * erfc(|u|/sqrt2)
+  const float cdf = u >= 0.f ? 1.0f - half_erfc : half_erfc;
+  *g = u * cdf;
+  *dg = fmaf(u * 0.39894228040143267794f, E, cdf);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

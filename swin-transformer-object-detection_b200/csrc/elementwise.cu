@@ -89,6 +89,14 @@ __global__ void shift_mask_kernel(float* __restrict__ mask, WinGeom g) {
   }
 }
 
+__global__ void mask_nonzero_kernel(const float* __restrict__ mask, int* __restrict__ flags, int nW, int NN) {
+  const int w = blockIdx.x;
+  int any = 0;
+  for (int e = threadIdx.x; e < NN; e += blockDim.x) any |= (mask[(size_t)w * NN + e] != 0.0f);
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) flags[w] = any ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // relative position bias: table ((2ws-1)^2, nH) <-> dense (nH, N, N)   (REF:101-111, :135-137)
 // ------------------------------------------------------------------------------------------
@@ -479,6 +487,12 @@ extern "C" int swin_shift_mask(float* mask, int H, int W, int ws, int shift, voi
   long long total = (long long)g.nW * g.N * g.N;
   int grid = (int)((total + 255) / 256 < kNumSMs * 8 ? (total + 255) / 256 : kNumSMs * 8);
   shift_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mask, g);
+  SWIN_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int swin_mask_nonzero(const float* mask, int32_t* flags, int nW, int N, void* stream) {
+  SWIN_REQUIRE(mask && flags && nW > 0 && N > 0, "mask_nonzero: bad arguments");
+  mask_nonzero_kernel<<<nW, 256, 0, (cudaStream_t)stream>>>(mask, flags, nW, N * N);
   SWIN_LAUNCH_CHECK();
   return 0;
 }

@@ -47,7 +47,7 @@ __device__ __forceinline__ bool epi_row_setup(const EpiParams& p, int row, long 
   return true;
 }
 
-template <int NV>
+template <int NV, bool FAST = false>
 __device__ __forceinline__ void epilogue_cols(const EpiParams& p, int row, long long drow, float scale, int col0, const float* v) {
 #pragma unroll
   for (int c = 0; c < NV; c += 4) {
@@ -65,7 +65,13 @@ __device__ __forceinline__ void epilogue_cols(const EpiParams& p, int row, long 
         break;
       case SWIN_EPI_GELU:
         store4(p.D2, p.d_dtype, o, a);
-        store4(p.D, p.d_dtype, o, make_float4(gelu_erf(a.x), gelu_erf(a.y), gelu_erf(a.z), gelu_erf(a.w)));
+        if (FAST) {
+          float4 gq, dq;
+          gelu_fast(a.x, &gq.x, &dq.x); gelu_fast(a.y, &gq.y, &dq.y); gelu_fast(a.z, &gq.z, &dq.z); gelu_fast(a.w, &gq.w, &dq.w);
+          store4(p.D, p.d_dtype, o, gq);
+        } else {
+          store4(p.D, p.d_dtype, o, make_float4(gelu_erf(a.x), gelu_erf(a.y), gelu_erf(a.z), gelu_erf(a.w)));
+        }
         break;
       case SWIN_EPI_RESIDUAL:
       case SWIN_EPI_SCATTER_RESIDUAL: {
@@ -75,7 +81,13 @@ __device__ __forceinline__ void epilogue_cols(const EpiParams& p, int row, long 
       }
       case SWIN_EPI_DGELU: {
         float4 u = load4(p.aux, p.d_dtype, o);
-        store4(p.D, p.d_dtype, o, make_float4(a.x * dgelu_erf(u.x), a.y * dgelu_erf(u.y), a.z * dgelu_erf(u.z), a.w * dgelu_erf(u.w)));
+        if (FAST) {
+          float4 gq, dq;
+          gelu_fast(u.x, &gq.x, &dq.x); gelu_fast(u.y, &gq.y, &dq.y); gelu_fast(u.z, &gq.z, &dq.z); gelu_fast(u.w, &gq.w, &dq.w);
+          store4(p.D, p.d_dtype, o, make_float4(a.x * dq.x, a.y * dq.y, a.z * dq.z, a.w * dq.w));
+        } else {
+          store4(p.D, p.d_dtype, o, make_float4(a.x * dgelu_erf(u.x), a.y * dgelu_erf(u.y), a.z * dgelu_erf(u.z), a.w * dgelu_erf(u.w)));
+        }
         break;
       }
       case SWIN_EPI_ATOMIC_ADD: {

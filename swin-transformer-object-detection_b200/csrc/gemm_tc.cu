@@ -1,7 +1,7 @@
 // bf16 GEMM on the 5th-generation tensor cores: persistent, warp-specialised
 //   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring)
 //   warp 1      MMA issuer     (one thread, tcgen05.mma kind::f16, fp32 accumulators in TMEM)
-//   warps 2..5  epilogue       (tcgen05.ld -> fused epilogue -> global), overlapped with the next
+//   warps 2..9  epilogue       (tcgen05.ld -> fused epilogue -> global), overlapped with the next
 //                               tile's main loop through two TMEM accumulator stages.
 // Operands may be K-major or MN-major ("transposed") so forward (X W^T), dX (dY W) and the
 // split-K weight gradient (dY^T X) all run on the same kernel.
@@ -12,14 +12,16 @@
 namespace swin {
 
 constexpr int TBM = 128, TBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;                 // two per TMEM lane quarter, alternating 32-column chunks
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
 
 struct GemmTcParams {
   int block_n;            // MMA N (multiple of 32, <= 256)
   int n_tiles, m_tiles, splits, kb_total, kb_per_split;
   int stages;
-  uint32_t a_bytes, b_bytes;   // per stage
+  uint32_t a_bytes, b_bytes;   // TMA bytes per stage (expect_tx)
+  uint32_t stage_bytes;        // smem stride per stage: a_bytes + b_bytes rounded up to the 1024-byte swizzle-atom alignment
   EpiParams epi;
 };
 
@@ -29,10 +31,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float4 epi_stage[kEpiWarps][32 * 8];     // per-epilogue-warp 32x32 fp32 transpose stage (4 KB each)
+  __shared__ long long epi_rowdst[kEpiWarps][32];
+  __shared__ float epi_rowscale[kEpiWarps][32];
 
   // 1024-byte aligned operand ring
   uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+  const uint32_t stage_bytes = p.stage_bytes;
+  const uint32_t tx_bytes = p.a_bytes + p.b_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto empty_bar = [&](int s) { return smem_u32(&bars[kMaxStages + s]); };
@@ -41,7 +47,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -69,7 +75,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), stage_bytes);
+          mbar_expect_tx(full_bar(s), tx_bytes);
           const uint32_t sa = smem0 + s * stage_bytes, sb = sa + p.a_bytes;
           if (!A_MN) {
             tma_load_2d(sa, &tmA, full_bar(s), kb * TBK, m0);
@@ -119,24 +125,51 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     __syncwarp();
   } else {
     // ===================================================== epilogue (4 warps = 128 TMEM lanes)
+    // TMEM gives each thread one accumulator ROW; global memory wants a warp per row segment.  Each warp
+    // therefore transposes 32x32 fp32 chunks through a private, XOR-swizzled smem stage and runs the fused
+    // epilogue in the coalesced layout (lane = 4 consecutive columns of one of 4 rows per instruction).
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int ew = warp - 2;                  // 0..7
+    const int chunk_sel = ew >> 2;            // this warp takes 32-column chunks with (c/32)%2 == chunk_sel
+    float4* stage = &epi_stage[ew][0];
     uint32_t u = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++u) {
       const int tile = unit / p.splits;
       const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
-      const int row = m_blk * TBM + q * 32 + lane;
+      const int row_base = m_blk * TBM + q * 32;
       const int n0 = n_blk * p.block_n;
       const uint32_t acc = u & 1, acc_ph = (u >> 1) & 1;
-      long long drow = 0; float scale = 1.f;
-      const bool live = epi_row_setup(p.epi, row, &drow, &scale);
+      {
+        long long drow = 0; float scale = 1.f;
+        const bool live = epi_row_setup(p.epi, row_base + lane, &drow, &scale);
+        epi_rowdst[ew][lane] = live ? drow : -1;
+        epi_rowscale[ew][lane] = scale;
+      }
+      __syncwarp();
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      for (int c = 0; c < p.block_n; c += 32) {
+      const int piece = lane & 7, rsub = lane >> 3;
+      for (int c = chunk_sel * 32; c < p.block_n; c += 64) {
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
         tmem_ld_wait();
-        if (live) epilogue_cols<32>(p.epi, row, drow, scale, n0 + c, reinterpret_cast<const float*>(v));
+#pragma unroll
+        for (int pc = 0; pc < 8; ++pc)
+          stage[lane * 8 + (pc ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * pc]), __uint_as_float(v[4 * pc + 1]),
+                                                            __uint_as_float(v[4 * pc + 2]), __uint_as_float(v[4 * pc + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + rsub;
+          const float4 a = stage[rr * 8 + (piece ^ (rr & 7))];
+          const long long drow = epi_rowdst[ew][rr];
+          if (drow >= 0) {
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            epilogue_cols<4, true>(p.epi, row_base + rr, drow, epi_rowscale[ew][rr], n0 + c + piece * 4, av);
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -149,7 +182,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 }
 
 static int pick_block_n(int N) {
-  const int cand[] = {256, 192, 128, 96, 64, 32};
+  if (N <= 256 && N % 16 == 0) return N;             // any legal UMMA N in one tile (e.g. 48 for the patch-embed dW)
+  const int cand[] = {256, 192, 128, 96, 64, 48, 32, 16};
   for (int c : cand) if (N % c == 0) return c;
   return 0;
 }
@@ -159,7 +193,7 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   int rc = make_epi_params(a, &ep);
   if (rc) return rc;
   SWIN_REQUIRE(a->A && a->B, "gemm: null operand");
-  SWIN_REQUIRE(a->N % 32 == 0, "gemm(bf16): N must be a multiple of 32 (got %d)", a->N);
+  SWIN_REQUIRE(a->N % 16 == 0, "gemm(bf16): N must be a multiple of 16 (got %d)", a->N);
   SWIN_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "gemm(bf16): lda/ldb must be multiples of 8");
   if (a->M == 0) return 0;
   const bool a_mn = a->a_trans != 0, b_mn = a->b_trans != 0;
@@ -183,8 +217,9 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   p.a_bytes = TBM * TBK * 2;
   const int bn_rows = b_mn ? ceil_div(p.block_n, 64) * 64 : p.block_n;
   p.b_bytes = (uint32_t)bn_rows * TBK * 2;
-  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-  const uint32_t budget = 200 * 1024;
+  p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
+  const uint32_t stage_bytes = p.stage_bytes;
+  const uint32_t budget = 184 * 1024;
   p.stages = (int)(budget / stage_bytes);
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   SWIN_REQUIRE(p.stages >= 2, "gemm(bf16): tile does not fit in shared memory");
@@ -204,7 +239,7 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   do {                                                                                                            \
     static bool attr_done = false;                                                                                \
     if (!attr_done) {                                                                                             \
-      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AM, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); \
+      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AM, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 188 * 1024); \
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }      \
       attr_done = true;                                                                                           \
     }                                                                                                             \

@@ -46,7 +46,7 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 class SwinBlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, n1w, n1b, table, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b, mask, s1, s2,
+    def forward(ctx, x, n1w, n1b, table, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b, mask, mask_nz, s1, s2,
                 H, W, ws, shift, nH, scale, dt, eps):
         B, Lx, Cc = x.shape
         x = _f32c(x)
@@ -58,7 +58,7 @@ class SwinBlockFn(torch.autograd.Function):
         Tp = xw.shape[0] * xw.shape[1]
         qkv = ops.gemm(xw, _w(qkvw, dt), Tp, 3 * Cc, Cc, bias=None if qkvb is None else qkvb.detach())
         bias = ops.rel_bias_expand(table.detach().contiguous(), ws)
-        o, lse = ops.window_attn_fwd(qkv.view(-1, ws * ws, 3 * Cc), bias, mask, Tp // (ws * ws), nH, ws, scale)
+        o, lse = ops.window_attn_fwd(qkv.view(-1, ws * ws, 3 * Cc), bias, mask, Tp // (ws * ws), nH, ws, scale, mask_nz)
         x1 = torch.empty_like(x)
         ops.gemm(o, _w(projw, dt), Tp, Cc, Cc, bias=projb.detach(), epilogue=L.EPI_SCATTER_RESIDUAL, out=x1, aux=x,
                  row_scale=s1, geom=geom)
@@ -69,14 +69,14 @@ class SwinBlockFn(torch.autograd.Function):
         x2 = torch.empty_like(x)
         ops.gemm(h, _w(fc2w, dt), T, Cc, hid, bias=fc2b.detach(), epilogue=L.EPI_RESIDUAL, out=x2, aux=x1, row_scale=s2,
                  rows_per_image=Lx)
-        ctx.save_for_backward(x, n1w, table, qkvw, projw, n2w, fc1w, fc2w, mask, s1, s2,
+        ctx.save_for_backward(x, n1w, table, qkvw, projw, n2w, fc1w, fc2w, mask, mask_nz, s1, s2,
                               xw, mean1, rstd1, qkv, bias, o, lse, x1, xn, mean2, rstd2, u, h)
         ctx.cfg = (B, H, W, Cc, ws, shift, nH, scale, dt, hid, qkvb is not None)
         return x2
 
     @staticmethod
     def backward(ctx, dx2):
-        (x, n1w, table, qkvw, projw, n2w, fc1w, fc2w, mask, s1, s2,
+        (x, n1w, table, qkvw, projw, n2w, fc1w, fc2w, mask, mask_nz, s1, s2,
          xw, mean1, rstd1, qkv, bias, o, lse, x1, xn, mean2, rstd2, u, h) = ctx.saved_tensors
         B, H, W, Cc, ws, shift, nH, scale, dt, hid, has_qkvb = ctx.cfg
         T = B * H * W
@@ -100,7 +100,7 @@ class SwinBlockFn(torch.autograd.Function):
         dprojw = torch.zeros_like(projw, dtype=torch.float32)
         ops.gemm(dy1, o, Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dprojw)
         do = ops.gemm(dy1, _w(projw, dt), Tp, Cc, Cc, b_trans=True)
-        dqkv, dbias = ops.window_attn_bwd(qkv.view(-1, N, 3 * Cc), o, do.view(-1, N, Cc), lse, bias, mask, Tp // N, nH, ws, scale)
+        dqkv, dbias = ops.window_attn_bwd(qkv.view(-1, N, 3 * Cc), o, do.view(-1, N, Cc), lse, bias, mask, Tp // N, nH, ws, scale, mask_nz)
         dtable = ops.rel_bias_reduce(dbias, ws)
         dqkvb = ops.colsum(dqkv) if has_qkvb else None
         dqkvw = torch.zeros_like(qkvw, dtype=torch.float32)
@@ -108,14 +108,14 @@ class SwinBlockFn(torch.autograd.Function):
         dxw = ops.gemm(dqkv.view(Tp, 3 * Cc), _w(qkvw, dt), Tp, Cc, 3 * Cc, b_trans=True)
         dx, dn1w, dn1b = ops.ln_bwd(1, dxw, x, n1w.detach(), mean1, rstd1, dx1, B, H, W, Cc, ws, shift)
         return (dx, dn1w, dn1b, dtable, dqkvw, dqkvb, dprojw, dprojb, dn2w, dn2b, dfc1w, dfc1b, dfc2w, dfc2b,
-                None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 class WindowAttentionFn(torch.autograd.Function):
     """x_windows (B_, N, C) -> (B_, N, C): qkv Linear, attention core, proj Linear."""
 
     @staticmethod
-    def forward(ctx, xwin, table, qkvw, qkvb, projw, projb, mask, ws, nH, scale, dt):
+    def forward(ctx, xwin, table, qkvw, qkvb, projw, projb, mask, mask_nz, ws, nH, scale, dt):
         B_, N, Cc = xwin.shape
         rows = B_ * N
         xin = _f32c(xwin)
@@ -123,15 +123,15 @@ class WindowAttentionFn(torch.autograd.Function):
         xw = xw.view(rows, Cc)
         qkv = ops.gemm(xw, _w(qkvw, dt), rows, 3 * Cc, Cc, bias=None if qkvb is None else qkvb.detach())
         bias = ops.rel_bias_expand(table.detach().contiguous(), ws)
-        o, lse = ops.window_attn_fwd(qkv.view(B_, N, 3 * Cc), bias, mask, B_, nH, ws, scale)
+        o, lse = ops.window_attn_fwd(qkv.view(B_, N, 3 * Cc), bias, mask, B_, nH, ws, scale, mask_nz)
         y = ops.gemm(o.view(rows, Cc), _w(projw, dt), rows, Cc, Cc, bias=projb.detach(), out_dtype=L.F32)
-        ctx.save_for_backward(table, qkvw, projw, mask, xw, qkv, bias, o, lse)
+        ctx.save_for_backward(table, qkvw, projw, mask, mask_nz, xw, qkv, bias, o, lse)
         ctx.cfg = (B_, N, Cc, ws, nH, scale, dt, qkvb is not None, xwin.dtype)
         return y.view(B_, N, Cc).to(xwin.dtype)
 
     @staticmethod
     def backward(ctx, dy):
-        table, qkvw, projw, mask, xw, qkv, bias, o, lse = ctx.saved_tensors
+        table, qkvw, projw, mask, mask_nz, xw, qkv, bias, o, lse = ctx.saved_tensors
         B_, N, Cc, ws, nH, scale, dt, has_qkvb, in_dtype = ctx.cfg
         rows = B_ * N
         dyf = _f32c(dy)
@@ -140,13 +140,13 @@ class WindowAttentionFn(torch.autograd.Function):
         dprojw = torch.zeros_like(projw, dtype=torch.float32)
         ops.gemm(dy1, o.view(rows, Cc), Cc, Cc, rows, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dprojw)
         do = ops.gemm(dy1, _w(projw, dt), rows, Cc, Cc, b_trans=True)
-        dqkv, dbias = ops.window_attn_bwd(qkv.view(B_, N, 3 * Cc), o, do.view(B_, N, Cc), lse, bias, mask, B_, nH, ws, scale)
+        dqkv, dbias = ops.window_attn_bwd(qkv.view(B_, N, 3 * Cc), o, do.view(B_, N, Cc), lse, bias, mask, B_, nH, ws, scale, mask_nz)
         dtable = ops.rel_bias_reduce(dbias, ws)
         dqkvb = ops.colsum(dqkv) if has_qkvb else None
         dqkvw = torch.zeros_like(qkvw, dtype=torch.float32)
         ops.gemm(dqkv.view(rows, 3 * Cc), xw, 3 * Cc, Cc, rows, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dqkvw)
         dx = ops.gemm(dqkv.view(rows, 3 * Cc), _w(qkvw, dt), rows, Cc, 3 * Cc, b_trans=True, out_dtype=L.F32)
-        return dx.view(B_, N, Cc).to(in_dtype), dtable, dqkvw, dqkvb, dprojw, dprojb, None, None, None, None, None
+        return dx.view(B_, N, Cc).to(in_dtype), dtable, dqkvw, dqkvb, dprojw, dprojb, None, None, None, None, None, None
 
 
 class PatchMergingFn(torch.autograd.Function):
@@ -172,3 +172,60 @@ class PatchMergingFn(torch.autograd.Function):
         dg = ops.gemm(dy1, _w(redw, dt), T2, 4 * Cc, 2 * Cc, b_trans=True)
         dx, dnw, dnb = ops.ln_bwd(2, dg, x, nw.detach(), mean, rstd, None, B, H, W, Cc, 1, 0)
         return dx, dnw, dnb, dredw, None, None, None, None
+
+
+class PatchEmbedFn(torch.autograd.Function):
+    """img (B,Cin,Hi,Wi) -> tokens (B, Hh*Ww, C): patch unfold + GEMM (+ LayerNorm), REF:429-445, emitted directly in
+    the token-major layout the block stack consumes (no NCHW round trip)."""
+
+    @staticmethod
+    def forward(ctx, img, projw, projb, nw, nb, patch, dt, eps):
+        B, Cin, Hi, Wi = img.shape
+        img32 = _f32c(img)
+        Cc = projw.shape[0]
+        K = Cin * patch * patch
+        cols = ops.patch_gather(img32, patch, dt)
+        T = cols.shape[0]
+        y0 = ops.gemm(cols, _w(projw, dt).view(Cc, K), T, Cc, K, bias=projb.detach(), out_dtype=L.F32)
+        if nw is not None:
+            y, mean, rstd = ops.ln_fwd(0, y0, nw.detach(), nb.detach(), 1, T, 1, Cc, 1, 0, eps, L.F32)
+        else:
+            y, mean, rstd = y0, None, None
+        ctx.save_for_backward(projw, nw, cols, y0, mean, rstd)
+        ctx.cfg = (B, Cin, Hi, Wi, patch, dt, Cc, K, T, ctx.needs_input_grad[0])
+        return y.view(B, T // B, Cc)
+
+    @staticmethod
+    def backward(ctx, dy):
+        projw, nw, cols, y0, mean, rstd = ctx.saved_tensors
+        B, Cin, Hi, Wi, patch, dt, Cc, K, T, need_dimg = ctx.cfg
+        dyf = _f32c(dy).view(T, Cc)
+        dnw = dnb = None
+        if nw is not None:
+            dyf, dnw, dnb = ops.ln_bwd(0, dyf, y0, nw.detach(), mean, rstd, None, 1, T, 1, Cc, 1, 0)
+        d16 = dyf if dt == L.F32 else ops.scale_cast(dyf, None, 0, 1, T, 1, Cc, 1, 0, dt)
+        db = ops.colsum(d16)
+        dw = torch.zeros((Cc, K), dtype=torch.float32, device=dy.device)
+        ops.gemm(d16, cols, Cc, K, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dw)
+        dimg = None
+        if need_dimg:
+            dcols = ops.gemm(d16, _w(projw, dt).view(Cc, K), T, K, Cc, b_trans=True, out_dtype=L.F32)
+            dimg = ops.patch_scatter(dcols, B, Cin, Hi, Wi, patch)
+        return dimg, dw.view_as(projw), db, dnw, dnb, None, None, None
+
+
+class OutNormFn(torch.autograd.Function):
+    """norm{i}(x).view(B,H,W,C).permute(0,3,1,2).contiguous()  (REF:618-623) as one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, x, nw, nb, H, W, eps):
+        x = _f32c(x)
+        out, mean, rstd = ops.ln_nchw_fwd(x, nw.detach(), nb.detach(), H, W, eps)
+        ctx.save_for_backward(x, nw, mean, rstd)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, nw, mean, rstd = ctx.saved_tensors
+        dx, dg, db = ops.ln_nchw_bwd(_f32c(dout), x, nw.detach(), mean, rstd)
+        return dx, dg, db, None, None, None

@@ -109,6 +109,15 @@ def shift_mask(H: int, W: int, ws: int, shift: int, device) -> torch.Tensor:
     return out
 
 
+def mask_nonzero(mask: torch.Tensor) -> torch.Tensor:
+    """(nW, N, N) fp32 -> (nW,) int32 flags: 1 where the window's mask has a non-zero entry."""
+    _chk(mask)
+    flags = torch.empty((mask.shape[0],), dtype=torch.int32, device=mask.device)
+    _count()
+    L.check(L.lib().swin_mask_nonzero(_p(mask), _p(flags), mask.shape[0], mask.shape[1], _stream()), "mask_nonzero")
+    return flags
+
+
 def rel_bias_expand(table: torch.Tensor, ws: int) -> torch.Tensor:
     _chk(table)
     nH = table.shape[1]
@@ -164,6 +173,48 @@ def ln_bwd(mode: int, dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, me
     _count()
     L.check(L.lib().swin_ln_bwd(C.byref(a), _stream()), "ln_bwd")
     return dx, dgb[0], dgb[1]
+
+
+def ln_nchw_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, H: int, W: int, eps: float):
+    """x (B, H*W, C) fp32 -> (out (B, C, H, W) fp32 contiguous, mean, rstd): output norm fused with the NCHW transpose."""
+    _chk(x, gamma, beta)
+    B, Lx, Cc = x.shape
+    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+    mean = torch.empty((B * Lx,), dtype=torch.float32, device=x.device)
+    rstd = torch.empty((B * Lx,), dtype=torch.float32, device=x.device)
+    _count()
+    L.check(L.lib().swin_ln_nchw_fwd(_p(x), _p(gamma), _p(beta), _p(out), _p(mean), _p(rstd), B, Lx, Cc, eps, _stream()), "ln_nchw_fwd")
+    return out, mean, rstd
+
+
+def ln_nchw_bwd(dout: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor):
+    _chk(dout, x, gamma, mean, rstd)
+    B, Lx, Cc = x.shape
+    dx = torch.empty_like(x)
+    dgb = torch.zeros((2, Cc), dtype=torch.float32, device=x.device)
+    _count()
+    L.check(L.lib().swin_ln_nchw_bwd(_p(dout), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dgb[0]), _p(dgb[1]), B, Lx, Cc,
+                                     _stream()), "ln_nchw_bwd")
+    return dx, dgb[0], dgb[1]
+
+
+def patch_gather(img: torch.Tensor, patch: int, dtype: int) -> torch.Tensor:
+    """img (B,Cin,Hi,Wi) fp32 -> cols (B*Hh*Ww, Cin*p*p)."""
+    _chk(img)
+    B, Cin, Hi, Wi = img.shape
+    Hh, Ww = -(-Hi // patch), -(-Wi // patch)
+    cols = torch.empty((B * Hh * Ww, Cin * patch * patch), dtype=torch_dtype(dtype), device=img.device)
+    _count()
+    L.check(L.lib().swin_patch_gather(_p(img), _p(cols), B, Cin, Hi, Wi, patch, dtype, _stream()), "patch_gather")
+    return cols
+
+
+def patch_scatter(dcols: torch.Tensor, B: int, Cin: int, Hi: int, Wi: int, patch: int) -> torch.Tensor:
+    _chk(dcols)
+    dimg = torch.empty((B, Cin, Hi, Wi), dtype=torch.float32, device=dcols.device)
+    _count()
+    L.check(L.lib().swin_patch_scatter(_p(dcols), _p(dimg), B, Cin, Hi, Wi, patch, _DT[dcols.dtype], _stream()), "patch_scatter")
+    return dimg
 
 
 # ------------------------------------------------------------------ GEMM
@@ -228,26 +279,27 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
 
 # ------------------------------------------------------------------ window attention core
 def window_attn_fwd(qkv: torch.Tensor, bias: torch.Tensor, mask: Optional[torch.Tensor], B_: int, nH: int, ws: int,
-                    scale: float):
-    _chk(qkv, bias, mask)
+                    scale: float, mask_nz: Optional[torch.Tensor] = None):
+    _chk(qkv, bias, mask, mask_nz)
     N, Cc = ws * ws, nH * 32
     out = torch.empty((B_, N, Cc), dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty((B_, nH, N), dtype=torch.float32, device=qkv.device)
     a = L.AttnArgs(dtype=_DT[qkv.dtype], B_=B_, nH=nH, ws=ws, nW=0 if mask is None else mask.shape[0], scale=scale,
-                   qkv=_p(qkv), bias=_p(bias), mask=_p(mask), out=_p(out), lse=_p(lse))
+                   qkv=_p(qkv), bias=_p(bias), mask=_p(mask), mask_nz=_p(mask_nz), out=_p(out), lse=_p(lse))
     _count()
     L.check(L.lib().swin_window_attn_fwd(C.byref(a), _stream()), "window_attn_fwd")
     return out, lse
 
 
 def window_attn_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, bias: torch.Tensor,
-                    mask: Optional[torch.Tensor], B_: int, nH: int, ws: int, scale: float):
-    _chk(qkv, out, dout, lse, bias, mask)
+                    mask: Optional[torch.Tensor], B_: int, nH: int, ws: int, scale: float,
+                    mask_nz: Optional[torch.Tensor] = None):
+    _chk(qkv, out, dout, lse, bias, mask, mask_nz)
     N = ws * ws
     dqkv = torch.empty_like(qkv)
     dbias = torch.zeros((nH, N, N), dtype=torch.float32, device=qkv.device)
     a = L.AttnArgs(dtype=_DT[qkv.dtype], B_=B_, nH=nH, ws=ws, nW=0 if mask is None else mask.shape[0], scale=scale,
-                   qkv=_p(qkv), bias=_p(bias), mask=_p(mask), out=_p(out), lse=_p(lse), dout=_p(dout), dqkv=_p(dqkv),
+                   qkv=_p(qkv), bias=_p(bias), mask=_p(mask), mask_nz=_p(mask_nz), out=_p(out), lse=_p(lse), dout=_p(dout), dqkv=_p(dqkv),
                    dbias=_p(dbias))
     _count()
     L.check(L.lib().swin_window_attn_bwd(C.byref(a), _stream()), "window_attn_bwd")

@@ -21,7 +21,7 @@ import torch.utils.checkpoint as cp
 
 from . import _lib as L
 from . import ops
-from .functional import PatchMergingFn, SwinBlockFn, WindowAttentionFn
+from .functional import OutNormFn, PatchEmbedFn, PatchMergingFn, SwinBlockFn, WindowAttentionFn
 from .registry import register_backbone
 
 
@@ -131,10 +131,14 @@ class WindowAttention(nn.Module):
         _need_cuda(x, "WindowAttention")
         if self.training and any(p > 0 for p in self._drops):
             raise NotImplementedError("attention/projection dropout > 0 is not implemented in the fused kernels")
+        mask_nz = None
         if mask is not None:
             mask = mask.detach().float().contiguous()
+            mask_nz = getattr(mask, "_swin_nz", None)
+            if mask_nz is None:
+                mask_nz = ops.mask_nonzero(mask)
         return WindowAttentionFn.apply(x, self.relative_position_bias_table, self.qkv.weight, self.qkv.bias,
-                                       self.proj.weight, self.proj.bias, mask, self.window_size[0], self.num_heads,
+                                       self.proj.weight, self.proj.bias, mask, mask_nz, self.window_size[0], self.num_heads,
                                        float(self.scale), self._dt)
 
 
@@ -166,11 +170,14 @@ class SwinTransformerBlock(nn.Module):
         assert Lx == H * W, "input feature has wrong size"
         if self.training and (self._drop > 0 or any(p > 0 for p in self.attn._drops)):
             raise NotImplementedError("dropout > 0 is not implemented in the fused kernels")
-        mask = None
+        mask = mask_nz = None
         if self.shift_size > 0:
             if mask_matrix is None:
                 raise ValueError("shifted block needs mask_matrix")
             mask = mask_matrix.detach().float().contiguous()
+            mask_nz = getattr(mask_matrix, "_swin_nz", None)     # set by BasicLayer.attn_mask (cached per geometry)
+            if mask_nz is None:
+                mask_nz = ops.mask_nonzero(mask)
         s1 = s2 = None
         if isinstance(self.drop_path, DropPath):
             s1 = self.drop_path.sample_scale(x)      # attention-branch draw first, then MLP (REF:252-253)
@@ -178,7 +185,7 @@ class SwinTransformerBlock(nn.Module):
         a, m = self.attn, self.mlp
         return SwinBlockFn.apply(x, self.norm1.weight, self.norm1.bias, a.relative_position_bias_table, a.qkv.weight,
                                  a.qkv.bias, a.proj.weight, a.proj.bias, self.norm2.weight, self.norm2.bias,
-                                 m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, mask, s1, s2,
+                                 m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, mask, mask_nz, s1, s2,
                                  H, W, self.window_size, self.shift_size, self.num_heads, float(a.scale), self._dt,
                                  float(self.norm1.eps))
 
@@ -228,6 +235,7 @@ class BasicLayer(nn.Module):
         m = self._mask_cache.get(key)
         if m is None:
             m = ops.shift_mask(H, W, self.window_size, self.shift_size, device)
+            m._swin_nz = ops.mask_nonzero(m)      # per-window "mask is not all-zero" flags for the attention kernels
             if len(self._mask_cache) > 16:
                 self._mask_cache.clear()
             self._mask_cache[key] = m
@@ -246,26 +254,32 @@ class BasicLayer(nn.Module):
 
 
 class PatchEmbed(nn.Module):
-    """REF:405-445 (zero-pad to the patch multiple, 4x4/4 conv, optional LayerNorm).  SURVEY.md §8 row f1
-    ("next"): still library code (cuDNN conv + ATen LN), 0.3 % of the backbone FLOPs."""
+    """REF:405-445: zero-pad to the patch multiple, patch x patch / patch conv, optional LayerNorm.  Runs as a
+    patch-unfold gather + the GEMM kernels + the LayerNorm kernel; ``tokens()`` emits the (B, Wh*Ww, C) layout the
+    block stack consumes, ``forward()`` keeps the reference's (B, C, Wh, Ww) return."""
 
-    def __init__(self, patch_size=4, in_chans=3, embed_dim=96, norm_layer=None):
+    def __init__(self, patch_size=4, in_chans=3, embed_dim=96, norm_layer=None, compute_dtype: Optional[str] = None):
         super().__init__()
         self.patch_size = _pair(patch_size)
+        if self.patch_size[0] != self.patch_size[1]:
+            raise NotImplementedError("square patches only")
         self.in_chans, self.embed_dim = in_chans, embed_dim
         self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=self.patch_size, stride=self.patch_size)
         self.norm = norm_layer(embed_dim) if norm_layer is not None else None
+        self._dt = _dt_code(compute_dtype)
+
+    def tokens(self, x):
+        _need_cuda(x, "PatchEmbed")
+        B, _, H, W = x.shape
+        p = self.patch_size[0]
+        nw, nb = (self.norm.weight, self.norm.bias) if self.norm is not None else (None, None)
+        eps = float(self.norm.eps) if self.norm is not None else 1e-5
+        t = PatchEmbedFn.apply(x, self.proj.weight, self.proj.bias, nw, nb, p, self._dt, eps)
+        return t, -(-H // p), -(-W // p)
 
     def forward(self, x):
-        _, _, H, W = x.shape
-        ph, pw = self.patch_size
-        if W % pw or H % ph:
-            x = F.pad(x, (0, (-W) % pw, 0, (-H) % ph))
-        x = self.proj(x)
-        if self.norm is not None:
-            Wh, Ww = x.shape[2], x.shape[3]
-            x = self.norm(x.flatten(2).transpose(1, 2)).transpose(1, 2).reshape(-1, self.embed_dim, Wh, Ww)
-        return x
+        t, Wh, Ww = self.tokens(x)
+        return t.transpose(1, 2).reshape(-1, self.embed_dim, Wh, Ww)
 
 
 @register_backbone
@@ -285,7 +299,7 @@ class SwinTransformer(nn.Module):
         self.out_indices = out_indices
         self.frozen_stages = frozen_stages
         self.compute_dtype = "fp32" if _dt_code(compute_dtype) == L.F32 else "bf16"
-        self.patch_embed = PatchEmbed(patch_size, in_chans, embed_dim, norm_layer if patch_norm else None)
+        self.patch_embed = PatchEmbed(patch_size, in_chans, embed_dim, norm_layer if patch_norm else None, compute_dtype)
         if ape:
             pis, ps = _pair(pretrain_img_size), _pair(patch_size)
             self.absolute_pos_embed = nn.Parameter(torch.zeros(1, embed_dim, pis[0] // ps[0], pis[1] // ps[1]))
@@ -340,17 +354,17 @@ class SwinTransformer(nn.Module):
 
     def forward(self, x):
         _need_cuda(x, "SwinTransformer")
-        x = self.patch_embed(x.float())
-        Wh, Ww = x.shape[2], x.shape[3]
+        x, Wh, Ww = self.patch_embed.tokens(x)
         if self.ape:
-            x = x + F.interpolate(self.absolute_pos_embed, size=(Wh, Ww), mode="bicubic")
-        x = self.pos_drop(x.flatten(2).transpose(1, 2).contiguous())
+            pos = F.interpolate(self.absolute_pos_embed, size=(Wh, Ww), mode="bicubic")
+            x = x + pos.flatten(2).transpose(1, 2)
+        x = self.pos_drop(x)
         outs = []
         for i, layer in enumerate(self.layers):
             x_out, H, W, x, Wh, Ww = layer(x, Wh, Ww)
             if i in self.out_indices:
-                y = getattr(self, f"norm{i}")(x_out)
-                outs.append(y.view(-1, H, W, self.num_features[i]).permute(0, 3, 1, 2).contiguous())
+                n = getattr(self, f"norm{i}")
+                outs.append(OutNormFn.apply(x_out, n.weight, n.bias, H, W, float(n.eps)))
         return tuple(outs)
 
     def train(self, mode=True):

@@ -1,0 +1,146 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header
+declares, argument validation returns errno-style codes without touching a GPU, the Python mirror keeps the
+reference's constructor / state_dict contract, and there is no CPU fallback."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from swin_b200 import _lib
+    if not os.path.isfile(_lib.LIB_PATH):
+        _lib.build()
+    return _lib.lib()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "swin_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(swin_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from swin_b200 import _lib
+    names = header_symbols()
+    assert len(names) >= 18
+    assert sorted(_lib.SYMBOLS) == names, "ctypes table and header disagree"
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (swin_[a-z0-9_]+)", nm))
+    assert set(names) <= exported
+    assert lib.swin_version() == 100
+
+
+def test_only_sm100a_code_is_embedded():
+    from swin_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_argument_validation_is_errno_style_and_does_not_need_a_gpu(lib):
+    from swin_b200 import _lib as L
+    a = L.GemmArgs(dtype=L.F32, M=4, N=12, K=4, A=16, B=16, D=16, d_dtype=L.F32, ldd=12, lda=4, ldb=4)
+    rc = lib.swin_gemm(ctypes.byref(a), None)
+    assert rc == -22 and b"multiple of 8" in lib.swin_last_error()          # -EINVAL
+    assert lib.swin_window_gather(16, 16, 1, 7, 7, 3, 7, 0, 2, None) == -22  # row bytes not a multiple of 16
+    assert lib.swin_window_gather(16, 16, 1, 7, 7, 8, 7, 7, 2, None) == -22  # shift must be < ws
+    assert lib.swin_shift_mask(16, 0, 7, 7, 3, None) == -22
+    at = L.AttnArgs(dtype=L.BF16, B_=4, nH=3, ws=12, qkv=16, bias=16, out=16, lse=16, scale=1.0)
+    assert lib.swin_window_attn_fwd(ctypes.byref(at), None) == -22
+    assert b"window_size 7" in lib.swin_last_error()
+    with pytest.raises(RuntimeError):
+        L.check(-22, "demo")
+
+
+def test_state_dict_contract_matches_reference():
+    import swin_b200
+    d = np.load(os.path.join(GOLDEN, "backbone_tiny.npz"))
+    net = swin_b200.SwinTransformer()
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(d["swin_t_keys"])
+    assert [",".join(map(str, v.shape)) for v in sd.values()] == list(d["swin_t_shapes"])
+    assert sd["layers.0.blocks.0.attn.relative_position_index"].dtype == torch.int64
+    from oracle import swin_oracle as so
+    assert torch.equal(sd["layers.0.blocks.0.attn.relative_position_index"], torch.from_numpy(so.relative_position_index_np(7)))
+    assert sum(p.numel() for p in net.parameters()) == 27520698
+
+
+def test_constructor_contract_and_schedule():
+    import swin_b200
+    net = swin_b200.SwinTransformer(embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32], drop_path_rate=0.3,
+                                    out_indices=(1, 3), frozen_stages=2)
+    rates = [b.drop_path.drop_prob if isinstance(b.drop_path, swin_b200.DropPath) else 0.0 for l in net.layers for b in l.blocks]
+    assert np.allclose(rates, torch.linspace(0, 0.3, 24).numpy())
+    assert [b.shift_size for b in net.layers[2].blocks][:4] == [0, 3, 0, 3]
+    assert hasattr(net, "norm1") and hasattr(net, "norm3") and not hasattr(net, "norm0")
+    # frozen_stages=2 freezes patch_embed and layer 0 and keeps them in eval after .train()
+    net.train()
+    assert not net.patch_embed.proj.weight.requires_grad and not net.layers[0].blocks[0].norm1.weight.requires_grad
+    assert net.layers[1].blocks[0].norm1.weight.requires_grad
+    assert not net.patch_embed.training and not net.layers[0].training and net.layers[1].training
+    with pytest.raises(TypeError):
+        net.init_weights(pretrained=123)
+
+
+def test_paramwise_optimizer_keys_exist():
+    """configs/swin/*: weight decay 0 for names containing these substrings -> they must exist under the same names."""
+    import swin_b200
+    names = [n for n, _ in swin_b200.SwinTransformer(ape=True).named_parameters()]
+    for sub in ("absolute_pos_embed", "relative_position_bias_table", "norm"):
+        assert any(sub in n for n in names)
+
+
+def test_registry_contract():
+    import swin_b200
+    cfg = dict(type="SwinTransformer", embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7,
+               ape=False, drop_path_rate=0.1, patch_norm=True, use_checkpoint=False)
+    net = swin_b200.build_backbone(cfg)
+    assert type(net).__name__ == "SwinTransformer" and cfg["type"] == "SwinTransformer"
+    with pytest.raises(KeyError):
+        swin_b200.build_backbone(dict(type="NoSuchBackbone"))
+
+
+def test_no_cpu_fallback():
+    import swin_b200
+    net = swin_b200.SwinTransformer(embed_dim=32, depths=[2], num_heads=[1], out_indices=(0,))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 3, 32, 32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        swin_b200.window_partition(torch.zeros(1, 7, 7, 8), 7)
+    blk = swin_b200.SwinTransformerBlock(32, 1)
+    blk.H = blk.W = 7
+    with pytest.raises(RuntimeError):
+        blk(torch.zeros(1, 49, 32), None)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "swin-transformer-object-detection_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert "oracle" not in src.replace("oracle/", ""), f
+
+
+def test_drop_path_scale_semantics():
+    import swin_b200
+    dp = swin_b200.DropPath(0.25)
+    dp.train()
+    torch.manual_seed(0)
+    s = dp.sample_scale(torch.zeros(1000, 4, 8))
+    assert s.shape == (1000,) and all(min(abs(v), abs(v - 1 / 0.75)) < 1e-6 for v in s.unique().tolist())
+    assert abs((s > 0).float().mean().item() - 0.75) < 0.05
+    dp.eval()
+    assert dp.sample_scale(torch.zeros(3, 4, 8)) is None
+    torch.manual_seed(0)
+    dp.train()
+    r = 0.75 + torch.rand((1000, 1, 1))
+    torch.manual_seed(0)
+    assert torch.equal(dp.sample_scale(torch.zeros(1000, 4, 8)), (r.floor() / 0.75).reshape(-1))

@@ -132,6 +132,41 @@ def test_scale_cast_and_colsum():
     assert torch.equal(ops.cast_bf16(w), w.bfloat16())
 
 
+@pytest.mark.parametrize("C,H,W", [(96, 9, 13), (768, 5, 7), (32, 40, 33)])
+def test_ln_nchw_fwd_bwd(C, H, W):
+    ops, _ = _ops()
+    B = 2
+    rng = np.random.default_rng(9)
+    x = torch.from_numpy(rng.standard_normal((B, H * W, C)).astype(np.float32))
+    gm = torch.from_numpy((1 + 0.2 * rng.standard_normal(C)).astype(np.float32))
+    bt = torch.from_numpy((0.3 * rng.standard_normal(C)).astype(np.float32))
+    xr, gr, br = x.double().requires_grad_(True), gm.double().requires_grad_(True), bt.double().requires_grad_(True)
+    yr = so.layer_norm(xr, gr, br).reshape(B, H, W, C).permute(0, 3, 1, 2)
+    out, mean, rstd = ops.ln_nchw_fwd(x.to(DEV), gm.to(DEV), bt.to(DEV), H, W, 1e-5)
+    assert out.shape == (B, C, H, W) and out.is_contiguous()
+    assert rel(out, yr) < 1e-5
+    cot = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32))
+    (yr * cot.double()).sum().backward()
+    dx, dg, db = ops.ln_nchw_bwd(cot.to(DEV), x.to(DEV), gm.to(DEV), mean, rstd)
+    assert rel(dx, xr.grad) < 1e-5 and rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("Hi,Wi", [(50, 70), (32, 32), (17, 9)])
+def test_patch_unfold_roundtrip_and_layout(dtype, Hi, Wi):
+    ops, L = _ops()
+    code = L.F32 if dtype == "f32" else L.BF16
+    B, Cin, p = 2, 3, 4
+    img = torch.randint(-100, 100, (B, Cin, Hi, Wi)).float()
+    cols = ops.patch_gather(img.to(DEV), p, code)
+    pad = torch.nn.functional.pad(img, (0, (-Wi) % p, 0, (-Hi) % p))
+    Hh, Ww = pad.shape[2] // p, pad.shape[3] // p
+    want = pad.reshape(B, Cin, Hh, p, Ww, p).permute(0, 2, 4, 1, 3, 5).reshape(B * Hh * Ww, Cin * p * p)
+    assert torch.equal(cols.float().cpu(), want)                       # bit-exact (small integers are exact in bf16)
+    back = ops.patch_scatter(cols, B, Cin, Hi, Wi, p)
+    assert torch.equal(back.cpu(), img)
+
+
 # ---------------------------------------------------------------- GEMM
 def _gemm_ref(A, Bm, a_trans, b_trans):
     A2 = A.double().t() if a_trans else A.double()
@@ -139,7 +174,7 @@ def _gemm_ref(A, Bm, a_trans, b_trans):
     return A2 @ B2
 
 
-GEMM_SHAPES = [(300, 96, 96), (257, 288, 96), (130, 384, 200), (128, 32, 64), (1000, 256, 512), (64, 768, 3072)]
+GEMM_SHAPES = [(300, 96, 96), (257, 288, 96), (130, 384, 200), (128, 32, 64), (1000, 256, 512), (64, 768, 3072), (200, 48, 96), (96, 96, 48), (5000, 48, 48), (3000, 16, 64)]
 
 
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
