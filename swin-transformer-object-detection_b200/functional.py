@@ -13,6 +13,7 @@ fp32 LayerNorm / softmax statistics and fp32 master weights (the reference's AMP
 """
 from __future__ import annotations
 
+import weakref
 from typing import Optional
 
 import torch
@@ -20,20 +21,22 @@ import torch
 from . import _lib as L
 from . import ops
 
-_W16 = {}
+_W16 = {}     # id(param) -> (weakref(param), version, bf16 copy)
 
 
 def _w(param: torch.Tensor, dt: int) -> torch.Tensor:
-    """Operand copy of a weight in the compute dtype; bf16 shadow copies are cached per parameter version."""
+    """Operand copy of a weight in the compute dtype.  bf16 shadow copies are cached per parameter OBJECT (weakly
+    referenced, so an address reused by another model's parameter can never alias) and re-cast when the
+    parameter's version counter changes (optimizer step, load_state_dict)."""
     if dt == L.F32:
         return param.detach()
-    key = (param.data_ptr(), tuple(param.shape))
+    key = id(param)
     hit = _W16.get(key)
     ver = param._version
-    if hit is not None and hit[0] == ver:
-        return hit[1]
+    if hit is not None and hit[0]() is param and hit[1] == ver and hit[2].device == param.device:
+        return hit[2]
     w16 = ops.cast_bf16(param.detach().contiguous())
-    _W16[key] = (ver, w16)
+    _W16[key] = (weakref.ref(param, lambda _r, k=key: _W16.pop(k, None)), ver, w16)
     return w16
 
 
