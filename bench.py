@@ -205,14 +205,18 @@ def main():
         ddp.zero_grad()
         return loss
 
+    host_ms = [0.0]
+
     def timed(fn, n):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        h0 = time.perf_counter()
         for _ in range(n):
             fn()
+        host_ms[0] = (time.perf_counter() - h0) * 1e3 / max(n, 1)     # CPU time to ENQUEUE one step (no sync inside)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -238,6 +242,7 @@ def main():
     ms_total = timed(lambda: step(x_dev), K)
     launches = (ops.LAUNCHES - l0) // max(K, 1) * K
     ms_step = ms_total / K
+    host_enqueue_ms = host_ms[0]
     value = world * B * K / (ms_total / 1e3)
 
     # end to end through the public API: pinned host batch -> H2D every step, scalar loss read back every step
@@ -288,7 +293,7 @@ def main():
                        "parallelism": f"dp{world}", "l2": "inputs (205 MB/step) and activations (>10 GB/step) exceed the 126 MB L2",
                        "precision": "bf16 tcgen05 operands, fp32 accumulate/LN/softmax/residual stream, fp32 master weights"},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}))
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}))
     if world > 1:
         dist.destroy_process_group()
 

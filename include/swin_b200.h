@@ -136,9 +136,10 @@ int swin_gemm(const swin_gemm_args* a, void* stream);
 int swin_colsum(const void* X, int M, int N, int64_t ld, int dtype, float* colsum, void* stream);
 
 /* y = row_scale[b] * x, fp32 -> dtype; mode 0 rows 1:1, mode 1 gathered into window slots (pad slots 0)
- * (the backward of the residual/scatter epilogues: dY for fc2 / proj). */
+ * (the backward of the residual/scatter epilogues: dY for fc2 / proj).  If colsum != NULL it also ACCUMULATES
+ * colsum[c] += sum_rows y[row, c] (the bias gradient of that Linear; fp32, caller zero-fills). */
 int swin_scale_cast(const float* x, void* y, const float* row_scale, int mode, int B, int H, int W, int C, int ws,
-                    int shift, int y_dtype, void* stream);
+                    int shift, int y_dtype, float* colsum, void* stream);
 /* fp32 -> bf16 copy (weights shadow copies), n elements */
 int swin_cast_bf16(const float* x, void* y, int64_t n, void* stream);
 

@@ -11,7 +11,7 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libswin_b200.so")
+LIB_PATH = os.environ.get("SWIN_B200_LIB") or os.path.join(_HERE, "libswin_b200.so")   # env override: development builds only
 CSRC = os.path.join(_HERE, "csrc")
 
 F32, BF16 = 0, 1
@@ -63,7 +63,7 @@ SYMBOLS = {
     "swin_patch_scatter": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp]),
     "swin_gemm": (c_int, [C.POINTER(GemmArgs), vp]),
     "swin_colsum": (c_int, [vp, c_int, c_int, c_i64, c_int, vp, vp]),
-    "swin_scale_cast": (c_int, [vp, vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, vp]),
+    "swin_scale_cast": (c_int, [vp, vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp]),
     "swin_cast_bf16": (c_int, [vp, vp, c_i64, vp]),
     "swin_window_attn_fwd": (c_int, [C.POINTER(AttnArgs), vp]),
     "swin_window_attn_bwd": (c_int, [C.POINTER(AttnArgs), vp]),

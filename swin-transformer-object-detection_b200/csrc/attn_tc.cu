@@ -46,23 +46,54 @@ __device__ __forceinline__ void store_row_bf16x8(uint8_t* dst, const float* v) {
   *reinterpret_cast<int4*>(dst) = pk;
 }
 
+// Thread mapping shared by both kernels: 256 threads = 8 warps.  Warp w owns TMEM lane quarter q = w & 3 (rows
+// q*32..q*32+31 of the stacked tile) and column half hf = w >> 2 of the row's own 64-column window block, so two
+// threads cooperate on one row (row statistics are exchanged through smem).  This doubles the warps available to
+// hide the LDS / TMEM / MUFU latencies of the per-row softmax math.
+constexpr int kBiasLd = 52;                      // sBias row pitch (floats): 16-byte aligned rows, pre-scaled by log2(e)
+constexpr int kAttnThreads = 256;
+
+__device__ __forceinline__ void load_bias_tile(float* sBias, const float* __restrict__ bias, int h) {
+  const float kLog2e = 1.4426950408889634f;
+  for (int e = threadIdx.x; e < AN * kBiasLd; e += blockDim.x) {
+    const int i = e / kBiasLd, j = e - i * kBiasLd;
+    sBias[e] = j < AN ? bias[((size_t)h * AN + i) * AN + j] * kLog2e : 0.f;
+  }
+}
+
+// Development aid: -DSWIN_ATTN_TIMING accumulates per-phase clock64() deltas of one softmax thread of CTA 0 and
+// prints them at kernel exit (never enabled in the shipped library).
+#ifdef SWIN_ATTN_TIMING
+#define TDECL long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tprev = clock64(); int titems = 0;
+#define TMARK(k) do { if (blockIdx.x == 0 && tid == 40) { long long t_ = clock64(); tacc[k] += t_ - tprev; tprev = t_; } } while (0)
+#define TITEM ++titems;
+#define TPRINT(name) do { if (blockIdx.x == 0 && tid == 40) printf("%s items=%d cycles/item: load+S %lld | tmem_ld %lld | math1 %lld | sync1 %lld | math2 %lld | Pstore+sync %lld | mmaO wait %lld | epilogue %lld | endsync %lld\n", name, titems, tacc[0] / titems, tacc[1] / titems, tacc[2] / titems, tacc[3] / titems, tacc[4] / titems, tacc[5] / titems, tacc[6] / titems, tacc[7] / titems, tacc[8] / titems); } while (0)
+#else
+#define TDECL
+#define TMARK(k)
+#define TITEM
+#define TPRINT(name)
+#endif
+
 // ------------------------------------------------------------------------------------------ forward
 constexpr uint32_t kFwdTiles = 3 * kTileBytes;     // Q,K,V per buffer
 
-__global__ void __launch_bounds__(128, 3) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnTcParams p) {
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[4];
   __shared__ uint32_t tmem_slot;
+  __shared__ float sRed[2][2][128];                       // [max|sum][half][row]
   uint8_t* sbase = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sT = sbase;                                   // 2 x {Q,K,V}
   uint8_t* sP = sT + 2 * kFwdTiles;                      // 16 KB
-  float* sBias = reinterpret_cast<float*>(sP + kPBytes); // [49][49]
-  const int tid = threadIdx.x, warp = tid >> 5;
+  float* sBias = reinterpret_cast<float*>(sP + kPBytes); // [49][52]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hf = warp >> 2;
   const int h = blockIdx.x % p.nH, g = blockIdx.x / p.nH;
   const uint32_t bar_load0 = smem_u32(&bars[0]), bar_s = smem_u32(&bars[2]), bar_o = smem_u32(&bars[3]);
 
   zero_smem(sT, 2 * kFwdTiles + kPBytes);
-  for (int e = tid; e < AN * AN; e += blockDim.x) sBias[e] = p.bias[(size_t)h * AN * AN + e];
+  load_bias_tile(sBias, p.bias, h);
   if (tid == 0) {
     mbar_init(bar_load0, 1); mbar_init(bar_load0 + 8, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
     fence_barrier_init();
@@ -74,13 +105,15 @@ __global__ void __launch_bounds__(128, 3) attn_tc_fwd_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tS = tmem_slot, tO = tmem_slot;          // O overlays S columns [0,64) once P is in smem
-  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_off = (uint32_t)(q * 32) << 16;
 
-  const int r = tid, wloc = r >> 6, i = r & 63;
+  const int r = q * 32 + lane, wloc = r >> 6, i = r & 63;
+  const int jbase = hf * 32;
   const uint32_t idesc_s = umma_idesc_bf16(128, false, false);
   const uint32_t idesc_o = umma_idesc_bf16(64, false, true);
   const uint32_t aT = smem_u32(sT), aP = smem_u32(sP);
   const float kLog2e = 1.4426950408889634f;
+  const float sc2 = p.scale * kLog2e;
 
   auto issue_loads = [&](int pair, int buf) {
     const uint32_t bar = bar_load0 + 8 * buf, base = aT + buf * kFwdTiles;
@@ -94,11 +127,13 @@ __global__ void __launch_bounds__(128, 3) attn_tc_fwd_kernel(const __grid_consta
     }
   };
   if (tid == 0 && g < p.npairs) issue_loads(g, 0);
+  TDECL
 
   uint32_t it = 0;
   for (int pair = g; pair < p.npairs; pair += p.ctas_per_head, ++it) {
     const uint32_t ph = it & 1, buf = it & 1, lph = (it >> 1) & 1;
     const uint32_t aQ = aT + buf * kFwdTiles, aK = aQ + kTileBytes, aV = aK + kTileBytes;
+    TITEM
     if (tid == 0) {
       if (pair + p.ctas_per_head < p.npairs) issue_loads(pair + p.ctas_per_head, buf ^ 1);
       mbar_wait(bar_load0 + 8 * buf, lph);
@@ -117,38 +152,61 @@ __global__ void __launch_bounds__(128, 3) attn_tc_fwd_kernel(const __grid_consta
     }
     mbar_wait(bar_s, ph);
     tc_fence_after();
-    uint32_t v[64];
-    tmem_ld32(tS + lane_off + wloc * 64, v);
-    tmem_ld32(tS + lane_off + wloc * 64 + 32, v + 32);
+    TMARK(0);
+    uint32_t v[32];
+    tmem_ld32(tS + lane_off + wloc * 64 + jbase, v);
     tmem_ld_wait();
-    float mx = -INFINITY, sum = 0.f;
+    TMARK(1);
+    float sv[32];
+    float mx = -INFINITY;
     if (valid) {
-      const float* brow = sBias + i * AN;
-      const float sc2 = p.scale * kLog2e;
+      const float4* b4 = reinterpret_cast<const float4*>(sBias + i * kBiasLd + jbase);
 #pragma unroll
-      for (int j = 0; j < AN; ++j) {
-        float s = fmaf(__uint_as_float(v[j]), sc2, brow[j] * kLog2e);
-        if (mrow) s = fmaf(__ldg(mrow + j), kLog2e, s);
-        v[j] = __float_as_uint(s);
-        mx = fmaxf(mx, s);
+      for (int c = 0; c < 8; ++c) {
+        if (jbase + 4 * c < kBiasLd) {
+          const float4 bb = b4[c];
+          sv[4 * c + 0] = fmaf(__uint_as_float(v[4 * c + 0]), sc2, bb.x);
+          sv[4 * c + 1] = fmaf(__uint_as_float(v[4 * c + 1]), sc2, bb.y);
+          sv[4 * c + 2] = fmaf(__uint_as_float(v[4 * c + 2]), sc2, bb.z);
+          sv[4 * c + 3] = fmaf(__uint_as_float(v[4 * c + 3]), sc2, bb.w);
+        } else {
+          sv[4 * c + 0] = sv[4 * c + 1] = sv[4 * c + 2] = sv[4 * c + 3] = 0.f;
+        }
+      }
+      if (mrow != nullptr) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj)
+          if (jbase + jj < AN) sv[jj] = fmaf(__ldg(mrow + jbase + jj), kLog2e, sv[jj]);
       }
 #pragma unroll
-      for (int j = 0; j < AN; ++j) {
-        float e = exp2f(__uint_as_float(v[j]) - mx);
-        sum += e;
-        v[j] = __float_as_uint(e);
-      }
+      for (int jj = 0; jj < 32; ++jj)
+        if (jbase + jj < AN) mx = fmaxf(mx, sv[jj]);
+    }
+    sRed[0][hf][r] = mx;
+    TMARK(2);
+    __syncthreads();
+    TMARK(3);
+    float sum = 0.f;
+    if (valid) {
+      mx = fmaxf(sRed[0][0][r], sRed[0][1][r]);
 #pragma unroll
-      for (int j = AN; j < 64; ++j) v[j] = 0u;
+      for (int jj = 0; jj < 32; ++jj) {
+        float e = 0.f;
+        if (jbase + jj < AN) { e = exp2f(sv[jj] - mx); sum += e; }
+        sv[jj] = e;
+      }
     } else {
 #pragma unroll
-      for (int j = 0; j < 64; ++j) v[j] = 0u;
+      for (int jj = 0; jj < 32; ++jj) sv[jj] = 0.f;
     }
+    sRed[1][hf][r] = sum;
+    TMARK(4);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) store_row_bf16x8(sP + sw128_off(r, c), reinterpret_cast<const float*>(v + 8 * c));
+    for (int c = 0; c < 4; ++c) store_row_bf16x8(sP + sw128_off(r, hf * 4 + c), sv + 8 * c);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    TMARK(5);
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
@@ -156,48 +214,55 @@ __global__ void __launch_bounds__(128, 3) attn_tc_fwd_kernel(const __grid_consta
         umma_bf16(tO, umma_desc(aP + kk * 32, 16, 1024, kSw128), umma_desc(aV + kk * 1024, 4096, 512, kSw64), idesc_o, kk);
       umma_commit(bar_o);
     }
+    sum = sRed[1][0][r] + sRed[1][1][r];
     mbar_wait(bar_o, ph);
     tc_fence_after();
-    uint32_t o[32];
-    tmem_ld32(tO + lane_off + wloc * 32, o);
+    TMARK(6);
+    uint32_t o[16];
+    tmem_ld16(tO + lane_off + wloc * 32 + hf * 16, o);
     tmem_ld_wait();
     if (valid) {
       const float inv = 1.0f / sum;
-      __nv_bfloat16* orow = p.out + ((size_t)win * AN + i) * p.C + h * AHD;
+      uint8_t* orow = reinterpret_cast<uint8_t*>(p.out + ((size_t)win * AN + i) * p.C + h * AHD + hf * 16);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float t[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) t[e] = __uint_as_float(o[8 * c + e]) * inv;
-        store_row_bf16x8(reinterpret_cast<uint8_t*>(orow) + 16 * c, t);
+        store_row_bf16x8(orow + 16 * c, t);
       }
-      p.lse[((size_t)win * p.nH + h) * AN + i] = (mx + log2f(sum)) * 0.6931471805599453f;   // natural-log LSE
+      if (hf == 0) p.lse[((size_t)win * p.nH + h) * AN + i] = (mx + log2f(sum)) * 0.6931471805599453f;   // natural-log LSE
     }
+    TMARK(7);
     tc_fence_before();
     __syncthreads();
+    TMARK(8);
   }
+  TPRINT("attn_fwd");
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_slot, 128); }
 }
 
 // ------------------------------------------------------------------------------------------ backward
 constexpr uint32_t kBwdTiles = 4 * kTileBytes;     // Q,K,V,dO per buffer
 
-__global__ void __launch_bounds__(128, 2) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
-                                                              const __grid_constant__ CUtensorMap tmDO, AttnTcParams p) {
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                                       const __grid_constant__ CUtensorMap tmDO, AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[4];
   __shared__ uint32_t tmem_slot;
+  __shared__ float sRed[2][128];                          // partial D per column half
   uint8_t* sbase = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sT = sbase;                     // 2 x {Q,K,V,dO}
   uint8_t* sP = sT + 2 * kBwdTiles;
   uint8_t* sdS = sP + kPBytes;
   float* sBias = reinterpret_cast<float*>(sdS + kPBytes);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hf = warp >> 2;
   const int h = blockIdx.x % p.nH, g = blockIdx.x / p.nH;
   const uint32_t bar_load0 = smem_u32(&bars[0]), bar_s = smem_u32(&bars[2]), bar_o = smem_u32(&bars[3]);
 
   zero_smem(sT, 2 * kBwdTiles + 2 * kPBytes);
-  for (int e = tid; e < AN * AN; e += blockDim.x) sBias[e] = p.bias[(size_t)h * AN * AN + e];
+  load_bias_tile(sBias, p.bias, h);
   if (tid == 0) {
     mbar_init(bar_load0, 1); mbar_init(bar_load0 + 8, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
     fence_barrier_init();
@@ -211,14 +276,16 @@ __global__ void __launch_bounds__(128, 2) attn_tc_bwd_kernel(const __grid_consta
   tc_fence_after();
   const uint32_t tS = tmem_slot, tdP = tmem_slot + 128;
   const uint32_t tdV = tmem_slot, tdK = tmem_slot + 64, tdQ = tmem_slot + 128;   // reuse S / dP columns after the softmax pass
-  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_off = (uint32_t)(q * 32) << 16;
 
-  const int r = tid, wloc = r >> 6, i = r & 63;
+  const int r = q * 32 + lane, wloc = r >> 6, i = r & 63;
+  const int jbase = hf * 32;
   const uint32_t idesc_s = umma_idesc_bf16(128, false, false);
   const uint32_t idesc_tt = umma_idesc_bf16(64, true, true);     // A^T B, both MN-major
   const uint32_t idesc_nt = umma_idesc_bf16(64, false, true);
   const uint32_t aT = smem_u32(sT), aP = smem_u32(sP), adS = smem_u32(sdS);
   const float kLog2e = 1.4426950408889634f;
+  const float sc2 = p.scale * kLog2e;
 
   auto issue_loads = [&](int pair, int buf) {
     const uint32_t bar = bar_load0 + 8 * buf, base = aT + buf * kBwdTiles;
@@ -234,14 +301,16 @@ __global__ void __launch_bounds__(128, 2) attn_tc_bwd_kernel(const __grid_consta
   };
   if (tid == 0 && g < p.npairs) issue_loads(g, 0);
 
-  float db[AN];
+  float db[32];
 #pragma unroll
-  for (int j = 0; j < AN; ++j) db[j] = 0.f;
+  for (int j = 0; j < 32; ++j) db[j] = 0.f;
+  TDECL
 
   uint32_t it = 0;
   for (int pair = g; pair < p.npairs; pair += p.ctas_per_head, ++it) {
     const uint32_t ph = it & 1, buf = it & 1, lph = (it >> 1) & 1;
     const uint32_t aQ = aT + buf * kBwdTiles, aK = aQ + kTileBytes, aV = aK + kTileBytes, adO = aV + kTileBytes;
+    TITEM
     if (tid == 0) {
       if (pair + p.ctas_per_head < p.npairs) issue_loads(pair + p.ctas_per_head, buf ^ 1);
       mbar_wait(bar_load0 + 8 * buf, lph);
@@ -257,7 +326,6 @@ __global__ void __launch_bounds__(128, 2) attn_tc_bwd_kernel(const __grid_consta
     const int win = 2 * pair + wloc;
     const bool valid = (i < AN) && (win < p.B_);
     const float lse2 = valid ? p.lse[((size_t)win * p.nH + h) * AN + i] * kLog2e : 0.f;
-    const float* brow = sBias + (valid ? i : 0) * AN;
     const float* mrow = nullptr;
     if (p.mask != nullptr && valid) {
       const int mw = win % p.nW;
@@ -265,56 +333,67 @@ __global__ void __launch_bounds__(128, 2) attn_tc_bwd_kernel(const __grid_consta
     }
     mbar_wait(bar_s, ph);
     tc_fence_after();
-    // pass 1: P row (kept in registers, fp32) and D_i = sum_j P_ij dP_ij from the SAME P and dP that form dS,
-    // so that sum_j dS_ij == 0 up to fp32 rounding (no bf16-rounded O in the cancellation)
-    float pr[64];
+    TMARK(0);
+    uint32_t s[32], dp[32];
+    tmem_ld32(tS + lane_off + wloc * 64 + jbase, s);
+    tmem_ld32(tdP + lane_off + wloc * 64 + jbase, dp);
+    tmem_ld_wait();
+    TMARK(1);
+    // P for this thread's 32 columns (fp32, registers) and the partial D = sum_j P_ij dP_ij, taken from the SAME
+    // P and dP that form dS so that sum_j dS_ij == 0 up to fp32 rounding
+    float pr[32];
     float delta = 0.f;
-    const float sc2 = p.scale * kLog2e;
+    if (valid) {
+      const float4* b4 = reinterpret_cast<const float4*>(sBias + i * kBiasLd + jbase);
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t s[32], dp[32];
-      tmem_ld32(tS + lane_off + wloc * 64 + half * 32, s);
-      tmem_ld32(tdP + lane_off + wloc * 64 + half * 32, dp);
-      tmem_ld_wait();
+      for (int c = 0; c < 8; ++c) {
+        if (jbase + 4 * c < kBiasLd) {
+          const float4 bb = b4[c];
+          pr[4 * c + 0] = fmaf(__uint_as_float(s[4 * c + 0]), sc2, bb.x);
+          pr[4 * c + 1] = fmaf(__uint_as_float(s[4 * c + 1]), sc2, bb.y);
+          pr[4 * c + 2] = fmaf(__uint_as_float(s[4 * c + 2]), sc2, bb.z);
+          pr[4 * c + 3] = fmaf(__uint_as_float(s[4 * c + 3]), sc2, bb.w);
+        } else {
+          pr[4 * c + 0] = pr[4 * c + 1] = pr[4 * c + 2] = pr[4 * c + 3] = 0.f;
+        }
+      }
+      if (mrow != nullptr) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj)
+          if (jbase + jj < AN) pr[jj] = fmaf(__ldg(mrow + jbase + jj), kLog2e, pr[jj]);
+      }
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj) {
-        const int j = half * 32 + jj;
         float pv = 0.f;
-        if (valid && j < AN) {
-          float sv = fmaf(__uint_as_float(s[jj]), sc2, brow[j < AN ? j : 0] * kLog2e);
-          if (mrow) sv = fmaf(__ldg(mrow + (j < AN ? j : 0)), kLog2e, sv);
-          pv = exp2f(sv - lse2);
-          delta = fmaf(pv, __uint_as_float(dp[jj]), delta);
-        }
-        pr[j] = pv;
+        if (jbase + jj < AN) { pv = exp2f(pr[jj] - lse2); delta = fmaf(pv, __uint_as_float(dp[jj]), delta); }
+        pr[jj] = pv;
       }
+    } else {
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) pr[jj] = 0.f;
     }
-    // pass 2: dS = P * (dP - D); P and scale*dS rows -> smem (bf16, 128-byte swizzle)
+    sRed[hf][r] = delta;
+    TMARK(2);
+    __syncthreads();
+    TMARK(3);
+    delta = sRed[0][r] + sRed[1][r];
+    float dsv[32];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t dp[32];
-      tmem_ld32(tdP + lane_off + wloc * 64 + half * 32, dp);
-      tmem_ld_wait();
-      float dsv[32];
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        const int j = half * 32 + jj;
-        float ds = 0.f;
-        if (j < AN) {
-          ds = pr[j] * (__uint_as_float(dp[jj]) - delta);
-          db[j < AN ? j : 0] += ds;
-        }
-        dsv[jj] = ds * p.scale;
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        store_row_bf16x8(sP + sw128_off(r, half * 4 + c), pr + half * 32 + 8 * c);
-        store_row_bf16x8(sdS + sw128_off(r, half * 4 + c), dsv + 8 * c);
-      }
+    for (int jj = 0; jj < 32; ++jj) {
+      const float ds = pr[jj] * (__uint_as_float(dp[jj]) - delta);
+      db[jj] += ds;
+      dsv[jj] = ds * p.scale;
     }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      store_row_bf16x8(sP + sw128_off(r, hf * 4 + c), pr + 8 * c);
+      store_row_bf16x8(sdS + sw128_off(r, hf * 4 + c), dsv + 8 * c);
+    }
+    TMARK(4);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    TMARK(5);
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
@@ -330,24 +409,31 @@ __global__ void __launch_bounds__(128, 2) attn_tc_bwd_kernel(const __grid_consta
     }
     mbar_wait(bar_o, ph);
     tc_fence_after();
+    TMARK(6);
+    uint32_t o[3][16];
+    tmem_ld16(tdQ + lane_off + wloc * 32 + hf * 16, o[0]);
+    tmem_ld16(tdK + lane_off + wloc * 32 + hf * 16, o[1]);
+    tmem_ld16(tdV + lane_off + wloc * 32 + hf * 16, o[2]);
+    tmem_ld_wait();
+    if (valid) {
 #pragma unroll
-    for (int part = 0; part < 3; ++part) {   // 0: dQ, 1: dK, 2: dV  (column blocks of dqkv)
-      uint32_t o[32];
-      tmem_ld32((part == 0 ? tdQ : part == 1 ? tdK : tdV) + lane_off + wloc * 32, o);
-      tmem_ld_wait();
-      if (valid) {
-        uint8_t* orow = reinterpret_cast<uint8_t*>(p.dqkv + ((size_t)win * AN + i) * 3 * p.C + part * p.C + h * AHD);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) store_row_bf16x8(orow + 16 * c, reinterpret_cast<const float*>(o + 8 * c));
+      for (int part = 0; part < 3; ++part) {   // 0: dQ, 1: dK, 2: dV  (column blocks of dqkv)
+        uint8_t* orow = reinterpret_cast<uint8_t*>(p.dqkv + ((size_t)win * AN + i) * 3 * p.C + part * p.C + h * AHD + hf * 16);
+        store_row_bf16x8(orow, reinterpret_cast<const float*>(o[part]));
+        store_row_bf16x8(orow + 16, reinterpret_cast<const float*>(o[part] + 8));
       }
     }
+    TMARK(7);
     tc_fence_before();
     __syncthreads();
+    TMARK(8);
   }
+  TPRINT("attn_bwd");
   if (i < AN) {
-    float* dst = p.dbias + ((size_t)h * AN + i) * AN;
+    float* dst = p.dbias + ((size_t)h * AN + i) * AN + jbase;
 #pragma unroll
-    for (int j = 0; j < AN; ++j) atomicAdd(dst + j, db[j]);
+    for (int jj = 0; jj < 32; ++jj)
+      if (jbase + jj < AN) atomicAdd(dst + jj, db[jj]);
   }
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_slot, 256); }
 }
@@ -362,7 +448,7 @@ static int attn_tc_common(const swin_attn_args* a, AttnTcParams* out, bool bwd, 
   AttnTcParams p;
   p.B_ = a->B_; p.nH = a->nH; p.nW = a->nW > 0 ? a->nW : 1; p.C = a->nH * AHD; p.scale = a->scale;
   p.npairs = (a->B_ + 1) / 2;
-  int per_head = ceil_div(kNumSMs * ctas_per_sm, a->nH);
+  int per_head = (kNumSMs * ctas_per_sm) / a->nH;     // floor: the whole grid must be co-resident (one wave, no tail CTA)
   if (per_head > p.npairs) per_head = p.npairs;
   if (per_head < 1) per_head = 1;
   p.ctas_per_head = per_head;
@@ -375,20 +461,20 @@ static int attn_tc_common(const swin_attn_args* a, AttnTcParams* out, bool bwd, 
 
 int attn_tc_fwd(const swin_attn_args* a, cudaStream_t st) {
   AttnTcParams p;
-  int rc = attn_tc_common(a, &p, false, 3);
+  int rc = attn_tc_common(a, &p, false, 2);
   if (rc) return rc;
   if (p.B_ == 0) return 0;
   CUtensorMap tm;
   rc = make_tmap_bf16_2d(&tm, a->qkv, (uint64_t)3 * p.C, (uint64_t)p.B_ * AN, (uint64_t)3 * p.C * 2, AHD, AN, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
-  const size_t smem = 2 * kFwdTiles + kPBytes + AN * AN * sizeof(float) + 1024;
+  const size_t smem = 2 * kFwdTiles + kPBytes + AN * kBiasLd * sizeof(float) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
-  attn_tc_fwd_kernel<<<p.nH * p.ctas_per_head, 128, smem, st>>>(tm, p);
+  attn_tc_fwd_kernel<<<p.nH * p.ctas_per_head, kAttnThreads, smem, st>>>(tm, p);
   SWIN_LAUNCH_CHECK();
   return 0;
 }
@@ -403,14 +489,14 @@ int attn_tc_bwd(const swin_attn_args* a, cudaStream_t st) {
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmdo, a->dout, (uint64_t)p.C, (uint64_t)p.B_ * AN, (uint64_t)p.C * 2, AHD, AN, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
-  const size_t smem = 2 * kBwdTiles + 2 * kPBytes + AN * AN * sizeof(float) + 1024;
+  const size_t smem = 2 * kBwdTiles + 2 * kPBytes + AN * kBiasLd * sizeof(float) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
-  attn_tc_bwd_kernel<<<p.nH * p.ctas_per_head, 128, smem, st>>>(tm, tmdo, p);
+  attn_tc_bwd_kernel<<<p.nH * p.ctas_per_head, kAttnThreads, smem, st>>>(tm, tmdo, p);
   SWIN_LAUNCH_CHECK();
   return 0;
 }

@@ -171,38 +171,49 @@ template <> struct Vec4IO<__nv_bfloat16> {
   }
 };
 
+// A row of the LN is handled by a group of G lanes (G = 8, 16 or 32) holding VPL float4 each, so a warp works on
+// 32/G rows at once: for the narrow stage-0/1 rows (C = 96, 192) this quadruples / doubles the loads in flight
+// per warp, which is what these HBM-bound kernels are limited by.
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // Forward.  Iteration rows: mode 0 -> LN rows; mode 1 -> window SLOTS (pad slots get zeros);
 // mode 2 -> merged rows.
-template <int VPL, typename YT>
+template <int VPL, int G, typename YT>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, YT* __restrict__ y,
                                                      float* __restrict__ mean, float* __restrict__ rstd, LnGeom lg) {
-  const int lane = threadIdx.x & 31;
+  constexpr int R = 32 / G;                  // rows per warp
+  const int lane = threadIdx.x & 31, gl = lane % G, gi = lane / G;
   const int wpb = blockDim.x >> 5;
   const int vps = lg.C >> 2;                 // float4 per segment
   const int vrow = vps * lg.nseg;            // float4 per LN row
   const float inv_n = 1.0f / (float)(lg.C * lg.nseg);
   const int per_img_slots = lg.g.nW * lg.g.N, per_img_tok = lg.g.H * lg.g.W;
-  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < lg.rows; row += (long long)gridDim.x * wpb) {
-    long long stat_row = row;
-    long long src0 = row;
-    if (lg.mode == 1) {
+  for (long long base = ((long long)blockIdx.x * wpb + (threadIdx.x >> 5)) * R; base < lg.rows; base += (long long)gridDim.x * wpb * R) {
+    const long long row = base + gi;
+    const bool inr = row < lg.rows;
+    long long stat_row = row, src0 = row;
+    bool pad = false;
+    if (lg.mode == 1 && inr) {
       int b = (int)(row / per_img_slots);
       int t = slot_to_token(lg.g, (int)(row - (long long)b * per_img_slots));
-      if (t < 0) {                           // zero padding AFTER the norm (REF:211 then :218)
-        for (int v = lane; v < vrow; v += 32) Vec4IO<YT>::st(y, row * vrow + v, make_float4(0.f, 0.f, 0.f, 0.f));
-        continue;
-      }
-      src0 = (long long)b * per_img_tok + t;
+      pad = t < 0;                           // zero padding AFTER the norm (REF:211 then :218)
+      src0 = (long long)b * per_img_tok + (pad ? 0 : t);
       stat_row = src0;
     }
+    const bool act = inr && !pad;
     float4 r[VPL];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
-      int v = lane + 32 * k;
+      const int v = gl + G * k;
       r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (v < vrow) {
+      if (act && v < vrow) {
         long long srow = src0;
         int off = v;
         if (lg.mode == 2) { int q = v / vps; off = v - q * vps; srow = merge_src(lg, row, q); }
@@ -210,28 +221,31 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
         s += r[k].x + r[k].y + r[k].z + r[k].w;
       }
     }
-    const float mu = warp_sum(s) * inv_n;
+    const float mu = group_sum<G>(s) * inv_n;
     float q2 = 0.f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
-      if (lane + 32 * k < vrow) {
+      if (gl + G * k < vrow) {
         float a = r[k].x - mu, b2 = r[k].y - mu, c = r[k].z - mu, d = r[k].w - mu;
         q2 += a * a + b2 * b2 + c * c + d * d;
       }
     }
-    const float rs = rsqrtf(warp_sum(q2) * inv_n + lg.eps);
-    if (lane == 0) { mean[stat_row] = mu; rstd[stat_row] = rs; }
+    const float rs = rsqrtf(group_sum<G>(q2) * inv_n + lg.eps);
+    if (act && gl == 0) { mean[stat_row] = mu; rstd[stat_row] = rs; }
+    if (!inr) continue;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
-      int v = lane + 32 * k;
+      const int v = gl + G * k;
       if (v < vrow) {
-        float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + v);
-        float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + v);
-        float4 o;
-        o.x = (r[k].x - mu) * rs * gm.x + bt.x;
-        o.y = (r[k].y - mu) * rs * gm.y + bt.y;
-        o.z = (r[k].z - mu) * rs * gm.z + bt.z;
-        o.w = (r[k].w - mu) * rs * gm.w + bt.w;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!pad) {
+          float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + v);
+          float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + v);
+          o.x = (r[k].x - mu) * rs * gm.x + bt.x;
+          o.y = (r[k].y - mu) * rs * gm.y + bt.y;
+          o.z = (r[k].z - mu) * rs * gm.z + bt.z;
+          o.w = (r[k].w - mu) * rs * gm.w + bt.w;
+        }
         Vec4IO<YT>::st(y, row * vrow + v, o);
       }
     }
@@ -241,14 +255,15 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 // Backward.  Iteration rows: mode 0 -> LN rows; mode 1 -> TOKENS (dy read through token->slot);
 // mode 2 -> merged rows (dx scattered to the 4 source tokens; pad segments dropped).
 // dx = (dres) + rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += dy*xhat; dbeta += dy.
-template <int VPL, typename YT>
+template <int VPL, int G, typename YT>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const YT* __restrict__ dy, const float* __restrict__ x,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const float* __restrict__ dres,
                                                      float* __restrict__ dx, float* __restrict__ dgamma,
                                                      float* __restrict__ dbeta, LnGeom lg) {
   extern __shared__ float sred[];            // [2][vrow*4] block partials
-  const int lane = threadIdx.x & 31;
+  constexpr int R = 32 / G;
+  const int lane = threadIdx.x & 31, gl = lane % G, gi = lane / G;
   const int wpb = blockDim.x >> 5;
   const int vps = lg.C >> 2;
   const int vrow = vps * lg.nseg;
@@ -260,21 +275,23 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const YT* __restrict__ dy, 
   float4 ag[VPL], ab[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) { ag[k] = make_float4(0.f, 0.f, 0.f, 0.f); ab[k] = ag[k]; }
-  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < lg.rows; row += (long long)gridDim.x * wpb) {
+  for (long long base = ((long long)blockIdx.x * wpb + (threadIdx.x >> 5)) * R; base < lg.rows; base += (long long)gridDim.x * wpb * R) {
+    const long long row = base + gi;
+    const bool inr = row < lg.rows;
     long long dyrow = row;
-    if (lg.mode == 1) {
+    if (lg.mode == 1 && inr) {
       int b = (int)(row / per_img_tok);
       dyrow = (long long)b * per_img_slots + token_to_slot(lg.g, (int)(row - (long long)b * per_img_tok));
     }
-    const float mu = mean[row], rs = rstd[row];
+    const float mu = inr ? mean[row] : 0.f, rs = inr ? rstd[row] : 0.f;
     float4 xh[VPL], gd[VPL];
     long long srow_k[VPL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
-      int v = lane + 32 * k;
+      const int v = gl + G * k;
       xh[k] = make_float4(0.f, 0.f, 0.f, 0.f); gd[k] = xh[k]; srow_k[k] = -1;
-      if (v < vrow) {
+      if (inr && v < vrow) {
         long long srow = row; int off = v;
         if (lg.mode == 2) { int q = v / vps; off = v - q * vps; srow = merge_src(lg, row, q); }
         srow_k[k] = srow < 0 ? -1 : srow * vps + off;
@@ -290,7 +307,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const YT* __restrict__ dy, 
         ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
       }
     }
-    const float m1 = warp_sum(s1) * inv_n, m2 = warp_sum(s2) * inv_n;
+    const float m1 = group_sum<G>(s1) * inv_n, m2 = group_sum<G>(s2) * inv_n;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       if (srow_k[k] >= 0) {
@@ -310,7 +327,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const YT* __restrict__ dy, 
   // block reduce of dgamma / dbeta partials, then one atomic per column per block
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
-    int v = lane + 32 * k;
+    const int v = gl + G * k;
     if (v < vrow) {
       atomicAdd(&sred[v * 4 + 0], ag[k].x); atomicAdd(&sred[v * 4 + 1], ag[k].y);
       atomicAdd(&sred[v * 4 + 2], ag[k].z); atomicAdd(&sred[v * 4 + 3], ag[k].w);
@@ -344,20 +361,32 @@ static int ln_geom(const swin_ln_args* a, bool bwd, LnGeom* out) {
   return 0;
 }
 
+// lanes per row: the smallest of 8/16/32 that keeps <= 4 float4 per lane (else 32 with more per lane)
+static void ln_shape(int vrow, int* G, int* vpl) {
+  int g = 8;
+  while (g < 32 && vrow > g * 4) g *= 2;
+  *G = g;
+  *vpl = ceil_div(vrow, g);
+}
+
+#define LN_CASES(X)                                                                                     \
+  X(1, 8) X(2, 8) X(3, 8) X(4, 8) X(3, 16) X(4, 16) X(3, 32) X(4, 32) X(6, 32) X(8, 32) X(12, 32) X(16, 32) \
+  X(24, 32) X(32, 32)
+
 template <typename YT>
 static int ln_fwd_dispatch(const swin_ln_args* a, const LnGeom& lg, cudaStream_t st) {
-  int vrow = lg.C / 4 * lg.nseg;
-  int vpl = ceil_div(vrow, 32);
-  long long blocks = ceil_div64(lg.rows, 8);
+  int vrow = lg.C / 4 * lg.nseg, G, vpl;
+  ln_shape(vrow, &G, &vpl);
+  const int rows_per_block = 8 * (32 / G);
+  long long blocks = ceil_div64(lg.rows, rows_per_block);
   int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
-#define LN_FWD_CASE(V)                                                                                         \
-  if (vpl <= V) {                                                                                              \
-    ln_fwd_kernel<V, YT><<<grid, 256, 0, st>>>(a->x, a->gamma, a->beta, (YT*)a->y, a->mean, a->rstd, lg);      \
-    SWIN_LAUNCH_CHECK();                                                                                       \
-    return 0;                                                                                                  \
+#define LN_FWD_CASE(V, GG)                                                                                    \
+  if (G == GG && vpl <= V) {                                                                                  \
+    ln_fwd_kernel<V, GG, YT><<<grid, 256, 0, st>>>(a->x, a->gamma, a->beta, (YT*)a->y, a->mean, a->rstd, lg); \
+    SWIN_LAUNCH_CHECK();                                                                                      \
+    return 0;                                                                                                 \
   }
-  LN_FWD_CASE(1) LN_FWD_CASE(2) LN_FWD_CASE(3) LN_FWD_CASE(4) LN_FWD_CASE(6) LN_FWD_CASE(8)
-  LN_FWD_CASE(12) LN_FWD_CASE(16) LN_FWD_CASE(24) LN_FWD_CASE(32)
+  LN_CASES(LN_FWD_CASE)
 #undef LN_FWD_CASE
   set_error("ln: row width %d too large", vrow * 4);
   return -EINVAL;
@@ -365,21 +394,21 @@ static int ln_fwd_dispatch(const swin_ln_args* a, const LnGeom& lg, cudaStream_t
 
 template <typename YT>
 static int ln_bwd_dispatch(const swin_ln_args* a, const LnGeom& lg, cudaStream_t st) {
-  int vrow = lg.C / 4 * lg.nseg;
-  int vpl = ceil_div(vrow, 32);
-  long long blocks = ceil_div64(lg.rows, 8 * 16);   // each warp walks >= 16 rows so the atomics amortise
+  int vrow = lg.C / 4 * lg.nseg, G, vpl;
+  ln_shape(vrow, &G, &vpl);
+  const int rows_per_block = 8 * (32 / G);
+  long long blocks = ceil_div64(lg.rows, (long long)rows_per_block * 16);   // each lane group walks >= 16 rows so the atomics amortise
   int grid = (int)(blocks < (long long)kNumSMs * 4 ? blocks : (long long)kNumSMs * 4);
   if (grid < 1) grid = 1;
   size_t smem = (size_t)2 * vrow * 4 * sizeof(float);
-#define LN_BWD_CASE(V)                                                                                         \
-  if (vpl <= V) {                                                                                              \
-    ln_bwd_kernel<V, YT><<<grid, 256, smem, st>>>((const YT*)a->dy, a->x, a->gamma, a->mean, a->rstd, a->dres, \
-                                                  a->dx, a->dgamma, a->dbeta, lg);                             \
-    SWIN_LAUNCH_CHECK();                                                                                       \
-    return 0;                                                                                                  \
+#define LN_BWD_CASE(V, GG)                                                                                         \
+  if (G == GG && vpl <= V) {                                                                                       \
+    ln_bwd_kernel<V, GG, YT><<<grid, 256, smem, st>>>((const YT*)a->dy, a->x, a->gamma, a->mean, a->rstd, a->dres, \
+                                                      a->dx, a->dgamma, a->dbeta, lg);                             \
+    SWIN_LAUNCH_CHECK();                                                                                           \
+    return 0;                                                                                                      \
   }
-  LN_BWD_CASE(1) LN_BWD_CASE(2) LN_BWD_CASE(3) LN_BWD_CASE(4) LN_BWD_CASE(6) LN_BWD_CASE(8)
-  LN_BWD_CASE(12) LN_BWD_CASE(16) LN_BWD_CASE(24) LN_BWD_CASE(32)
+  LN_CASES(LN_BWD_CASE)
 #undef LN_BWD_CASE
   set_error("ln: row width %d too large", vrow * 4);
   return -EINVAL;
@@ -391,11 +420,20 @@ static int ln_bwd_dispatch(const swin_ln_args* a, const LnGeom& lg, cudaStream_t
 template <typename YT>
 __global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict__ x, YT* __restrict__ y,
                                                          const float* __restrict__ row_scale, int mode, WinGeom g,
-                                                         long long rows) {
+                                                         long long rows, float* __restrict__ colsum) {
+  extern __shared__ float scol[];           // [C] block partial column sums (only when colsum != nullptr)
+  constexpr int kMaxV = 8;                  // C <= 1024
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int vrow = g.C >> 2;
   const int per_img_slots = g.nW * g.N, per_img_tok = g.H * g.W;
+  float4 acc[kMaxV];
+#pragma unroll
+  for (int k = 0; k < kMaxV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (colsum != nullptr) {
+    for (int i = threadIdx.x; i < g.C; i += blockDim.x) scol[i] = 0.f;
+    __syncthreads();
+  }
   for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
     long long srow = row;
     int b;
@@ -411,10 +449,28 @@ __global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict
       continue;
     }
     const float sc = row_scale ? row_scale[b] : 1.0f;
-    for (int v = lane; v < vrow; v += 32) {
-      float4 t = Vec4IO<float>::ld(x, srow * vrow + v);
-      Vec4IO<YT>::st(y, row * vrow + v, make_float4(t.x * sc, t.y * sc, t.z * sc, t.w * sc));
+#pragma unroll
+    for (int k = 0; k < kMaxV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < vrow) {
+        float4 t = Vec4IO<float>::ld(x, srow * vrow + v);
+        t = make_float4(t.x * sc, t.y * sc, t.z * sc, t.w * sc);
+        Vec4IO<YT>::st(y, row * vrow + v, t);
+        acc[k].x += t.x; acc[k].y += t.y; acc[k].z += t.z; acc[k].w += t.w;
+      }
     }
+  }
+  if (colsum != nullptr) {
+#pragma unroll
+    for (int k = 0; k < kMaxV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < vrow) {
+        atomicAdd(&scol[4 * v + 0], acc[k].x); atomicAdd(&scol[4 * v + 1], acc[k].y);
+        atomicAdd(&scol[4 * v + 2], acc[k].z); atomicAdd(&scol[4 * v + 3], acc[k].w);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < g.C; i += blockDim.x) atomicAdd(colsum + i, scol[i]);
   }
 }
 
@@ -534,18 +590,20 @@ extern "C" int swin_ln_bwd(const swin_ln_args* a, void* stream) {
 }
 
 extern "C" int swin_scale_cast(const float* x, void* y, const float* row_scale, int mode, int B, int H, int W, int C, int ws,
-                               int shift, int y_dtype, void* stream) {
+                               int shift, int y_dtype, float* colsum, void* stream) {
   SWIN_REQUIRE(mode == 0 || mode == 1, "scale_cast: bad mode");
-  SWIN_REQUIRE(C % 4 == 0 && B > 0 && H > 0 && W > 0, "scale_cast: bad shape");
+  SWIN_REQUIRE(C % 4 == 0 && C <= 1024 && B > 0 && H > 0 && W > 0, "scale_cast: bad shape (C %% 4 == 0, C <= 1024)");
   SWIN_REQUIRE(aligned16(x) && aligned16(y), "scale_cast: alignment");
   if (mode == 0) { ws = 1; shift = 0; }
   SWIN_REQUIRE(ws > 0 && shift >= 0 && shift < ws, "scale_cast: bad window geometry");
   WinGeom g = make_geom(B, H, W, C, ws, shift);
   long long rows = mode == 1 ? (long long)B * g.nW * g.N : (long long)B * H * W;
-  long long blocks = ceil_div64(rows, 8);
+  long long blocks = ceil_div64(rows, 8 * 8);
   int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
-  if (y_dtype == SWIN_F32) scale_cast_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (float*)y, row_scale, mode, g, rows);
-  else if (y_dtype == SWIN_BF16) scale_cast_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, row_scale, mode, g, rows);
+  if (grid < 1) grid = 1;
+  size_t smem = colsum ? (size_t)C * sizeof(float) : 0;
+  if (y_dtype == SWIN_F32) scale_cast_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(x, (float*)y, row_scale, mode, g, rows, colsum);
+  else if (y_dtype == SWIN_BF16) scale_cast_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, row_scale, mode, g, rows, colsum);
   else { set_error("scale_cast: bad dtype"); return -EINVAL; }
   SWIN_LAUNCH_CHECK();
   return 0;

@@ -31,39 +31,62 @@ __global__ void __launch_bounds__(256) patch_unfold_kernel(float* __restrict__ i
 }
 
 // ------------------------------------------------------------------------------------------ LN + NCHW store
+// A block owns a tile of 32 consecutive tokens.  Each token is normalised by a group of G lanes holding VPL float4
+// (like the LN kernels in elementwise.cu), so 8 warps x 32/G tokens are in flight per round; the tile is then
+// written (read) channel-major so that global accesses are 128-byte rows of 32 tokens.
 constexpr int kTokTile = 32;
-constexpr int kMaxVpl = 32;      // C <= 1024
 
+template <int G>
+__device__ __forceinline__ float group_sum_e(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int VPL, int G>
 __global__ void __launch_bounds__(256) ln_nchw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float* __restrict__ out,
                                                           float* __restrict__ mean, float* __restrict__ rstd, int L, int C, float eps) {
   extern __shared__ float tile[];            // [C][33]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int R = 32 / G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G, gi = lane / G;
   const int b = blockIdx.y, t0 = blockIdx.x * kTokTile;
-  const int vpl = (C + 31) / 32;
+  const int vrow = C >> 2;
   const float inv_n = 1.0f / (float)C;
-  for (int tt = warp; tt < kTokTile; tt += 8) {
+#pragma unroll 1
+  for (int tt = warp * R + gi; tt < kTokTile; tt += 8 * R) {
     const int t = t0 + tt;
-    if (t >= L) break;
-    const float* row = x + ((long long)b * L + t) * C;
-    float r[kMaxVpl];
+    const bool act = t < L;
+    const float4* row = reinterpret_cast<const float4*>(x + ((long long)b * L + (act ? t : 0)) * C);
+    float4 r[VPL];
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxVpl; ++k) {
-      r[k] = 0.f;
-      if (k < vpl && lane + 32 * k < C) { r[k] = __ldg(row + lane + 32 * k); s += r[k]; }
+    for (int k = 0; k < VPL; ++k) {
+      const int v = gl + G * k;
+      r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (act && v < vrow) { r[k] = __ldg(row + v); s += r[k].x + r[k].y + r[k].z + r[k].w; }
     }
-    const float mu = warp_sum(s) * inv_n;
+    const float mu = group_sum_e<G>(s) * inv_n;
     float q2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxVpl; ++k)
-      if (k < vpl && lane + 32 * k < C) { float d = r[k] - mu; q2 += d * d; }
-    const float rs = rsqrtf(warp_sum(q2) * inv_n + eps);
-    if (lane == 0) { mean[(long long)b * L + t] = mu; rstd[(long long)b * L + t] = rs; }
+    for (int k = 0; k < VPL; ++k)
+      if (gl + G * k < vrow) {
+        float a = r[k].x - mu, b2 = r[k].y - mu, c2 = r[k].z - mu, d = r[k].w - mu;
+        q2 += a * a + b2 * b2 + c2 * c2 + d * d;
+      }
+    const float rs = rsqrtf(group_sum_e<G>(q2) * inv_n + eps);
+    if (act && gl == 0) { mean[(long long)b * L + t] = mu; rstd[(long long)b * L + t] = rs; }
 #pragma unroll
-    for (int k = 0; k < kMaxVpl; ++k) {
-      const int c = lane + 32 * k;
-      if (k < vpl && c < C) tile[c * 33 + tt] = (r[k] - mu) * rs * __ldg(gamma + c) + __ldg(beta + c);
+    for (int k = 0; k < VPL; ++k) {
+      const int v = gl + G * k;
+      if (act && v < vrow) {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + v), bt = __ldg(reinterpret_cast<const float4*>(beta) + v);
+        const int c = 4 * v;
+        tile[(c + 0) * 33 + tt] = (r[k].x - mu) * rs * gm.x + bt.x;
+        tile[(c + 1) * 33 + tt] = (r[k].y - mu) * rs * gm.y + bt.y;
+        tile[(c + 2) * 33 + tt] = (r[k].z - mu) * rs * gm.z + bt.z;
+        tile[(c + 3) * 33 + tt] = (r[k].w - mu) * rs * gm.w + bt.w;
+      }
     }
   }
   __syncthreads();
@@ -72,6 +95,7 @@ __global__ void __launch_bounds__(256) ln_nchw_fwd_kernel(const float* __restric
     for (int c = warp; c < C; c += 8) out[((long long)b * C + c) * L + t] = tile[c * 33 + lane];
 }
 
+template <int VPL, int G>
 __global__ void __launch_bounds__(256) ln_nchw_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x,
                                                           const float* __restrict__ gamma, const float* __restrict__ mean,
                                                           const float* __restrict__ rstd, float* __restrict__ dx,
@@ -79,14 +103,15 @@ __global__ void __launch_bounds__(256) ln_nchw_bwd_kernel(const float* __restric
                                                           int tiles_per_block) {
   extern __shared__ float tile[];            // [C][33] + [2][C] partials
   float* sred = tile + (size_t)C * 33;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int R = 32 / G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G, gi = lane / G;
   const int b = blockIdx.y;
-  const int vpl = (C + 31) / 32;
+  const int vrow = C >> 2;
   const float inv_n = 1.0f / (float)C;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
-  float ag[kMaxVpl], ab[kMaxVpl];
+  float4 ag[VPL], ab[VPL];
 #pragma unroll
-  for (int k = 0; k < kMaxVpl; ++k) { ag[k] = 0.f; ab[k] = 0.f; }
+  for (int k = 0; k < VPL; ++k) { ag[k] = make_float4(0.f, 0.f, 0.f, 0.f); ab[k] = ag[k]; }
   for (int tb = 0; tb < tiles_per_block; ++tb) {
     const int t0 = (blockIdx.x * tiles_per_block + tb) * kTokTile;
     if (t0 >= L) break;
@@ -96,42 +121,64 @@ __global__ void __launch_bounds__(256) ln_nchw_bwd_kernel(const float* __restric
       for (int c = warp; c < C; c += 8) tile[c * 33 + lane] = (t < L) ? __ldg(dout + ((long long)b * C + c) * L + t) : 0.f;
     }
     __syncthreads();
-    for (int tt = warp; tt < kTokTile; tt += 8) {
+#pragma unroll 1
+    for (int tt = warp * R + gi; tt < kTokTile; tt += 8 * R) {
       const int t = t0 + tt;
-      if (t >= L) break;
-      const long long rowi = (long long)b * L + t;
+      const bool act = t < L;
+      const long long rowi = (long long)b * L + (act ? t : 0);
       const float mu = mean[rowi], rs = rstd[rowi];
-      float xh[kMaxVpl], gd[kMaxVpl];
+      const float4* xrow = reinterpret_cast<const float4*>(x + rowi * C);
+      float4 xh[VPL], gd[VPL];
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int k = 0; k < kMaxVpl; ++k) {
-        const int c = lane + 32 * k;
-        xh[k] = 0.f; gd[k] = 0.f;
-        if (k < vpl && c < C) {
-          const float d = tile[c * 33 + tt];
-          xh[k] = (__ldg(x + rowi * C + c) - mu) * rs;
-          gd[k] = d * __ldg(gamma + c);
-          s1 += gd[k]; s2 += gd[k] * xh[k];
-          ag[k] += d * xh[k]; ab[k] += d;
+      for (int k = 0; k < VPL; ++k) {
+        const int v = gl + G * k;
+        xh[k] = make_float4(0.f, 0.f, 0.f, 0.f); gd[k] = xh[k];
+        if (act && v < vrow) {
+          const int c = 4 * v;
+          const float4 d = make_float4(tile[(c + 0) * 33 + tt], tile[(c + 1) * 33 + tt], tile[(c + 2) * 33 + tt], tile[(c + 3) * 33 + tt]);
+          const float4 xv = __ldg(xrow + v);
+          const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + v);
+          xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+          gd[k] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+          s1 += gd[k].x + gd[k].y + gd[k].z + gd[k].w;
+          s2 += gd[k].x * xh[k].x + gd[k].y * xh[k].y + gd[k].z * xh[k].z + gd[k].w * xh[k].w;
+          ag[k].x += d.x * xh[k].x; ag[k].y += d.y * xh[k].y; ag[k].z += d.z * xh[k].z; ag[k].w += d.w * xh[k].w;
+          ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
         }
       }
-      const float m1 = warp_sum(s1) * inv_n, m2 = warp_sum(s2) * inv_n;
+      const float m1 = group_sum_e<G>(s1) * inv_n, m2 = group_sum_e<G>(s2) * inv_n;
 #pragma unroll
-      for (int k = 0; k < kMaxVpl; ++k) {
-        const int c = lane + 32 * k;
-        if (k < vpl && c < C) dx[rowi * C + c] = rs * (gd[k] - m1 - xh[k] * m2);
+      for (int k = 0; k < VPL; ++k) {
+        const int v = gl + G * k;
+        if (act && v < vrow)
+          reinterpret_cast<float4*>(dx + rowi * C)[v] = make_float4(rs * (gd[k].x - m1 - xh[k].x * m2), rs * (gd[k].y - m1 - xh[k].y * m2),
+                                                                    rs * (gd[k].z - m1 - xh[k].z * m2), rs * (gd[k].w - m1 - xh[k].w * m2));
       }
     }
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < kMaxVpl; ++k) {
-    const int c = lane + 32 * k;
-    if (k < vpl && c < C) { atomicAdd(&sred[c], ag[k]); atomicAdd(&sred[C + c], ab[k]); }
+  for (int k = 0; k < VPL; ++k) {
+    const int v = gl + G * k;
+    if (v < vrow) {
+      atomicAdd(&sred[4 * v + 0], ag[k].x); atomicAdd(&sred[4 * v + 1], ag[k].y);
+      atomicAdd(&sred[4 * v + 2], ag[k].z); atomicAdd(&sred[4 * v + 3], ag[k].w);
+      atomicAdd(&sred[C + 4 * v + 0], ab[k].x); atomicAdd(&sred[C + 4 * v + 1], ab[k].y);
+      atomicAdd(&sred[C + 4 * v + 2], ab[k].z); atomicAdd(&sred[C + 4 * v + 3], ab[k].w);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) { atomicAdd(dgamma + i, sred[i]); atomicAdd(dbeta + i, sred[C + i]); }
 }
+
+static void nchw_shape(int vrow, int* G, int* vpl) {
+  int g = 8;
+  while (g < 32 && vrow > g * 4) g *= 2;
+  *G = g;
+  *vpl = (vrow + g - 1) / g;
+}
+#define NCHW_CASES(X) X(1, 8) X(2, 8) X(3, 8) X(4, 8) X(3, 16) X(4, 16) X(3, 32) X(4, 32) X(6, 32) X(8, 32)
 
 }  // namespace swin
 
@@ -169,28 +216,48 @@ extern "C" int swin_patch_scatter(const void* dcols, float* dimg, int B, int Cin
 
 extern "C" int swin_ln_nchw_fwd(const float* x, const float* gamma, const float* beta, float* out, float* mean, float* rstd, int B,
                                 int L, int C, float eps, void* stream) {
-  SWIN_REQUIRE(B > 0 && L > 0 && C > 0 && C <= 32 * kMaxVpl, "ln_nchw: bad shape (C <= 1024)");
+  SWIN_REQUIRE(B > 0 && L > 0 && C > 0 && C % 4 == 0 && C <= 1024, "ln_nchw: bad shape (C %% 4 == 0, C <= 1024)");
   SWIN_REQUIRE(x && gamma && beta && out && mean && rstd, "ln_nchw: null pointer");
+  SWIN_REQUIRE(aligned16(x) && aligned16(gamma) && aligned16(beta), "ln_nchw: alignment");
   size_t smem = (size_t)C * 33 * sizeof(float);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(ln_nchw_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
+  int G, vpl;
+  nchw_shape(C / 4, &G, &vpl);
   dim3 grid(ceil_div(L, kTokTile), B);
-  ln_nchw_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, gamma, beta, out, mean, rstd, L, C, eps);
-  SWIN_LAUNCH_CHECK();
-  return 0;
+#define NCHW_FWD(V, GG)                                                                                                   \
+  if (G == GG && vpl <= V) {                                                                                              \
+    static bool attr = false;                                                                                             \
+    if (!attr) { cudaFuncSetAttribute(ln_nchw_fwd_kernel<V, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; } \
+    ln_nchw_fwd_kernel<V, GG><<<grid, 256, smem, (cudaStream_t)stream>>>(x, gamma, beta, out, mean, rstd, L, C, eps);      \
+    SWIN_LAUNCH_CHECK();                                                                                                  \
+    return 0;                                                                                                             \
+  }
+  NCHW_CASES(NCHW_FWD)
+#undef NCHW_FWD
+  set_error("ln_nchw: unsupported C %d", C);
+  return -EINVAL;
 }
 extern "C" int swin_ln_nchw_bwd(const float* dout, const float* x, const float* gamma, const float* mean, const float* rstd,
                                 float* dx, float* dgamma, float* dbeta, int B, int L, int C, void* stream) {
-  SWIN_REQUIRE(B > 0 && L > 0 && C > 0 && C <= 32 * kMaxVpl, "ln_nchw: bad shape (C <= 1024)");
+  SWIN_REQUIRE(B > 0 && L > 0 && C > 0 && C % 4 == 0 && C <= 1024, "ln_nchw: bad shape (C %% 4 == 0, C <= 1024)");
   SWIN_REQUIRE(dout && x && gamma && mean && rstd && dx && dgamma && dbeta, "ln_nchw_bwd: null pointer");
+  SWIN_REQUIRE(aligned16(x) && aligned16(dx) && aligned16(gamma), "ln_nchw_bwd: alignment");
   size_t smem = ((size_t)C * 33 + 2 * C) * sizeof(float);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(ln_nchw_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
   int tiles = ceil_div(L, kTokTile);
-  int tpb = ceil_div(tiles * B, kNumSMs * 4);      // a few tiles per block so the dgamma/dbeta atomics amortise
+  int tpb = ceil_div(tiles * B, kNumSMs * 16);     // a few tiles per block so the dgamma/dbeta atomics amortise
   if (tpb < 1) tpb = 1;
   dim3 grid(ceil_div(tiles, tpb), B);
-  ln_nchw_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dout, x, gamma, mean, rstd, dx, dgamma, dbeta, L, C, tpb);
-  SWIN_LAUNCH_CHECK();
-  return 0;
+  int G, vpl;
+  nchw_shape(C / 4, &G, &vpl);
+#define NCHW_BWD(V, GG)                                                                                                   \
+  if (G == GG && vpl <= V) {                                                                                              \
+    static bool attr = false;                                                                                             \
+    if (!attr) { cudaFuncSetAttribute(ln_nchw_bwd_kernel<V, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; } \
+    ln_nchw_bwd_kernel<V, GG><<<grid, 256, smem, (cudaStream_t)stream>>>(dout, x, gamma, mean, rstd, dx, dgamma, dbeta, L, C, tpb); \
+    SWIN_LAUNCH_CHECK();                                                                                                  \
+    return 0;                                                                                                             \
+  }
+  NCHW_CASES(NCHW_BWD)
+#undef NCHW_BWD
+  set_error("ln_nchw: unsupported C %d", C);
+  return -EINVAL;
 }

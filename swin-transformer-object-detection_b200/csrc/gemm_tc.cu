@@ -25,11 +25,84 @@ struct GemmTcParams {
   EpiParams epi;
 };
 
+
+// One 32x32 accumulator chunk in the coalesced layout: lane = 4 consecutive columns (piece) of rows
+// rr = 4*i + rsub, i = 0..7.  All smem/global loads of the 8 rows are issued before any dependent math so
+// each lane keeps 8 independent memory operations in flight (the serial version was latency-bound).
+template <int EPI>
+__device__ __forceinline__ void epi_chunk(const EpiParams& p, const float4* __restrict__ stage, const long long* __restrict__ rowdst,
+                                          const float* __restrict__ rowscale, int col, int rsub, int piece) {
+  if (col >= p.N) return;
+  float4 a[8];
+  long long off[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = 4 * i + rsub;
+    a[i] = stage[rr * 8 + (piece ^ (rr & 7))];
+    const long long dr = rowdst[rr];
+    off[i] = dr < 0 ? -1 : dr * p.ldd + col;
+  }
+  if (p.bias != nullptr) {
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i].x += b4.x; a[i].y += b4.y; a[i].z += b4.z; a[i].w += b4.w; }
+  }
+  if (EPI == SWIN_EPI_STORE) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (off[i] >= 0) store4(p.D, p.d_dtype, off[i], a[i]);
+  } else if (EPI == SWIN_EPI_GELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (off[i] < 0) continue;
+      float4 g, d;
+      gelu_fast(a[i].x, &g.x, &d.x); gelu_fast(a[i].y, &g.y, &d.y); gelu_fast(a[i].z, &g.z, &d.z); gelu_fast(a[i].w, &g.w, &d.w);
+      store4(p.D2, p.d_dtype, off[i], a[i]);
+      store4(p.D, p.d_dtype, off[i], g);
+    }
+  } else if (EPI == SWIN_EPI_RESIDUAL || EPI == SWIN_EPI_SCATTER_RESIDUAL) {
+    // all 8 residual loads are issued unconditionally (clamped address, read-only path) BEFORE any use, so they
+    // overlap; a predicated load-then-convert sequence gets serialised by in-order issue
+    float4 r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + (off[i] >= 0 ? off[i] : 0)));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (off[i] < 0) continue;
+      const float sc = rowscale[4 * i + rsub];
+      store4(p.D, SWIN_F32, off[i], make_float4(fmaf(sc, a[i].x, r[i].x), fmaf(sc, a[i].y, r[i].y), fmaf(sc, a[i].z, r[i].z), fmaf(sc, a[i].w, r[i].w)));
+    }
+  } else if (EPI == SWIN_EPI_DGELU) {
+    float4 u[8];
+    if (p.d_dtype == SWIN_BF16) {
+      uint2 raw[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) raw[i] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + (off[i] >= 0 ? off[i] : 0)));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] = make_float4(bf16_lo(raw[i].x), bf16_hi(raw[i].x), bf16_lo(raw[i].y), bf16_hi(raw[i].y));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + (off[i] >= 0 ? off[i] : 0)));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (off[i] < 0) continue;
+      float4 g, d;
+      gelu_fast(u[i].x, &g.x, &d.x); gelu_fast(u[i].y, &g.y, &d.y); gelu_fast(u[i].z, &g.z, &d.z); gelu_fast(u[i].w, &g.w, &d.w);
+      store4(p.D, p.d_dtype, off[i], make_float4(a[i].x * d.x, a[i].y * d.y, a[i].z * d.z, a[i].w * d.w));
+    }
+  } else {  // SWIN_EPI_ATOMIC_ADD
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (off[i] >= 0) atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + off[i]), a[i]);
+  }
+}
+
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB, GemmTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 8];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float4 epi_stage[kEpiWarps][32 * 8];     // per-epilogue-warp 32x32 fp32 transpose stage (4 KB each)
   __shared__ long long epi_rowdst[kEpiWarps][32];
@@ -43,11 +116,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto empty_bar = [&](int s) { return smem_u32(&bars[kMaxStages + s]); };
   auto tfull_bar = [&](int s) { return smem_u32(&bars[2 * kMaxStages + s]); };
-  auto tempty_bar = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 2 + s]); };
+  auto tempty_bar = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 4 + s]); };
+  const uint32_t acc_stride = p.block_n <= 128 ? 128u : 256u;      // TMEM columns per accumulator stage
+  const uint32_t num_acc = 512u / acc_stride;                       // 4 or 2 stages in flight
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
+    for (int s = 0; s < 4; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -101,10 +176,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         const int ks = unit % p.splits;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        const uint32_t acc = u & 1, acc_ph = (u >> 1) & 1;
+        const uint32_t acc = u % num_acc, acc_ph = (u / num_acc) & 1;
         mbar_wait(tempty_bar(acc), acc_ph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
+        const uint32_t d_tmem = tmem_base + acc * acc_stride;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
@@ -138,7 +213,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
       const int row_base = m_blk * TBM + q * 32;
       const int n0 = n_blk * p.block_n;
-      const uint32_t acc = u & 1, acc_ph = (u >> 1) & 1;
+      const uint32_t acc = u % num_acc, acc_ph = (u / num_acc) & 1;
       {
         long long drow = 0; float scale = 1.f;
         const bool live = epi_row_setup(p.epi, row_base + lane, &drow, &scale);
@@ -148,26 +223,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       __syncwarp();
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
       const int piece = lane & 7, rsub = lane >> 3;
-      for (int c = chunk_sel * 32; c < p.block_n; c += 64) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c, v);
+      uint32_t v[32];
+      int c = chunk_sel * 32;
+      if (c < p.block_n) tmem_ld32(taddr + c, v);
+      for (; c < p.block_n; c += 64) {
         tmem_ld_wait();
 #pragma unroll
         for (int pc = 0; pc < 8; ++pc)
           stage[lane * 8 + (pc ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * pc]), __uint_as_float(v[4 * pc + 1]),
                                                             __uint_as_float(v[4 * pc + 2]), __uint_as_float(v[4 * pc + 3]));
         __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = 4 * i + rsub;
-          const float4 a = stage[rr * 8 + (piece ^ (rr & 7))];
-          const long long drow = epi_rowdst[ew][rr];
-          if (drow >= 0) {
-            const float av[4] = {a.x, a.y, a.z, a.w};
-            epilogue_cols<4, true>(p.epi, row_base + rr, drow, epi_rowscale[ew][rr], n0 + c + piece * 4, av);
-          }
+        if (c + 64 < p.block_n) tmem_ld32(taddr + c + 64, v);      // next chunk's TMEM read overlaps this chunk's stores
+        const int col = n0 + c + piece * 4;
+        switch (p.epi.epilogue) {
+          case SWIN_EPI_STORE: epi_chunk<SWIN_EPI_STORE>(p.epi, stage, epi_rowdst[ew], epi_rowscale[ew], col, rsub, piece); break;
+          case SWIN_EPI_GELU: epi_chunk<SWIN_EPI_GELU>(p.epi, stage, epi_rowdst[ew], epi_rowscale[ew], col, rsub, piece); break;
+          case SWIN_EPI_RESIDUAL:
+          case SWIN_EPI_SCATTER_RESIDUAL: epi_chunk<SWIN_EPI_RESIDUAL>(p.epi, stage, epi_rowdst[ew], epi_rowscale[ew], col, rsub, piece); break;
+          case SWIN_EPI_DGELU: epi_chunk<SWIN_EPI_DGELU>(p.epi, stage, epi_rowdst[ew], epi_rowscale[ew], col, rsub, piece); break;
+          default: epi_chunk<SWIN_EPI_ATOMIC_ADD>(p.epi, stage, epi_rowdst[ew], epi_rowscale[ew], col, rsub, piece); break;
         }
         __syncwarp();
       }

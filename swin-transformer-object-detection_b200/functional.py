@@ -87,8 +87,7 @@ class SwinBlockFn(torch.autograd.Function):
         Tp = xw.shape[0] * N
         dx2 = _f32c(dx2)
         # ---- MLP branch
-        dy2 = ops.scale_cast(dx2, s2, 0, B, H, W, Cc, 1, 0, dt)                         # (T, C)
-        dfc2b = ops.colsum(dy2)
+        dy2, dfc2b = ops.scale_cast(dx2, s2, 0, B, H, W, Cc, 1, 0, dt, want_colsum=True)  # (T, C) + bias grad in one pass
         dfc2w = torch.zeros_like(fc2w, dtype=torch.float32)
         ops.gemm(dy2, h, Cc, hid, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc2w)
         du = ops.gemm(dy2, _w(fc2w, dt), T, hid, Cc, b_trans=True, epilogue=L.EPI_DGELU, aux=u)
@@ -98,8 +97,7 @@ class SwinBlockFn(torch.autograd.Function):
         dxn = ops.gemm(du, _w(fc1w, dt), T, Cc, hid, b_trans=True)
         dx1, dn2w, dn2b = ops.ln_bwd(0, dxn, x1, n2w.detach(), mean2, rstd2, dx2, B, H, W, Cc, 1, 0)
         # ---- attention branch
-        dy1 = ops.scale_cast(dx1, s1, 1, B, H, W, Cc, ws, shift, dt)                    # (Tp, C), pad slots 0
-        dprojb = ops.colsum(dy1)
+        dy1, dprojb = ops.scale_cast(dx1, s1, 1, B, H, W, Cc, ws, shift, dt, want_colsum=True)  # (Tp, C), pad slots 0
         dprojw = torch.zeros_like(projw, dtype=torch.float32)
         ops.gemm(dy1, o, Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dprojw)
         do = ops.gemm(dy1, _w(projw, dt), Tp, Cc, Cc, b_trans=True)

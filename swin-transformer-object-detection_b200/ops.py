@@ -254,7 +254,9 @@ def colsum(X: torch.Tensor) -> torch.Tensor:
 
 
 def scale_cast(x: torch.Tensor, row_scale: Optional[torch.Tensor], mode: int, B: int, H: int, W: int, Cc: int, ws: int,
-               shift: int, y_dtype: int) -> torch.Tensor:
+               shift: int, y_dtype: int, want_colsum: bool = False):
+    """fp32 -> y_dtype cast with per-image scale (mode 1: gathered into window slots).  With want_colsum also returns the
+    fp32 column sums of the result (the bias gradient), computed in the same pass."""
     _chk(x, row_scale)
     assert x.dtype == torch.float32
     if mode == 1:
@@ -263,9 +265,10 @@ def scale_cast(x: torch.Tensor, row_scale: Optional[torch.Tensor], mode: int, B:
     else:
         rows = B * H * W
     y = torch.empty((rows, Cc), dtype=torch_dtype(y_dtype), device=x.device)
+    cs = torch.zeros((Cc,), dtype=torch.float32, device=x.device) if want_colsum else None
     _count()
-    L.check(L.lib().swin_scale_cast(_p(x), _p(y), _p(row_scale), mode, B, H, W, Cc, ws, shift, y_dtype, _stream()), "scale_cast")
-    return y
+    L.check(L.lib().swin_scale_cast(_p(x), _p(y), _p(row_scale), mode, B, H, W, Cc, ws, shift, y_dtype, _p(cs), _stream()), "scale_cast")
+    return (y, cs) if want_colsum else y
 
 
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:

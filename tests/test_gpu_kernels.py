@@ -122,9 +122,12 @@ def test_scale_cast_and_colsum():
     s = torch.tensor([0.0, 1.25], device=DEV)
     y = ops.scale_cast(x, s, 0, B, H, W, C, 1, 0, L.BF16)
     assert torch.equal(y.view(B, H * W, C), (x * s.view(B, 1, 1)).bfloat16())
-    yw = ops.scale_cast(x, s, 1, B, H, W, C, ws, shift, L.F32)
+    yw, cs = ops.scale_cast(x, s, 1, B, H, W, C, ws, shift, L.F32, want_colsum=True)
     want = so.shift_gather((x * s.view(B, 1, 1)).cpu(), H, W, ws, shift)
     assert torch.equal(yw.cpu().view(want.shape), want)
+    assert rel(cs, want.double().sum((0, 1))) < 1e-5                  # fused bias-gradient column sums
+    y2, cs2 = ops.scale_cast(x, s, 0, B, H, W, C, 1, 0, L.BF16, want_colsum=True)
+    assert torch.equal(y2, y) and rel(cs2, (x * s.view(B, 1, 1)).double().sum((0, 1))) < 1e-5
     for dt in (torch.float32, torch.bfloat16):
         X = torch.randn(1000, 96, device=DEV).to(dt)
         assert rel(ops.colsum(X), X.double().sum(0)) < 1e-5
