@@ -110,10 +110,10 @@ int swin_patch_scatter(const void* dcols, float* dimg, int B, int Cin, int Hi, i
  */
 enum {
   SWIN_EPI_STORE = 0,            /* D = acc (+bias)                              qkv REF:129, reduction REF:296, dX  */
-  SWIN_EPI_GELU = 1,             /* D2 = u = acc+bias ; D = gelu_erf(u)          fc1 + act, REF:33-34                */
+  SWIN_EPI_GELU = 1,             /* u = acc+bias ; D = gelu_erf(u) ; D2 = gelu_erf'(u)  fc1 + act, REF:33-34 (D2 saved for bwd) */
   SWIN_EPI_RESIDUAL = 2,         /* D(fp32) = aux + row_scale[b] * (acc+bias)    fc2 + drop_path + residual REF:253  */
   SWIN_EPI_SCATTER_RESIDUAL = 3, /* same, rows are window slots scattered through the REF:236-252 inverse map        */
-  SWIN_EPI_DGELU = 4,            /* D = acc * gelu'(aux)  (aux = saved u)        backward of REF:34                  */
+  SWIN_EPI_DGELU = 4,            /* D = acc * aux  (aux = the saved gelu')       backward of REF:34                  */
   SWIN_EPI_ATOMIC_ADD = 5        /* D(fp32) += acc   (split-K weight gradients)                                      */
 };
 typedef struct swin_gemm_args {
@@ -124,8 +124,8 @@ typedef struct swin_gemm_args {
   int epilogue;
   const float* bias;    /* (N) fp32 or NULL */
   void* D; int d_dtype; int64_t ldd;
-  void* D2;             /* GELU: pre-activation output, same dtype/ld as D */
-  const void* aux;      /* RESIDUAL / SCATTER_RESIDUAL: fp32 residual (same layout as D); DGELU: u (dtype d_dtype, ld ldd) */
+  void* D2;             /* GELU: second output gelu'(u), same dtype/ld as D */
+  const void* aux;      /* RESIDUAL / SCATTER_RESIDUAL: fp32 residual (same layout as D); DGELU: saved gelu' (dtype d_dtype, ld ldd) */
   const float* row_scale; /* per-image drop-path multiplier (B) or NULL                                 */
   int rows_per_image;   /* RESIDUAL: H*W ; SCATTER_RESIDUAL: nW*N                                      */
   int H, W, ws, shift;  /* SCATTER_RESIDUAL geometry                                                   */

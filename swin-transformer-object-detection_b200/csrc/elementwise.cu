@@ -284,19 +284,20 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const YT* __restrict__ dy, 
       dyrow = (long long)b * per_img_slots + token_to_slot(lg.g, (int)(row - (long long)b * per_img_tok));
     }
     const float mu = inr ? mean[row] : 0.f, rs = inr ? rstd[row] : 0.f;
-    float4 xh[VPL], gd[VPL];
+    float4 xh[VPL], gd[VPL], rr[VPL];
     long long srow_k[VPL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int v = gl + G * k;
-      xh[k] = make_float4(0.f, 0.f, 0.f, 0.f); gd[k] = xh[k]; srow_k[k] = -1;
+      xh[k] = make_float4(0.f, 0.f, 0.f, 0.f); gd[k] = xh[k]; rr[k] = xh[k]; srow_k[k] = -1;
       if (inr && v < vrow) {
         long long srow = row; int off = v;
         if (lg.mode == 2) { int q = v / vps; off = v - q * vps; srow = merge_src(lg, row, q); }
         srow_k[k] = srow < 0 ? -1 : srow * vps + off;
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (srow >= 0) xv = Vec4IO<float>::ld(x, srow * vps + off);
+        if (srow >= 0 && dres != nullptr) rr[k] = Vec4IO<float>::ld(dres, srow * vps + off);   // issued with x/dy, before the reductions
         float4 d = Vec4IO<YT>::ld(dy, dyrow * vrow + v);
         float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + v);
         xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
@@ -316,10 +317,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const YT* __restrict__ dy, 
         o.y = rs * (gd[k].y - m1 - xh[k].y * m2);
         o.z = rs * (gd[k].z - m1 - xh[k].z * m2);
         o.w = rs * (gd[k].w - m1 - xh[k].w * m2);
-        if (dres != nullptr) {
-          float4 rr = Vec4IO<float>::ld(dres, srow_k[k]);
-          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-        }
+        o.x += rr[k].x; o.y += rr[k].y; o.z += rr[k].z; o.w += rr[k].w;
         Vec4IO<float>::st(dx, srow_k[k], o);
       }
     }
@@ -398,7 +396,7 @@ static int ln_bwd_dispatch(const swin_ln_args* a, const LnGeom& lg, cudaStream_t
   ln_shape(vrow, &G, &vpl);
   const int rows_per_block = 8 * (32 / G);
   long long blocks = ceil_div64(lg.rows, (long long)rows_per_block * 16);   // each lane group walks >= 16 rows so the atomics amortise
-  int grid = (int)(blocks < (long long)kNumSMs * 4 ? blocks : (long long)kNumSMs * 4);
+  int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
   if (grid < 1) grid = 1;
   size_t smem = (size_t)2 * vrow * 4 * sizeof(float);
 #define LN_BWD_CASE(V, GG)                                                                                         \
@@ -434,29 +432,42 @@ __global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict
     for (int i = threadIdx.x; i < g.C; i += blockDim.x) scol[i] = 0.f;
     __syncthreads();
   }
-  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
-    long long srow = row;
-    int b;
-    if (mode == 1) {
-      b = (int)(row / per_img_slots);
-      int t = slot_to_token(g, (int)(row - (long long)b * per_img_slots));
-      srow = t < 0 ? -1 : (long long)b * per_img_tok + t;
-    } else {
-      b = (int)(row / per_img_tok);
+  // 4 rows per warp iteration: their loads are independent, so 4x the bytes are in flight per warp
+  constexpr int RU = 4;
+  for (long long row0 = ((long long)blockIdx.x * wpb + (threadIdx.x >> 5)) * RU; row0 < rows; row0 += (long long)gridDim.x * wpb * RU) {
+    long long srow[RU];
+    float sc[RU];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const long long row = row0 + u;
+      srow[u] = -2; sc[u] = 1.0f;
+      if (row < rows) {
+        int b;
+        if (mode == 1) {
+          b = (int)(row / per_img_slots);
+          int t = slot_to_token(g, (int)(row - (long long)b * per_img_slots));
+          srow[u] = t < 0 ? -1 : (long long)b * per_img_tok + t;
+        } else {
+          b = (int)(row / per_img_tok);
+          srow[u] = row;
+        }
+        if (row_scale) sc[u] = row_scale[b];
+      }
     }
-    if (srow < 0) {
-      for (int v = lane; v < vrow; v += 32) Vec4IO<YT>::st(y, row * vrow + v, make_float4(0.f, 0.f, 0.f, 0.f));
-      continue;
-    }
-    const float sc = row_scale ? row_scale[b] : 1.0f;
 #pragma unroll
     for (int k = 0; k < kMaxV; ++k) {
       const int v = lane + 32 * k;
       if (v < vrow) {
-        float4 t = Vec4IO<float>::ld(x, srow * vrow + v);
-        t = make_float4(t.x * sc, t.y * sc, t.z * sc, t.w * sc);
-        Vec4IO<YT>::st(y, row * vrow + v, t);
-        acc[k].x += t.x; acc[k].y += t.y; acc[k].z += t.z; acc[k].w += t.w;
+        float4 t[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) t[u] = srow[u] >= 0 ? Vec4IO<float>::ld(x, srow[u] * vrow + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+          if (srow[u] == -2) continue;
+          t[u] = make_float4(t[u].x * sc[u], t[u].y * sc[u], t[u].z * sc[u], t[u].w * sc[u]);
+          Vec4IO<YT>::st(y, (row0 + u) * vrow + v, t[u]);
+          acc[k].x += t[u].x; acc[k].y += t[u].y; acc[k].z += t[u].z; acc[k].w += t[u].w;
+        }
       }
     }
   }
@@ -598,7 +609,7 @@ extern "C" int swin_scale_cast(const float* x, void* y, const float* row_scale, 
   SWIN_REQUIRE(ws > 0 && shift >= 0 && shift < ws, "scale_cast: bad window geometry");
   WinGeom g = make_geom(B, H, W, C, ws, shift);
   long long rows = mode == 1 ? (long long)B * g.nW * g.N : (long long)B * H * W;
-  long long blocks = ceil_div64(rows, 8 * 8);
+  long long blocks = ceil_div64(rows, 8 * 4 * 4);
   int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
   if (grid < 1) grid = 1;
   size_t smem = colsum ? (size_t)C * sizeof(float) : 0;

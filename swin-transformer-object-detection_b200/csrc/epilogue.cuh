@@ -63,14 +63,15 @@ __device__ __forceinline__ void epilogue_cols(const EpiParams& p, int row, long 
       case SWIN_EPI_STORE:
         store4(p.D, p.d_dtype, o, a);
         break;
-      case SWIN_EPI_GELU:
-        store4(p.D2, p.d_dtype, o, a);
+      case SWIN_EPI_GELU:                       // D = gelu(u), D2 = gelu'(u)  (u = acc + bias)
         if (FAST) {
           float4 gq, dq;
           gelu_fast(a.x, &gq.x, &dq.x); gelu_fast(a.y, &gq.y, &dq.y); gelu_fast(a.z, &gq.z, &dq.z); gelu_fast(a.w, &gq.w, &dq.w);
           store4(p.D, p.d_dtype, o, gq);
+          store4(p.D2, p.d_dtype, o, dq);
         } else {
           store4(p.D, p.d_dtype, o, make_float4(gelu_erf(a.x), gelu_erf(a.y), gelu_erf(a.z), gelu_erf(a.w)));
+          store4(p.D2, p.d_dtype, o, make_float4(dgelu_erf(a.x), dgelu_erf(a.y), dgelu_erf(a.z), dgelu_erf(a.w)));
         }
         break;
       case SWIN_EPI_RESIDUAL:
@@ -79,15 +80,9 @@ __device__ __forceinline__ void epilogue_cols(const EpiParams& p, int row, long 
         store4(p.D, SWIN_F32, o, make_float4(r.x + scale * a.x, r.y + scale * a.y, r.z + scale * a.z, r.w + scale * a.w));
         break;
       }
-      case SWIN_EPI_DGELU: {
-        float4 u = load4(p.aux, p.d_dtype, o);
-        if (FAST) {
-          float4 gq, dq;
-          gelu_fast(u.x, &gq.x, &dq.x); gelu_fast(u.y, &gq.y, &dq.y); gelu_fast(u.z, &gq.z, &dq.z); gelu_fast(u.w, &gq.w, &dq.w);
-          store4(p.D, p.d_dtype, o, make_float4(a.x * dq.x, a.y * dq.y, a.z * dq.z, a.w * dq.w));
-        } else {
-          store4(p.D, p.d_dtype, o, make_float4(a.x * dgelu_erf(u.x), a.y * dgelu_erf(u.y), a.z * dgelu_erf(u.z), a.w * dgelu_erf(u.w)));
-        }
+      case SWIN_EPI_DGELU: {                    // D = acc * aux  (aux = gelu'(u) saved by the GELU epilogue)
+        float4 g = load4(p.aux, p.d_dtype, o);
+        store4(p.D, p.d_dtype, o, make_float4(a.x * g.x, a.y * g.y, a.z * g.z, a.w * g.w));
         break;
       }
       case SWIN_EPI_ATOMIC_ADD: {
@@ -132,7 +127,7 @@ inline int make_epi_params(const swin_gemm_args* a, EpiParams* out) {
       break;
     }
     case SWIN_EPI_DGELU:
-      SWIN_REQUIRE(a->aux != nullptr && aligned16(a->aux), "gemm: DGELU needs aux = u");
+      SWIN_REQUIRE(a->aux != nullptr && aligned16(a->aux), "gemm: DGELU needs aux = saved gelu'");
       break;
     case SWIN_EPI_ATOMIC_ADD:
       SWIN_REQUIRE(a->d_dtype == SWIN_F32 && a->bias == nullptr, "gemm: ATOMIC_ADD needs fp32 D and no bias");

@@ -21,6 +21,7 @@ struct GemmTcParams {
   int n_tiles, m_tiles, splits, kb_total, kb_per_split;
   int stages;
   uint32_t a_bytes, b_bytes;   // TMA bytes per stage (expect_tx)
+  int tma_epi;                 // 1: STORE/GELU with bf16 outputs go out through TMA stores (tmD / tmD2)
   uint32_t stage_bytes;        // smem stride per stage: a_bytes + b_bytes rounded up to the 1024-byte swizzle-atom alignment
   EpiParams epi;
 };
@@ -57,8 +58,8 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, const float4* __re
       if (off[i] < 0) continue;
       float4 g, d;
       gelu_fast(a[i].x, &g.x, &d.x); gelu_fast(a[i].y, &g.y, &d.y); gelu_fast(a[i].z, &g.z, &d.z); gelu_fast(a[i].w, &g.w, &d.w);
-      store4(p.D2, p.d_dtype, off[i], a[i]);
       store4(p.D, p.d_dtype, off[i], g);
+      store4(p.D2, p.d_dtype, off[i], d);
     }
   } else if (EPI == SWIN_EPI_RESIDUAL || EPI == SWIN_EPI_SCATTER_RESIDUAL) {
     // all 8 residual loads are issued unconditionally (clamped address, read-only path) BEFORE any use, so they
@@ -85,12 +86,8 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, const float4* __re
       for (int i = 0; i < 8; ++i) u[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + (off[i] >= 0 ? off[i] : 0)));
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (off[i] < 0) continue;
-      float4 g, d;
-      gelu_fast(u[i].x, &g.x, &d.x); gelu_fast(u[i].y, &g.y, &d.y); gelu_fast(u[i].z, &g.z, &d.z); gelu_fast(u[i].w, &g.w, &d.w);
-      store4(p.D, p.d_dtype, off[i], make_float4(a[i].x * d.x, a[i].y * d.y, a[i].z * d.z, a[i].w * d.w));
-    }
+    for (int i = 0; i < 8; ++i)
+      if (off[i] >= 0) store4(p.D, p.d_dtype, off[i], make_float4(a[i].x * u[i].x, a[i].y * u[i].y, a[i].z * u[i].z, a[i].w * u[i].w));
   } else {  // SWIN_EPI_ATOMIC_ADD
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -98,13 +95,15 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, const float4* __re
   }
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool TMA_EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                   const __grid_constant__ CUtensorMap tmB, GemmTcParams p) {
+                                                                   const __grid_constant__ CUtensorMap tmB,
+                                                                   const __grid_constant__ CUtensorMap tmD,
+                                                                   const __grid_constant__ CUtensorMap tmD2, GemmTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 8];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float4 epi_stage[kEpiWarps][32 * 8];     // per-epilogue-warp 32x32 fp32 transpose stage (4 KB each)
+  __shared__ __align__(1024) float4 epi_stage[kEpiWarps][32 * 8];     // per-epilogue-warp staging (4 KB each)
   __shared__ long long epi_rowdst[kEpiWarps][32];
   __shared__ float epi_rowscale[kEpiWarps][32];
 
@@ -205,7 +204,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     // epilogue in the coalesced layout (lane = 4 consecutive columns of one of 4 rows per instruction).
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
     const int ew = warp - 2;                  // 0..7
-    const int chunk_sel = ew >> 2;            // this warp takes 32-column chunks with (c/32)%2 == chunk_sel
     float4* stage = &epi_stage[ew][0];
     uint32_t u = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++u) {
@@ -214,6 +212,68 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       const int row_base = m_blk * TBM + q * 32;
       const int n0 = n_blk * p.block_n;
       const uint32_t acc = u % num_acc, acc_ph = (u / num_acc) & 1;
+      // the two warps of a lane quarter take alternate 32-column chunks; which of them starts at chunk 0 flips every
+      // tile so odd chunk counts (N = 96: 3 chunks) balance out across tiles
+      const int chunk_sel = (ew >> 2) ^ (int)(u & 1);
+      if (TMA_EPI) {
+        // ---- STORE / GELU with bf16 outputs: math in the TMEM row layout, bf16 tile staged in the TMA 64B-swizzle
+        //      layout, one TMA store per 32x32 chunk (no per-lane global stores, no address arithmetic)
+        mbar_wait(tfull_bar(acc), acc_ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
+        const bool gelu = p.epi.epilogue == SWIN_EPI_GELU;
+        uint8_t* sbuf = reinterpret_cast<uint8_t*>(stage);
+        const uint32_t sbuf_a = smem_u32(sbuf);
+        const uint32_t swz = (uint32_t)((lane >> 1) & 3);
+        uint32_t v[32];
+        int c = chunk_sel * 32;
+        if (c < p.block_n) tmem_ld32(taddr + c, v);
+        for (; c < p.block_n; c += 64) {
+          float4 b4[8];
+          if (p.epi.bias != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) b4[k] = __ldg(reinterpret_cast<const float4*>(p.epi.bias + n0 + c) + k);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) b4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          tmem_ld_wait();
+          uint32_t pu[16], ph[16];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float x0 = __uint_as_float(v[4 * k + 0]) + b4[k].x, x1 = __uint_as_float(v[4 * k + 1]) + b4[k].y;
+            const float x2 = __uint_as_float(v[4 * k + 2]) + b4[k].z, x3 = __uint_as_float(v[4 * k + 3]) + b4[k].w;
+            if (gelu) {                                // pu <- gelu(u) (D), ph <- gelu'(u) (D2)
+              float g0, g1, g2, g3, d0, d1, d2, d3;
+              gelu_fast(x0, &g0, &d0); gelu_fast(x1, &g1, &d1); gelu_fast(x2, &g2, &d2); gelu_fast(x3, &g3, &d3);
+              pu[2 * k] = pack_bf16(g0, g1); pu[2 * k + 1] = pack_bf16(g2, g3);
+              ph[2 * k] = pack_bf16(d0, d1); ph[2 * k + 1] = pack_bf16(d2, d3);
+            } else {
+              pu[2 * k] = pack_bf16(x0, x1); pu[2 * k + 1] = pack_bf16(x2, x3);
+            }
+          }
+          if (c + 64 < p.block_n) tmem_ld32(taddr + c + 64, v);      // next chunk's TMEM read overlaps the stores below
+          if (lane == 0) tma_store_wait_read<0>();                   // previous chunk's TMA stores have drained the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const uint32_t o = (uint32_t)lane * 64u + ((cc ^ swz) << 4);
+            *reinterpret_cast<int4*>(sbuf + o) = make_int4(pu[4 * cc], pu[4 * cc + 1], pu[4 * cc + 2], pu[4 * cc + 3]);
+            if (gelu) *reinterpret_cast<int4*>(sbuf + 2048 + o) = make_int4(ph[4 * cc], ph[4 * cc + 1], ph[4 * cc + 2], ph[4 * cc + 3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (gelu) { tma_store_2d(&tmD, sbuf_a, n0 + c, row_base); tma_store_2d(&tmD2, sbuf_a + 2048, n0 + c, row_base); }
+            else tma_store_2d(&tmD, sbuf_a, n0 + c, row_base);
+            tma_store_commit();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        continue;
+      }
       {
         long long drow = 0; float scale = 1.f;
         const bool live = epi_row_setup(p.epi, row_base + lane, &drow, &scale);
@@ -252,6 +312,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
   }
+  if (TMA_EPI && warp >= 2 && lane == 0) tma_store_wait_all<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
@@ -309,22 +370,36 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   else       rc = make_tmap_bf16_2d(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, 64, TBK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
 
+  // TMA-store epilogue: bf16 STORE / GELU outputs whose tile is a whole number of 32-column chunks
+  CUtensorMap tmD = tmA, tmD2 = tmA;
+  p.tma_epi = 0;
+  if ((a->epilogue == SWIN_EPI_STORE || a->epilogue == SWIN_EPI_GELU) && a->d_dtype == SWIN_BF16 && p.block_n % 32 == 0) {
+    rc = make_tmap_bf16_2d(&tmD, a->D, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    if (a->epilogue == SWIN_EPI_GELU) {
+      rc = make_tmap_bf16_2d(&tmD2, a->D2, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
+    p.tma_epi = 1;
+  }
   const int total_units = p.m_tiles * p.n_tiles * p.splits;
   const int grid = total_units < kNumSMs ? total_units : kNumSMs;
-#define LAUNCH_TC(AM, BM)                                                                                         \
+#define LAUNCH_TC(AM, BM, TE)                                                                                     \
   do {                                                                                                            \
     static bool attr_done = false;                                                                                \
     if (!attr_done) {                                                                                             \
-      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AM, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 188 * 1024); \
+      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AM, BM, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 188 * 1024); \
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }      \
       attr_done = true;                                                                                           \
     }                                                                                                             \
-    gemm_tc_kernel<AM, BM><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);                                        \
+    gemm_tc_kernel<AM, BM, TE><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, tmD, tmD2, p);                         \
   } while (0)
-  if (!a_mn && !b_mn) LAUNCH_TC(false, false);
-  else if (!a_mn && b_mn) LAUNCH_TC(false, true);
-  else if (a_mn && b_mn) LAUNCH_TC(true, true);
-  else LAUNCH_TC(true, false);
+#define LAUNCH_TC2(AM, BM) do { if (p.tma_epi) LAUNCH_TC(AM, BM, true); else LAUNCH_TC(AM, BM, false); } while (0)
+  if (!a_mn && !b_mn) LAUNCH_TC2(false, false);
+  else if (!a_mn && b_mn) LAUNCH_TC2(false, true);
+  else if (a_mn && b_mn) LAUNCH_TC2(true, true);
+  else LAUNCH_TC2(true, false);
+#undef LAUNCH_TC2
 #undef LAUNCH_TC
   SWIN_LAUNCH_CHECK();
   return 0;

@@ -67,7 +67,7 @@ class SwinBlockFn(torch.autograd.Function):
                  row_scale=s1, geom=geom)
         # MLP branch: LN2 -> fc1 + GELU -> fc2 + residual
         xn, mean2, rstd2 = ops.ln_fwd(0, x1, n2w.detach(), n2b.detach(), B, H, W, Cc, 1, 0, eps, dt)
-        u = torch.empty((T, hid), dtype=xn.dtype, device=x.device)
+        u = torch.empty((T, hid), dtype=xn.dtype, device=x.device)      # gelu'(fc1 pre-activation), saved for backward
         h = ops.gemm(xn, _w(fc1w, dt), T, hid, Cc, bias=fc1b.detach(), epilogue=L.EPI_GELU, out2=u)
         x2 = torch.empty_like(x)
         ops.gemm(h, _w(fc2w, dt), T, Cc, hid, bias=fc2b.detach(), epilogue=L.EPI_RESIDUAL, out=x2, aux=x1, row_scale=s2,

@@ -208,17 +208,17 @@ def test_gemm_epilogues(dtype):
     X = (torch.randn(T, C, generator=g)).to(td).to(DEV)
     Wt = (torch.randn(4 * C, C, generator=g) * 0.2).to(td).to(DEV)
     b = torch.randn(4 * C, generator=g).to(DEV)
-    # GELU: D = gelu(u), D2 = u
-    u = torch.empty(T, 4 * C, dtype=td, device=DEV)
-    h = ops.gemm(X, Wt, T, 4 * C, C, bias=b, epilogue=L.EPI_GELU, out2=u)
-    ur = X.double().cpu() @ Wt.double().cpu().t() + b.double().cpu()
-    assert rel(u, ur) < tol_store and rel(h, so.gelu_erf(ur)) < tol_store
-    # DGELU: D = acc * gelu'(u)
+    # GELU: D = gelu(u), D2 = gelu'(u)
+    dg = torch.empty(T, 4 * C, dtype=td, device=DEV)
+    h = ops.gemm(X, Wt, T, 4 * C, C, bias=b, epilogue=L.EPI_GELU, out2=dg)
+    ur = (X.double().cpu() @ Wt.double().cpu().t() + b.double().cpu()).requires_grad_(True)
+    hr = so.gelu_erf(ur)
+    hr.sum().backward()
+    assert rel(h, hr) < tol_store and rel(dg, ur.grad) < tol_store
+    # DGELU: D = acc * aux (aux = saved gelu')
     dy = (torch.randn(T, C, generator=g)).to(td).to(DEV)
-    du = ops.gemm(dy, Wt, T, 4 * C, C, b_trans=False, epilogue=L.EPI_DGELU, aux=u)
-    uu = u.double().cpu().requires_grad_(True)
-    so.gelu_erf(uu).sum().backward()
-    assert rel(du, (dy.double().cpu() @ Wt.double().cpu().t()) * uu.grad) < tol_store
+    du = ops.gemm(dy, Wt, T, 4 * C, C, b_trans=False, epilogue=L.EPI_DGELU, aux=dg)
+    assert rel(du, (dy.double().cpu() @ Wt.double().cpu().t()) * dg.double().cpu()) < tol_store
     # RESIDUAL with per-image scale
     W2 = (torch.randn(C, 4 * C, generator=g) * 0.1).to(td).to(DEV)
     b2 = torch.randn(C, generator=g).to(DEV)
