@@ -21,6 +21,7 @@ struct GemmTcParams {
   int n_tiles, m_tiles, splits, kb_total, kb_per_split;
   int stages;
   uint32_t a_bytes, b_bytes;   // TMA bytes per stage (expect_tx)
+  uint32_t epi_bytes_per_warp; // epilogue staging per warp in dynamic smem (4 KB; 8 KB for fp32 class-2 double buffers)
   int tma_epi;                 // 1: STORE/GELU with bf16 outputs go out through TMA stores (tmD / tmD2)
   uint32_t stage_bytes;        // smem stride per stage: a_bytes + b_bytes rounded up to the 1024-byte swizzle-atom alignment
   EpiParams epi;
@@ -95,7 +96,9 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, const float4* __re
   }
 }
 
-template <bool A_MN, bool B_MN, bool TMA_EPI>
+// EPI_CLASS: 0 = generic coalesced-lane epilogue; 1 = bf16 STORE/GELU through TMA stores; 2 = DGELU (bf16) / RESIDUAL (fp32):
+//            the aux tile is TMA-loaded, updated in place in the TMEM row layout and TMA-stored.
+template <bool A_MN, bool B_MN, int EPI_CLASS>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmD,
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 8];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(1024) float4 epi_stage[kEpiWarps][32 * 8];     // per-epilogue-warp staging (4 KB each)
+  __shared__ __align__(8) uint64_t aux_bars[kEpiWarps][2];
   __shared__ long long epi_rowdst[kEpiWarps][32];
   __shared__ float epi_rowscale[kEpiWarps][32];
 
@@ -122,6 +125,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 4; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
+    for (int w = 0; w < kEpiWarps; ++w) { mbar_init(smem_u32(&aux_bars[w][0]), 1); mbar_init(smem_u32(&aux_bars[w][1]), 1); }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -204,8 +208,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     // epilogue in the coalesced layout (lane = 4 consecutive columns of one of 4 rows per instruction).
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
     const int ew = warp - 2;                  // 0..7
-    float4* stage = &epi_stage[ew][0];
+    // per-epilogue-warp staging lives in dynamic smem right after the operand ring (4 KB per warp; 2 x 4 KB for class 2)
+    float4* stage = reinterpret_cast<float4*>(smem_raw + (smem0 - smem_u32(smem_raw)) + (uint32_t)p.stages * stage_bytes + (uint32_t)ew * p.epi_bytes_per_warp);
     uint32_t u = 0;
+    uint32_t aux_n = 0;                       // class 2: aux tiles requested so far by this warp (buffer = n & 1)
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++u) {
       const int tile = unit / p.splits;
       const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
@@ -215,7 +221,109 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       // the two warps of a lane quarter take alternate 32-column chunks; which of them starts at chunk 0 flips every
       // tile so odd chunk counts (N = 96: 3 chunks) balance out across tiles
       const int chunk_sel = (ew >> 2) ^ (int)(u & 1);
-      if (TMA_EPI) {
+      if (EPI_CLASS == 2) {
+        // ---- DGELU (bf16: D = (acc+bias) * aux) / RESIDUAL (fp32: D = aux + row_scale * (acc+bias)):
+        //      the aux tile of each 32x32 chunk is TMA-loaded one chunk ahead into a per-warp double buffer, updated in
+        //      place by the thread that owns the row (TMEM row layout) and TMA-stored from the same buffer.
+        const bool resid = p.epi.epilogue == SWIN_EPI_RESIDUAL;
+        const uint32_t tile_bytes = resid ? 4096u : 2048u;
+        uint8_t* sbuf = reinterpret_cast<uint8_t*>(stage);
+        const uint32_t sbuf_a = smem_u32(sbuf);
+        const uint32_t abar0 = smem_u32(&aux_bars[ew][0]);
+        float rscale = 1.0f;
+        if (resid && p.epi.row_scale != nullptr) {
+          int rr = row_base + lane; if (rr >= p.epi.M) rr = p.epi.M - 1;
+          rscale = p.epi.row_scale[rr / p.epi.rows_per_image];
+        }
+        int c = chunk_sel * 32;
+        uint32_t cur = aux_n;
+        if (c < p.block_n) {
+          if (lane == 0) {
+            tma_store_wait_read<0>();
+            const uint32_t b = aux_n & 1;
+            mbar_expect_tx(abar0 + 8 * b, tile_bytes);
+            tma_load_2d(sbuf_a + b * tile_bytes, &tmD2, abar0 + 8 * b, n0 + c, row_base);
+          }
+          ++aux_n;
+        }
+        mbar_wait(tfull_bar(acc), acc_ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
+        uint32_t v[32];
+        if (c < p.block_n) tmem_ld32(taddr + c, v);
+        for (; c < p.block_n; c += 64, ++cur) {
+          float4 b4[8];
+          if (p.epi.bias != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) b4[k] = __ldg(reinterpret_cast<const float4*>(p.epi.bias + n0 + c) + k);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) b4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          const uint32_t b = cur & 1;
+          uint8_t* tile = sbuf + b * tile_bytes;
+          tmem_ld_wait();
+          mbar_wait(abar0 + 8 * b, (cur >> 1) & 1);
+          if (resid) {
+            float4 ax[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) ax[cc] = *reinterpret_cast<const float4*>(tile + lane * 128 + ((cc ^ (lane & 7)) << 4));
+            if (c + 64 < p.block_n) {                 // request the next chunk's aux tile (other buffer)
+              if (lane == 0) {
+                tma_store_wait_read<0>();
+                const uint32_t nb = aux_n & 1;
+                mbar_expect_tx(abar0 + 8 * nb, tile_bytes);
+                tma_load_2d(sbuf_a + nb * tile_bytes, &tmD2, abar0 + 8 * nb, n0 + c + 64, row_base);
+              }
+              ++aux_n;
+            }
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              float4 o;
+              o.x = fmaf(rscale, __uint_as_float(v[4 * cc + 0]) + b4[cc].x, ax[cc].x);
+              o.y = fmaf(rscale, __uint_as_float(v[4 * cc + 1]) + b4[cc].y, ax[cc].y);
+              o.z = fmaf(rscale, __uint_as_float(v[4 * cc + 2]) + b4[cc].z, ax[cc].z);
+              o.w = fmaf(rscale, __uint_as_float(v[4 * cc + 3]) + b4[cc].w, ax[cc].w);
+              *reinterpret_cast<float4*>(tile + lane * 128 + ((cc ^ (lane & 7)) << 4)) = o;
+            }
+          } else {
+            const uint32_t swz = (uint32_t)((lane >> 1) & 3);
+            int4 ax[4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) ax[cc] = *reinterpret_cast<const int4*>(tile + lane * 64 + ((cc ^ swz) << 4));
+            if (c + 64 < p.block_n) {
+              if (lane == 0) {
+                tma_store_wait_read<0>();
+                const uint32_t nb = aux_n & 1;
+                mbar_expect_tx(abar0 + 8 * nb, tile_bytes);
+                tma_load_2d(sbuf_a + nb * tile_bytes, &tmD2, abar0 + 8 * nb, n0 + c + 64, row_base);
+              }
+              ++aux_n;
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              const uint32_t g[4] = {(uint32_t)ax[cc].x, (uint32_t)ax[cc].y, (uint32_t)ax[cc].z, (uint32_t)ax[cc].w};
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int k = 8 * cc + 2 * e;          // columns k, k+1
+                const float bx = (k & 3) == 0 ? b4[k >> 2].x : b4[k >> 2].z, by = (k & 3) == 0 ? b4[k >> 2].y : b4[k >> 2].w;
+                o[e] = pack_bf16((__uint_as_float(v[k]) + bx) * bf16_lo(g[e]), (__uint_as_float(v[k + 1]) + by) * bf16_hi(g[e]));
+              }
+              *reinterpret_cast<int4*>(tile + lane * 64 + ((cc ^ swz) << 4)) = make_int4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          if (c + 64 < p.block_n) tmem_ld32(taddr + c + 64, v);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&tmD, sbuf_a + b * tile_bytes, n0 + c, row_base); tma_store_commit(); }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        continue;
+      }
+      if (EPI_CLASS == 1) {
         // ---- STORE / GELU with bf16 outputs: math in the TMEM row layout, bf16 tile staged in the TMA 64B-swizzle
         //      layout, one TMA store per 32x32 chunk (no per-lane global stores, no address arithmetic)
         mbar_wait(tfull_bar(acc), acc_ph);
@@ -312,7 +420,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
   }
-  if (TMA_EPI && warp >= 2 && lane == 0) tma_store_wait_all<0>();
+  if (EPI_CLASS != 0 && warp >= 2 && lane == 0) tma_store_wait_all<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
@@ -356,11 +464,10 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   p.b_bytes = (uint32_t)bn_rows * TBK * 2;
   p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
   const uint32_t stage_bytes = p.stage_bytes;
-  const uint32_t budget = 184 * 1024;
+  const uint32_t budget = 187 * 1024;
   p.stages = (int)(budget / stage_bytes);
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   SWIN_REQUIRE(p.stages >= 2, "gemm(bf16): tile does not fit in shared memory");
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
 
   CUtensorMap tmA, tmB;
   if (!a_mn) rc = make_tmap_bf16_2d(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, TBK, TBM, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -370,31 +477,58 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   else       rc = make_tmap_bf16_2d(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, 64, TBK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
 
-  // TMA-store epilogue: bf16 STORE / GELU outputs whose tile is a whole number of 32-column chunks
+  // TMA epilogues: class 1 = bf16 STORE / GELU outputs; class 2 = DGELU (bf16 aux/out) and RESIDUAL (fp32 aux/out);
+  // all need the tile to be a whole number of 32-column chunks
   CUtensorMap tmD = tmA, tmD2 = tmA;
   p.tma_epi = 0;
-  if ((a->epilogue == SWIN_EPI_STORE || a->epilogue == SWIN_EPI_GELU) && a->d_dtype == SWIN_BF16 && p.block_n % 32 == 0) {
-    rc = make_tmap_bf16_2d(&tmD, a->D, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
-    if (rc) return rc;
-    if (a->epilogue == SWIN_EPI_GELU) {
-      rc = make_tmap_bf16_2d(&tmD2, a->D2, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (p.block_n % 32 == 0) {
+    if ((a->epilogue == SWIN_EPI_STORE || a->epilogue == SWIN_EPI_GELU) && a->d_dtype == SWIN_BF16) {
+      rc = make_tmap_bf16_2d(&tmD, a->D, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
+      if (a->epilogue == SWIN_EPI_GELU) {
+        rc = make_tmap_bf16_2d(&tmD2, a->D2, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+      }
+      p.tma_epi = 1;
+    } else if (a->epilogue == SWIN_EPI_DGELU && a->d_dtype == SWIN_BF16) {
+      rc = make_tmap_bf16_2d(&tmD, a->D, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+      rc = make_tmap_bf16_2d(&tmD2, a->aux, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+      p.tma_epi = 2;
+    } else if (a->epilogue == SWIN_EPI_RESIDUAL && (220u * 1024 - 8192u * kEpiWarps - 1024) / stage_bytes >= 4) {
+      rc = make_tmap_f32_2d(&tmD, a->D, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+      rc = make_tmap_f32_2d(&tmD2, a->aux, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+      p.tma_epi = 2;
     }
-    p.tma_epi = 1;
   }
+  p.epi_bytes_per_warp = (p.tma_epi == 2 && a->epilogue == SWIN_EPI_RESIDUAL) ? 8192u : 4096u;
+  const uint32_t epi_bytes = p.epi_bytes_per_warp * kEpiWarps;
+  {
+    const uint32_t ring_budget = 220 * 1024 - epi_bytes - 1024;     // dynamic smem: ring + epilogue staging + alignment slack
+    int st2 = (int)(ring_budget / stage_bytes);
+    if (st2 < p.stages) p.stages = st2;
+  }
+  const size_t smem = (size_t)p.stages * stage_bytes + epi_bytes + 1024;
   const int total_units = p.m_tiles * p.n_tiles * p.splits;
   const int grid = total_units < kNumSMs ? total_units : kNumSMs;
 #define LAUNCH_TC(AM, BM, TE)                                                                                     \
   do {                                                                                                            \
     static bool attr_done = false;                                                                                \
     if (!attr_done) {                                                                                             \
-      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AM, BM, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 188 * 1024); \
+      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AM, BM, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           220 * 1024);                                                           \
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }      \
       attr_done = true;                                                                                           \
     }                                                                                                             \
     gemm_tc_kernel<AM, BM, TE><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, tmD, tmD2, p);                         \
   } while (0)
-#define LAUNCH_TC2(AM, BM) do { if (p.tma_epi) LAUNCH_TC(AM, BM, true); else LAUNCH_TC(AM, BM, false); } while (0)
+#define LAUNCH_TC2(AM, BM)                                                                                        \
+  do {                                                                                                            \
+    if (p.tma_epi == 2) LAUNCH_TC(AM, BM, 2); else if (p.tma_epi == 1) LAUNCH_TC(AM, BM, 1); else LAUNCH_TC(AM, BM, 0); \
+  } while (0)
   if (!a_mn && !b_mn) LAUNCH_TC2(false, false);
   else if (!a_mn && b_mn) LAUNCH_TC2(false, true);
   else if (a_mn && b_mn) LAUNCH_TC2(true, true);

@@ -24,8 +24,18 @@ inline tmap_encode_fn get_tmap_encode() {
 
 // 2-D bf16 tensor, row-major: `inner` contiguous elements per row, `outer` rows, row pitch in bytes.
 // Out-of-bounds box elements are filled with zeros.
+inline int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                        uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz);
 inline int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                              uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz) {
+  return make_tmap_2d(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, ptr, inner, outer, pitch_bytes, box_inner, box_outer, swz);
+}
+inline int make_tmap_f32_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                            uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz) {
+  return make_tmap_2d(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ptr, inner, outer, pitch_bytes, box_inner, box_outer, swz);
+}
+inline int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                        uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz) {
   tmap_encode_fn enc = get_tmap_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return -ENOTSUP; }
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (pitch_bytes & 15)) {
@@ -37,7 +47,7 @@ inline int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, ui
   cuuint64_t strides[1] = {pitch_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): dims=%llu x %llu pitch=%llu box=%u x %u", (int)r, (unsigned long long)inner,
