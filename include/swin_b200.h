@@ -84,6 +84,13 @@ typedef struct swin_ln_args {
   float* dx;           /* bwd out fp32, same layout as x                                           */
   float* dgamma;       /* bwd out, ACCUMULATED (+=) with atomics: caller zero-fills               */
   float* dbeta;
+  /* bwd, mode 0, optional (NULL = off): dy2[slot(token)] = dy2_scale[b] * dx[token] in y_dtype, laid out as window
+   * slots (B*nW, N, C) for (ws2, shift2) — the drop-path-scaled, partitioned dY of the proj Linear (REF:252 backward),
+   * emitted while dx is in registers.  Pad slots are NOT written (caller zero-fills dy2).  dy2_colsum (C) += column sums. */
+  void* dy2;
+  const float* dy2_scale;
+  float* dy2_colsum;
+  int ws2, shift2;
 } swin_ln_args;
 int swin_ln_fwd(const swin_ln_args* a, void* stream);
 int swin_ln_bwd(const swin_ln_args* a, void* stream);

@@ -23,7 +23,8 @@ c_int, c_i64, c_f32, vp = C.c_int, C.c_int64, C.c_float, C.c_void_p
 class LnArgs(C.Structure):
     _fields_ = [("mode", c_int), ("B", c_int), ("H", c_int), ("W", c_int), ("C", c_int), ("ws", c_int), ("shift", c_int),
                 ("eps", c_f32), ("y_dtype", c_int), ("x", vp), ("gamma", vp), ("beta", vp), ("y", vp), ("mean", vp),
-                ("rstd", vp), ("dy", vp), ("dres", vp), ("dx", vp), ("dgamma", vp), ("dbeta", vp)]
+                ("rstd", vp), ("dy", vp), ("dres", vp), ("dx", vp), ("dgamma", vp), ("dbeta", vp),
+                ("dy2", vp), ("dy2_scale", vp), ("dy2_colsum", vp), ("ws2", c_int), ("shift2", c_int)]
 
 
 class GemmArgs(C.Structure):

@@ -80,7 +80,7 @@ constexpr uint32_t kFwdTiles = 3 * kTileBytes;     // Q,K,V per buffer
 
 __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[4];
+  __shared__ __align__(8) uint64_t bars[5];              // load[2], s[2], o
   __shared__ uint32_t tmem_slot;
   __shared__ float sRed[2][2][128];                       // [max|sum][half][row]
   uint8_t* sbase = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -90,21 +90,23 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __gr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, hf = warp >> 2;
   const int h = blockIdx.x % p.nH, g = blockIdx.x / p.nH;
-  const uint32_t bar_load0 = smem_u32(&bars[0]), bar_s = smem_u32(&bars[2]), bar_o = smem_u32(&bars[3]);
+  const uint32_t bar_load0 = smem_u32(&bars[0]), bar_s0 = smem_u32(&bars[2]), bar_o = smem_u32(&bars[4]);
 
   zero_smem(sT, 2 * kFwdTiles + kPBytes);
   load_bias_tile(sBias, p.bias, h);
   if (tid == 0) {
-    mbar_init(bar_load0, 1); mbar_init(bar_load0 + 8, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    mbar_init(bar_load0, 1); mbar_init(bar_load0 + 8, 1); mbar_init(bar_s0, 1); mbar_init(bar_s0 + 8, 1); mbar_init(bar_o, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmQKV);
   }
-  if (warp == 0) { tmem_alloc(smem_u32(&tmem_slot), 128); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(smem_u32(&tmem_slot), 256); tmem_relinquish(); }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tS = tmem_slot, tO = tmem_slot;          // O overlays S columns [0,64) once P is in smem
+  // two S accumulators (128 columns each): S of item i+1 is computed while item i is in its P.V / epilogue phase.
+  // O of item i overlays columns [0,64) of its own S buffer once P is in smem.
+  const uint32_t tmem0 = tmem_slot;
   const uint32_t lane_off = (uint32_t)(q * 32) << 16;
 
   const int r = q * 32 + lane, wloc = r >> 6, i = r & 63;
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __gr
   const uint32_t aT = smem_u32(sT), aP = smem_u32(sP);
   const float kLog2e = 1.4426950408889634f;
   const float sc2 = p.scale * kLog2e;
+  const int stride = p.ctas_per_head;
 
   auto issue_loads = [&](int pair, int buf) {
     const uint32_t bar = bar_load0 + 8 * buf, base = aT + buf * kFwdTiles;
@@ -126,23 +129,29 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __gr
       tma_load_2d(base + 2 * kTileBytes + w * 4096, &tmQKV, bar, 2 * p.C + h * AHD, row0);
     }
   };
-  if (tid == 0 && g < p.npairs) issue_loads(g, 0);
+  auto issue_s = [&](uint32_t item) {          // S(item) = Q K^T into S buffer item&1, once its tiles have landed
+    const uint32_t b = item & 1;
+    mbar_wait(bar_load0 + 8 * b, (item >> 1) & 1);
+    tc_fence_after();
+    const uint32_t aQ = aT + b * kFwdTiles, aK = aQ + kTileBytes;
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      umma_bf16(tmem0 + 128 * b, umma_desc(aQ + k * 32, 16, 512, kSw64), umma_desc(aK + k * 32, 16, 512, kSw64), idesc_s, k);
+    umma_commit(bar_s0 + 8 * b);
+  };
+  if (tid == 0 && g < p.npairs) {
+    issue_loads(g, 0);
+    if (g + stride < p.npairs) issue_loads(g + stride, 1);
+    issue_s(0);
+  }
   TDECL
 
   uint32_t it = 0;
-  for (int pair = g; pair < p.npairs; pair += p.ctas_per_head, ++it) {
-    const uint32_t ph = it & 1, buf = it & 1, lph = (it >> 1) & 1;
-    const uint32_t aQ = aT + buf * kFwdTiles, aK = aQ + kTileBytes, aV = aK + kTileBytes;
+  for (int pair = g; pair < p.npairs; pair += stride, ++it) {
+    const uint32_t ph = it & 1, buf = it & 1, sph = (it >> 1) & 1;
+    const uint32_t aV = aT + buf * kFwdTiles + 2 * kTileBytes;
+    const uint32_t tS = tmem0 + 128 * buf, tO = tS;
     TITEM
-    if (tid == 0) {
-      if (pair + p.ctas_per_head < p.npairs) issue_loads(pair + p.ctas_per_head, buf ^ 1);
-      mbar_wait(bar_load0 + 8 * buf, lph);
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 2; ++k)
-        umma_bf16(tS, umma_desc(aQ + k * 32, 16, 512, kSw64), umma_desc(aK + k * 32, 16, 512, kSw64), idesc_s, k);
-      umma_commit(bar_s);
-    }
     const int win = 2 * pair + wloc;
     const bool valid = (i < AN) && (win < p.B_);
     const float* mrow = nullptr;
@@ -150,7 +159,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __gr
       const int mw = win % p.nW;
       if (p.mask_nz == nullptr || p.mask_nz[mw]) mrow = p.mask + ((size_t)mw * AN + i) * AN;
     }
-    mbar_wait(bar_s, ph);
+    mbar_wait(bar_s0 + 8 * buf, sph);
     tc_fence_after();
     TMARK(0);
     uint32_t v[32];
@@ -213,6 +222,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __gr
       for (int kk = 0; kk < 4; ++kk)
         umma_bf16(tO, umma_desc(aP + kk * 32, 16, 1024, kSw128), umma_desc(aV + kk * 1024, 4096, 512, kSw64), idesc_o, kk);
       umma_commit(bar_o);
+      if (pair + stride < p.npairs) issue_s(it + 1);      // next item's S overlaps this item's P.V + epilogue
     }
     sum = sRed[1][0][r] + sRed[1][1][r];
     mbar_wait(bar_o, ph);
@@ -237,9 +247,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __gr
     tc_fence_before();
     __syncthreads();
     TMARK(8);
+    // tile buffer `buf` (Q,K used by S(it), V by O(it)) is free again: fetch item it+2 into it
+    if (tid == 0 && pair + 2 * stride < p.npairs) issue_loads(pair + 2 * stride, buf);
   }
   TPRINT("attn_fwd");
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_slot, 128); }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_slot, 256); }
 }
 
 // ------------------------------------------------------------------------------------------ backward
@@ -312,7 +324,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
     const uint32_t aQ = aT + buf * kBwdTiles, aK = aQ + kTileBytes, aV = aK + kTileBytes, adO = aV + kTileBytes;
     TITEM
     if (tid == 0) {
-      if (pair + p.ctas_per_head < p.npairs) issue_loads(pair + p.ctas_per_head, buf ^ 1);
       mbar_wait(bar_load0 + 8 * buf, lph);
       tc_fence_after();
 #pragma unroll
@@ -322,6 +333,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
       for (int k = 0; k < 2; ++k)
         umma_bf16(tdP, umma_desc(adO + k * 32, 16, 512, kSw64), umma_desc(aV + k * 32, 16, 512, kSw64), idesc_s, k);
       umma_commit(bar_s);
+      if (pair + p.ctas_per_head < p.npairs) issue_loads(pair + p.ctas_per_head, buf ^ 1);   // after the MMAs are in flight
     }
     const int win = 2 * pair + wloc;
     const bool valid = (i < AN) && (win < p.B_);

@@ -145,6 +145,12 @@ struct LnGeom {
   int H2, W2;      // merge
   long long rows;  // iteration rows (see kernels)
   float eps;
+  // backward, mode 0 only: optional second output  y2[slot(token)] = y2_scale[b] * dx[token]  (window-slot layout,
+  // dtype of dy) + its column sums: the dY of the proj Linear, produced while dx is still in registers
+  WinGeom g2;
+  void* y2;
+  const float* y2_scale;
+  float* y2_colsum;
 };
 
 // merged row (b, oh, ow) segment q -> source token row or -1   (REF:288-292 order (0,0),(1,0),(0,1),(1,1))
@@ -272,9 +278,9 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const YT* __restrict__ dy, 
   const int per_img_slots = lg.g.nW * lg.g.N, per_img_tok = lg.g.H * lg.g.W;
   for (int i = threadIdx.x; i < 2 * width; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
-  float4 ag[VPL], ab[VPL];
+  float4 ag[VPL], ab[VPL], a2[VPL];
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) { ag[k] = make_float4(0.f, 0.f, 0.f, 0.f); ab[k] = ag[k]; }
+  for (int k = 0; k < VPL; ++k) { ag[k] = make_float4(0.f, 0.f, 0.f, 0.f); ab[k] = ag[k]; a2[k] = ag[k]; }
   for (long long base = ((long long)blockIdx.x * wpb + (threadIdx.x >> 5)) * R; base < lg.rows; base += (long long)gridDim.x * wpb * R) {
     const long long row = base + gi;
     const bool inr = row < lg.rows;
@@ -309,6 +315,14 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const YT* __restrict__ dy, 
       }
     }
     const float m1 = group_sum<G>(s1) * inv_n, m2 = group_sum<G>(s2) * inv_n;
+    long long slot2 = 0;
+    float sc2 = 1.0f;
+    if (lg.y2 != nullptr && inr) {
+      const int tok_per_img = lg.g2.H * lg.g2.W;
+      const int b2 = (int)(row / tok_per_img);
+      slot2 = (long long)b2 * (lg.g2.nW * lg.g2.N) + token_to_slot(lg.g2, (int)(row - (long long)b2 * tok_per_img));
+      if (lg.y2_scale != nullptr) sc2 = lg.y2_scale[b2];
+    }
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       if (srow_k[k] >= 0) {
@@ -319,6 +333,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const YT* __restrict__ dy, 
         o.w = rs * (gd[k].w - m1 - xh[k].w * m2);
         o.x += rr[k].x; o.y += rr[k].y; o.z += rr[k].z; o.w += rr[k].w;
         Vec4IO<float>::st(dx, srow_k[k], o);
+        if (lg.y2 != nullptr) {
+          o.x *= sc2; o.y *= sc2; o.z *= sc2; o.w *= sc2;
+          Vec4IO<YT>::st(reinterpret_cast<YT*>(lg.y2), slot2 * vrow + (gl + G * k), o);
+          a2[k].x += o.x; a2[k].y += o.y; a2[k].z += o.z; a2[k].w += o.w;
+        }
       }
     }
   }
@@ -338,6 +357,21 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const YT* __restrict__ dy, 
     atomicAdd(dgamma + i, sred[i]);
     atomicAdd(dbeta + i, sred[width + i]);
   }
+  if (lg.y2_colsum != nullptr) {               // column sums of the second output, reusing the first half of sred
+    __syncthreads();
+    for (int i = threadIdx.x; i < width; i += blockDim.x) sred[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int v = gl + G * k;
+      if (v < vrow) {
+        atomicAdd(&sred[v * 4 + 0], a2[k].x); atomicAdd(&sred[v * 4 + 1], a2[k].y);
+        atomicAdd(&sred[v * 4 + 2], a2[k].z); atomicAdd(&sred[v * 4 + 3], a2[k].w);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < width; i += blockDim.x) atomicAdd(lg.y2_colsum + i, sred[i]);
+  }
 }
 
 static int ln_geom(const swin_ln_args* a, bool bwd, LnGeom* out) {
@@ -355,6 +389,13 @@ static int ln_geom(const swin_ln_args* a, bool bwd, LnGeom* out) {
   else if (a->mode == 1) lg.rows = bwd ? tokens : (long long)a->B * lg.g.nW * lg.g.N;
   else lg.rows = (long long)a->B * lg.H2 * lg.W2;
   SWIN_REQUIRE(a->y_dtype == SWIN_F32 || (a->y_dtype == SWIN_BF16), "ln: bad y dtype");
+  lg.g2 = lg.g; lg.y2 = nullptr; lg.y2_scale = nullptr; lg.y2_colsum = nullptr;
+  if (bwd && a->dy2 != nullptr) {
+    SWIN_REQUIRE(a->mode == 0, "ln_bwd: the window-slot second output (dy2) is only available in mode 0");
+    SWIN_REQUIRE(a->ws2 > 0 && a->shift2 >= 0 && a->shift2 < a->ws2 && aligned16(a->dy2), "ln_bwd: bad dy2 geometry/alignment");
+    lg.g2 = make_geom(a->B, a->H, a->W, a->C, a->ws2, a->shift2);
+    lg.y2 = a->dy2; lg.y2_scale = a->dy2_scale; lg.y2_colsum = a->dy2_colsum;
+  }
   *out = lg;
   return 0;
 }

@@ -22,6 +22,14 @@ __global__ void __launch_bounds__(256) patch_unfold_kernel(float* __restrict__ i
     const int ph = y / p, i = y - ph * p;
     T* dst = cols + ((long long)(b * Hh + ph) * Ww + pw) * K + c * p * p + i * p;
     float* src = img + (((long long)b * Cin + c) * Hi + y) * Wi + (long long)pw * p;
+    if (!SCATTER && p == 4) {                  // the 4 pixels of one patch row -> one 8/16-byte store
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = ((y < Hi) && (pw * 4 + j < Wi)) ? __ldg(src + j) : 0.f;
+      if (sizeof(T) == 2) *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+      else *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      continue;
+    }
     for (int j = 0; j < p; ++j) {
       const bool in = (y < Hi) && (pw * p + j < Wi);
       if (SCATTER) { if (in) src[j] = (float)dst[j]; }

@@ -95,9 +95,11 @@ class SwinBlockFn(torch.autograd.Function):
         dfc1w = torch.zeros_like(fc1w, dtype=torch.float32)
         ops.gemm(du, xn, hid, Cc, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc1w)
         dxn = ops.gemm(du, _w(fc1w, dt), T, Cc, hid, b_trans=True)
-        dx1, dn2w, dn2b = ops.ln_bwd(0, dxn, x1, n2w.detach(), mean2, rstd2, dx2, B, H, W, Cc, 1, 0)
+        # LN2 backward + residual-gradient add; the same kernel also emits dY of the proj Linear (drop-path scaled,
+        # cast and partitioned into window slots) and its column sums (= d proj.bias)
+        dx1, dn2w, dn2b, dy1, dprojb = ops.ln_bwd(0, dxn, x1, n2w.detach(), mean2, rstd2, dx2, B, H, W, Cc, 1, 0,
+                                                  emit_windows=(ws, shift, s1))
         # ---- attention branch
-        dy1, dprojb = ops.scale_cast(dx1, s1, 1, B, H, W, Cc, ws, shift, dt, want_colsum=True)  # (Tp, C), pad slots 0
         dprojw = torch.zeros_like(projw, dtype=torch.float32)
         ops.gemm(dy1, o, Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dprojw)
         do = ops.gemm(dy1, _w(projw, dt), Tp, Cc, Cc, b_trans=True)

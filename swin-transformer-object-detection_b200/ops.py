@@ -162,16 +162,26 @@ def ln_fwd(mode: int, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, 
 
 
 def ln_bwd(mode: int, dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor,
-           dres: Optional[torch.Tensor], B: int, H: int, W: int, Cc: int, ws: int, shift: int):
-    """Returns (dx fp32 like x, dgamma, dbeta)."""
+           dres: Optional[torch.Tensor], B: int, H: int, W: int, Cc: int, ws: int, shift: int, emit_windows=None):
+    """Returns (dx fp32 like x, dgamma, dbeta).  With ``emit_windows=(ws2, shift2, row_scale)`` (mode 0 only) it also
+    returns (dy2, colsum2): row_scale[b]*dx cast to dy's dtype and gathered into window slots, plus its column sums."""
     _chk(dy, x, gamma, mean, rstd, dres)
     dx = torch.empty_like(x)
     width = Cc * (4 if mode == 2 else 1)
-    dgb = torch.zeros((2, width), dtype=torch.float32, device=x.device)
+    dgb = torch.zeros((3, width), dtype=torch.float32, device=x.device)
     a = L.LnArgs(mode=mode, B=B, H=H, W=W, C=Cc, ws=ws, shift=shift, eps=0.0, y_dtype=_DT[dy.dtype], x=_p(x), gamma=_p(gamma),
                  mean=_p(mean), rstd=_p(rstd), dy=_p(dy), dres=_p(dres), dx=_p(dx), dgamma=_p(dgb[0]), dbeta=_p(dgb[1]))
+    dy2 = None
+    if emit_windows is not None:
+        ws2, shift2, scale2 = emit_windows
+        _chk(scale2)
+        Hp, Wp = padded_hw(H, W, ws2)
+        dy2 = torch.zeros((B * (Hp // ws2) * (Wp // ws2) * ws2 * ws2, Cc), dtype=dy.dtype, device=x.device)   # pad slots stay 0
+        a.dy2, a.dy2_scale, a.dy2_colsum, a.ws2, a.shift2 = _p(dy2), _p(scale2), _p(dgb[2]), ws2, shift2
     _count()
     L.check(L.lib().swin_ln_bwd(C.byref(a), _stream()), "ln_bwd")
+    if emit_windows is not None:
+        return dx, dgb[0], dgb[1], dy2, dgb[2]
     return dx, dgb[0], dgb[1]
 
 

@@ -115,6 +115,28 @@ def test_layernorm_modes(mode, ydt, C):
     assert rel(db, br.grad) < 1e-4
 
 
+@pytest.mark.parametrize("ydt", ["f32", "bf16"])
+def test_ln_bwd_emits_partitioned_proj_dy(ydt):
+    """ln_bwd (mode 0) with the fused second output == scale_cast(mode 1)(dx) + column sums."""
+    ops, L = _ops()
+    B, H, W, C, ws, shift = 2, 9, 13, 96, 7, 3
+    td = torch.float32 if ydt == "f32" else torch.bfloat16
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = torch.randn(B, H * W, C, generator=g).to(DEV)
+    gm = (1 + 0.2 * torch.randn(C, generator=g)).to(DEV)
+    bt = torch.randn(C, generator=g).to(DEV)
+    dy = torch.randn(B * H * W, C, generator=g).to(td).to(DEV)
+    dres = torch.randn(B, H * W, C, generator=g).to(DEV)
+    s = torch.tensor([0.5, 1.25], device=DEV)
+    _, mean, rstd = ops.ln_fwd(0, x, gm, bt, B, H, W, C, 1, 0, 1e-5, L.F32 if ydt == "f32" else L.BF16)
+    dx0, dg0, db0 = ops.ln_bwd(0, dy, x, gm, mean, rstd, dres, B, H, W, C, 1, 0)
+    dx1, dg1, db1, dy2, cs2 = ops.ln_bwd(0, dy, x, gm, mean, rstd, dres, B, H, W, C, 1, 0, emit_windows=(ws, shift, s))
+    assert torch.equal(dx0, dx1) and rel(dg1, dg0) < 1e-5 and rel(db1, db0) < 1e-5
+    want, wcs = ops.scale_cast(dx0, s, 1, B, H, W, C, ws, shift, L.F32 if ydt == "f32" else L.BF16, want_colsum=True)
+    assert torch.equal(dy2, want)
+    assert rel(cs2, wcs) < 1e-5
+
+
 def test_scale_cast_and_colsum():
     ops, L = _ops()
     B, H, W, C, ws, shift = 2, 9, 13, 64, 7, 3
