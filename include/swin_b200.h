@@ -164,6 +164,9 @@ typedef struct swin_attn_args {
   const float* bias;
   const float* mask;
   const int32_t* mask_nz; /* optional (nW): 0 where mask[w] is all zeros, so the kernel skips reading it; NULL = unknown */
+  int canon_nwh, canon_nww; /* optional: > 0 asserts that `mask` is the canonical SW-MSA mask of REF:370-389 for an
+                               (nwh x nww) window grid with shift = ws/2; the bf16 kernel then evaluates it in closed
+                               form (region ids) instead of reading the tensor.  0 = honour the tensor as given.      */
   void* out;
   float* lse;
   /* backward */

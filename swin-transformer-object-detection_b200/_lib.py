@@ -39,7 +39,7 @@ class GemmArgs(C.Structure):
 
 class AttnArgs(C.Structure):
     _fields_ = [("dtype", c_int), ("B_", c_int), ("nH", c_int), ("ws", c_int), ("nW", c_int), ("scale", c_f32),
-                ("qkv", vp), ("bias", vp), ("mask", vp), ("mask_nz", vp), ("out", vp), ("lse", vp),
+                ("qkv", vp), ("bias", vp), ("mask", vp), ("mask_nz", vp), ("canon_nwh", c_int), ("canon_nww", c_int), ("out", vp), ("lse", vp),
                 ("dout", vp), ("dqkv", vp), ("dbias", vp)]
 
 

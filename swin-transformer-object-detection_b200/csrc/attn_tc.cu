@@ -27,6 +27,7 @@ constexpr uint32_t kPBytes = 128 * 128;       // compact P / dS tile: 128 rows x
 
 struct AttnTcParams {
   int B_, nH, nW, C, npairs, ctas_per_head;
+  int canon_nwh, canon_nww;    // > 0: canonical shift mask in closed form
   float scale;
   const float* bias; const float* mask; const int* mask_nz;
   __nv_bfloat16* out; float* lse;
@@ -44,6 +45,21 @@ __device__ __forceinline__ void store_row_bf16x8(uint8_t* dst, const float* v) {
   int4 pk;
   pk.x = pack_bf16(v[0], v[1]); pk.y = pack_bf16(v[2], v[3]); pk.z = pack_bf16(v[4], v[5]); pk.w = pack_bf16(v[6], v[7]);
   *reinterpret_cast<int4*>(dst) = pk;
+}
+
+
+// Canonical SW-MSA mask (REF:370-389) of one window row in closed form, window 7 / shift 3.  Region ids on the
+// padded grid differ only inside the last window row / column, where tokens with row (col) index >= ws - shift = 4
+// belong to another region than those < 4.  Returns a 49-bit set: bit j = 1 <=> mask[w][i][j] == -100.
+__device__ __forceinline__ unsigned long long canon_mask_bits(int wi, int nwh, int nww, int i) {
+  constexpr unsigned long long kRowHi = 0x1FFFFF0000000ULL;          // j/7 >= 4  <=> j >= 28   (bits 28..48)
+  constexpr unsigned long long kColHi = 0x1C3870E1C3870ULL;          // j%7 >= 4  (bits {4,5,6} + 7k, k = 0..6)
+  constexpr unsigned long long kAll = 0x1FFFFFFFFFFFFULL;
+  const int wh = wi / nww, ww = wi - wh * nww;
+  unsigned long long m = 0ULL;
+  if (wh == nwh - 1) m |= (i / 7 >= 4) ? (~kRowHi & kAll) : kRowHi;
+  if (ww == nww - 1) m |= (i % 7 >= 4) ? (~kColHi & kAll) : kColHi;
+  return m;
 }
 
 // Thread mapping shared by both kernels: 256 threads = 8 warps.  Warp w owns TMEM lane quarter q = w & 3 (rows
@@ -155,9 +171,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __gr
     const int win = 2 * pair + wloc;
     const bool valid = (i < AN) && (win < p.B_);
     const float* mrow = nullptr;
+    uint32_t mb = 0u;                          // closed-form mask bits of this thread's 32 columns
     if (p.mask != nullptr && valid) {
       const int mw = win % p.nW;
-      if (p.mask_nz == nullptr || p.mask_nz[mw]) mrow = p.mask + ((size_t)mw * AN + i) * AN;
+      if (p.canon_nwh > 0) mb = (uint32_t)(canon_mask_bits(mw, p.canon_nwh, p.canon_nww, i) >> jbase);
+      else if (p.mask_nz == nullptr || p.mask_nz[mw]) mrow = p.mask + ((size_t)mw * AN + i) * AN;
     }
     mbar_wait(bar_s0 + 8 * buf, sph);
     tc_fence_after();
@@ -186,6 +204,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __gr
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj)
           if (jbase + jj < AN) sv[jj] = fmaf(__ldg(mrow + jbase + jj), kLog2e, sv[jj]);
+      }
+      if (mb != 0u) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj)
+          if ((mb >> jj) & 1u) sv[jj] -= 100.0f * kLog2e;
       }
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj)
@@ -339,9 +362,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
     const bool valid = (i < AN) && (win < p.B_);
     const float lse2 = valid ? p.lse[((size_t)win * p.nH + h) * AN + i] * kLog2e : 0.f;
     const float* mrow = nullptr;
+    uint32_t mb = 0u;
     if (p.mask != nullptr && valid) {
       const int mw = win % p.nW;
-      if (p.mask_nz == nullptr || p.mask_nz[mw]) mrow = p.mask + ((size_t)mw * AN + i) * AN;
+      if (p.canon_nwh > 0) mb = (uint32_t)(canon_mask_bits(mw, p.canon_nwh, p.canon_nww, i) >> jbase);
+      else if (p.mask_nz == nullptr || p.mask_nz[mw]) mrow = p.mask + ((size_t)mw * AN + i) * AN;
     }
     mbar_wait(bar_s, ph);
     tc_fence_after();
@@ -373,6 +398,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj)
           if (jbase + jj < AN) pr[jj] = fmaf(__ldg(mrow + jbase + jj), kLog2e, pr[jj]);
+      }
+      if (mb != 0u) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj)
+          if ((mb >> jj) & 1u) pr[jj] -= 100.0f * kLog2e;
       }
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj) {
@@ -465,6 +495,11 @@ static int attn_tc_common(const swin_attn_args* a, AttnTcParams* out, bool bwd, 
   if (per_head < 1) per_head = 1;
   p.ctas_per_head = per_head;
   p.bias = a->bias; p.mask = a->mask; p.mask_nz = a->mask ? a->mask_nz : nullptr;
+  p.canon_nwh = 0; p.canon_nww = 0;
+  if (a->mask && a->canon_nwh > 0 && a->canon_nww > 0) {
+    SWIN_REQUIRE(a->canon_nwh * a->canon_nww == a->nW, "attn: canonical mask grid %d x %d does not match nW = %d", a->canon_nwh, a->canon_nww, a->nW);
+    p.canon_nwh = a->canon_nwh; p.canon_nww = a->canon_nww;
+  }
   p.out = (__nv_bfloat16*)a->out; p.lse = a->lse;
   p.dout = (const __nv_bfloat16*)a->dout; p.dqkv = (__nv_bfloat16*)a->dqkv; p.dbias = a->dbias;
   *out = p;

@@ -50,7 +50,7 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 class SwinBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, n1w, n1b, table, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b, mask, mask_nz, s1, s2,
-                H, W, ws, shift, nH, scale, dt, eps):
+                H, W, ws, shift, nH, scale, dt, eps, canon=(0, 0)):
         B, Lx, Cc = x.shape
         x = _f32c(x)
         geom = (H, W, ws, shift)
@@ -61,7 +61,7 @@ class SwinBlockFn(torch.autograd.Function):
         Tp = xw.shape[0] * xw.shape[1]
         qkv = ops.gemm(xw, _w(qkvw, dt), Tp, 3 * Cc, Cc, bias=None if qkvb is None else qkvb.detach())
         bias = ops.rel_bias_expand(table.detach().contiguous(), ws)
-        o, lse = ops.window_attn_fwd(qkv.view(-1, ws * ws, 3 * Cc), bias, mask, Tp // (ws * ws), nH, ws, scale, mask_nz)
+        o, lse = ops.window_attn_fwd(qkv.view(-1, ws * ws, 3 * Cc), bias, mask, Tp // (ws * ws), nH, ws, scale, mask_nz, canon)
         x1 = torch.empty_like(x)
         ops.gemm(o, _w(projw, dt), Tp, Cc, Cc, bias=projb.detach(), epilogue=L.EPI_SCATTER_RESIDUAL, out=x1, aux=x,
                  row_scale=s1, geom=geom)
@@ -74,14 +74,14 @@ class SwinBlockFn(torch.autograd.Function):
                  rows_per_image=Lx)
         ctx.save_for_backward(x, n1w, table, qkvw, projw, n2w, fc1w, fc2w, mask, mask_nz, s1, s2,
                               xw, mean1, rstd1, qkv, bias, o, lse, x1, xn, mean2, rstd2, u, h)
-        ctx.cfg = (B, H, W, Cc, ws, shift, nH, scale, dt, hid, qkvb is not None)
+        ctx.cfg = (B, H, W, Cc, ws, shift, nH, scale, dt, hid, qkvb is not None, canon)
         return x2
 
     @staticmethod
     def backward(ctx, dx2):
         (x, n1w, table, qkvw, projw, n2w, fc1w, fc2w, mask, mask_nz, s1, s2,
          xw, mean1, rstd1, qkv, bias, o, lse, x1, xn, mean2, rstd2, u, h) = ctx.saved_tensors
-        B, H, W, Cc, ws, shift, nH, scale, dt, hid, has_qkvb = ctx.cfg
+        B, H, W, Cc, ws, shift, nH, scale, dt, hid, has_qkvb, canon = ctx.cfg
         T = B * H * W
         N = ws * ws
         Tp = xw.shape[0] * N
@@ -103,7 +103,7 @@ class SwinBlockFn(torch.autograd.Function):
         dprojw = torch.zeros_like(projw, dtype=torch.float32)
         ops.gemm(dy1, o, Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dprojw)
         do = ops.gemm(dy1, _w(projw, dt), Tp, Cc, Cc, b_trans=True)
-        dqkv, dbias = ops.window_attn_bwd(qkv.view(-1, N, 3 * Cc), o, do.view(-1, N, Cc), lse, bias, mask, Tp // N, nH, ws, scale, mask_nz)
+        dqkv, dbias = ops.window_attn_bwd(qkv.view(-1, N, 3 * Cc), o, do.view(-1, N, Cc), lse, bias, mask, Tp // N, nH, ws, scale, mask_nz, canon)
         dtable = ops.rel_bias_reduce(dbias, ws)
         dqkvb = ops.colsum(dqkv) if has_qkvb else None
         dqkvw = torch.zeros_like(qkvw, dtype=torch.float32)
@@ -111,7 +111,7 @@ class SwinBlockFn(torch.autograd.Function):
         dxw = ops.gemm(dqkv.view(Tp, 3 * Cc), _w(qkvw, dt), Tp, Cc, 3 * Cc, b_trans=True)
         dx, dn1w, dn1b = ops.ln_bwd(1, dxw, x, n1w.detach(), mean1, rstd1, dx1, B, H, W, Cc, ws, shift)
         return (dx, dn1w, dn1b, dtable, dqkvw, dqkvb, dprojw, dprojb, dn2w, dn2b, dfc1w, dfc1b, dfc2w, dfc2b,
-                None, None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 class WindowAttentionFn(torch.autograd.Function):

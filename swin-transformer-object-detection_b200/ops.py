@@ -292,13 +292,13 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
 
 # ------------------------------------------------------------------ window attention core
 def window_attn_fwd(qkv: torch.Tensor, bias: torch.Tensor, mask: Optional[torch.Tensor], B_: int, nH: int, ws: int,
-                    scale: float, mask_nz: Optional[torch.Tensor] = None):
+                    scale: float, mask_nz: Optional[torch.Tensor] = None, canon=(0, 0)):
     _chk(qkv, bias, mask, mask_nz)
     N, Cc = ws * ws, nH * 32
     out = torch.empty((B_, N, Cc), dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty((B_, nH, N), dtype=torch.float32, device=qkv.device)
     a = L.AttnArgs(dtype=_DT[qkv.dtype], B_=B_, nH=nH, ws=ws, nW=0 if mask is None else mask.shape[0], scale=scale,
-                   qkv=_p(qkv), bias=_p(bias), mask=_p(mask), mask_nz=_p(mask_nz), out=_p(out), lse=_p(lse))
+                   qkv=_p(qkv), bias=_p(bias), mask=_p(mask), mask_nz=_p(mask_nz), canon_nwh=canon[0], canon_nww=canon[1], out=_p(out), lse=_p(lse))
     _count()
     L.check(L.lib().swin_window_attn_fwd(C.byref(a), _stream()), "window_attn_fwd")
     return out, lse
@@ -306,13 +306,13 @@ def window_attn_fwd(qkv: torch.Tensor, bias: torch.Tensor, mask: Optional[torch.
 
 def window_attn_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, bias: torch.Tensor,
                     mask: Optional[torch.Tensor], B_: int, nH: int, ws: int, scale: float,
-                    mask_nz: Optional[torch.Tensor] = None):
+                    mask_nz: Optional[torch.Tensor] = None, canon=(0, 0)):
     _chk(qkv, out, dout, lse, bias, mask, mask_nz)
     N = ws * ws
     dqkv = torch.empty_like(qkv)
     dbias = torch.zeros((nH, N, N), dtype=torch.float32, device=qkv.device)
     a = L.AttnArgs(dtype=_DT[qkv.dtype], B_=B_, nH=nH, ws=ws, nW=0 if mask is None else mask.shape[0], scale=scale,
-                   qkv=_p(qkv), bias=_p(bias), mask=_p(mask), mask_nz=_p(mask_nz), out=_p(out), lse=_p(lse), dout=_p(dout), dqkv=_p(dqkv),
+                   qkv=_p(qkv), bias=_p(bias), mask=_p(mask), mask_nz=_p(mask_nz), canon_nwh=canon[0], canon_nww=canon[1], out=_p(out), lse=_p(lse), dout=_p(dout), dqkv=_p(dqkv),
                    dbias=_p(dbias))
     _count()
     L.check(L.lib().swin_window_attn_bwd(C.byref(a), _stream()), "window_attn_bwd")

@@ -171,6 +171,7 @@ class SwinTransformerBlock(nn.Module):
         if self.training and (self._drop > 0 or any(p > 0 for p in self.attn._drops)):
             raise NotImplementedError("dropout > 0 is not implemented in the fused kernels")
         mask = mask_nz = None
+        canon = (0, 0)
         if self.shift_size > 0:
             if mask_matrix is None:
                 raise ValueError("shifted block needs mask_matrix")
@@ -178,6 +179,8 @@ class SwinTransformerBlock(nn.Module):
             mask_nz = getattr(mask_matrix, "_swin_nz", None)     # set by BasicLayer.attn_mask (cached per geometry)
             if mask_nz is None:
                 mask_nz = ops.mask_nonzero(mask)
+            # the mask built by BasicLayer.attn_mask is the canonical one: the kernel evaluates it in closed form
+            canon = getattr(mask_matrix, "_swin_canon", (0, 0)) if self.window_size == 7 and self.shift_size == 3 else (0, 0)
         s1 = s2 = None
         if isinstance(self.drop_path, DropPath):
             s1 = self.drop_path.sample_scale(x)      # attention-branch draw first, then MLP (REF:252-253)
@@ -187,7 +190,7 @@ class SwinTransformerBlock(nn.Module):
                                  a.qkv.bias, a.proj.weight, a.proj.bias, self.norm2.weight, self.norm2.bias,
                                  m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, mask, mask_nz, s1, s2,
                                  H, W, self.window_size, self.shift_size, self.num_heads, float(a.scale), self._dt,
-                                 float(self.norm1.eps))
+                                 float(self.norm1.eps), canon)
 
 
 class PatchMerging(nn.Module):
@@ -236,6 +239,7 @@ class BasicLayer(nn.Module):
         if m is None:
             m = ops.shift_mask(H, W, self.window_size, self.shift_size, device)
             m._swin_nz = ops.mask_nonzero(m)      # per-window "mask is not all-zero" flags for the attention kernels
+            m._swin_canon = (-(-H // self.window_size), -(-W // self.window_size))   # canonical: closed form allowed
             if len(self._mask_cache) > 16:
                 self._mask_cache.clear()
             self._mask_cache[key] = m

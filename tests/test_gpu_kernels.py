@@ -323,3 +323,26 @@ def test_window_attention_core(dtype, B_, nH, masked):
     assert rel(dqkv[..., C_:2 * C_], dqkv_r[..., C_:2 * C_]) < tolb, "dK"
     assert rel(dqkv[..., 2 * C_:], dqkv_r[..., 2 * C_:]) < tolb, "dV"
     assert rel(dbias, dbias_r) < tolb, "dBias"
+
+
+@pytest.mark.parametrize("H,W", [(10, 13), (25, 42), (7, 7)])
+def test_window_attention_closed_form_canonical_mask_equals_tensor_mask(H, W):
+    """bf16 kernel: evaluating the canonical SW-MSA mask in closed form == reading the (nW,49,49) tensor."""
+    ops, L = _ops()
+    ws, N, nH = 7, 49, 2
+    nwh, nww = -(-H // ws), -(-W // ws)
+    nW = nwh * nww
+    B_ = 3 * nW
+    g = torch.Generator(device="cpu").manual_seed(5)
+    qkv = torch.randn(B_, N, 3 * nH * 32, generator=g).bfloat16().to(DEV)
+    bias = (torch.randn(nH, N, N, generator=g) * 0.5).to(DEV)
+    dout = torch.randn(B_, N, nH * 32, generator=g).bfloat16().to(DEV)
+    mask = ops.shift_mask(H, W, ws, 3, DEV)
+    assert torch.equal(mask.cpu(), torch.from_numpy(so.shift_mask_np(H, W, ws, 3)))
+    nz = ops.mask_nonzero(mask)
+    o1, l1 = ops.window_attn_fwd(qkv, bias, mask, B_, nH, ws, 32 ** -0.5, nz)
+    o2, l2 = ops.window_attn_fwd(qkv, bias, mask, B_, nH, ws, 32 ** -0.5, nz, canon=(nwh, nww))
+    assert torch.equal(o1, o2) and torch.equal(l1, l2)
+    d1, b1 = ops.window_attn_bwd(qkv, o1, dout, l1, bias, mask, B_, nH, ws, 32 ** -0.5, nz)
+    d2, b2 = ops.window_attn_bwd(qkv, o1, dout, l1, bias, mask, B_, nH, ws, 32 ** -0.5, nz, canon=(nwh, nww))
+    assert torch.equal(d1, d2) and rel(b2, b1) < 1e-5
