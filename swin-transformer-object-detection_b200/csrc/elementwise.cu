@@ -436,7 +436,10 @@ static int ln_bwd_dispatch(const swin_ln_args* a, const LnGeom& lg, cudaStream_t
   int vrow = lg.C / 4 * lg.nseg, G, vpl;
   ln_shape(vrow, &G, &vpl);
   const int rows_per_block = 8 * (32 / G);
-  long long blocks = ceil_div64(lg.rows, (long long)rows_per_block * 16);   // each lane group walks >= 16 rows so the atomics amortise
+  // each lane group walks ~16 rows so the closing atomics amortise, but never fewer than 2 blocks per SM if rows allow
+  long long blocks = ceil_div64(lg.rows, (long long)rows_per_block * 16);
+  const long long min_blocks = ceil_div64(lg.rows, rows_per_block) < 2LL * kNumSMs ? ceil_div64(lg.rows, rows_per_block) : 2LL * kNumSMs;
+  if (blocks < min_blocks) blocks = min_blocks;
   int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
   if (grid < 1) grid = 1;
   size_t smem = (size_t)2 * vrow * 4 * sizeof(float);
@@ -456,12 +459,11 @@ static int ln_bwd_dispatch(const swin_ln_args* a, const LnGeom& lg, cudaStream_t
 // ------------------------------------------------------------------------------------------
 // scale + cast (+ optional gather into window slots): dY of the residual epilogues.
 // ------------------------------------------------------------------------------------------
-template <typename YT>
+template <typename YT, int kMaxV>
 __global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict__ x, YT* __restrict__ y,
                                                          const float* __restrict__ row_scale, int mode, WinGeom g,
                                                          long long rows, float* __restrict__ colsum) {
   extern __shared__ float scol[];           // [C] block partial column sums (only when colsum != nullptr)
-  constexpr int kMaxV = 8;                  // C <= 1024
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int vrow = g.C >> 2;
@@ -654,9 +656,18 @@ extern "C" int swin_scale_cast(const float* x, void* y, const float* row_scale, 
   int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
   if (grid < 1) grid = 1;
   size_t smem = colsum ? (size_t)C * sizeof(float) : 0;
-  if (y_dtype == SWIN_F32) scale_cast_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(x, (float*)y, row_scale, mode, g, rows, colsum);
-  else if (y_dtype == SWIN_BF16) scale_cast_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, row_scale, mode, g, rows, colsum);
+  const int kv = ceil_div(C / 4, 32);           // float4 vectors per lane (C <= 1024 -> <= 8)
+#define SC_LAUNCH(T, KV) scale_cast_kernel<T, KV><<<grid, 256, smem, (cudaStream_t)stream>>>(x, (T*)y, row_scale, mode, g, rows, colsum)
+#define SC_DISPATCH(T)                                                                          \
+  do {                                                                                          \
+    if (kv <= 1) SC_LAUNCH(T, 1); else if (kv <= 2) SC_LAUNCH(T, 2); else if (kv <= 3) SC_LAUNCH(T, 3); \
+    else if (kv <= 4) SC_LAUNCH(T, 4); else if (kv <= 6) SC_LAUNCH(T, 6); else SC_LAUNCH(T, 8);   \
+  } while (0)
+  if (y_dtype == SWIN_F32) SC_DISPATCH(float);
+  else if (y_dtype == SWIN_BF16) SC_DISPATCH(__nv_bfloat16);
   else { set_error("scale_cast: bad dtype"); return -EINVAL; }
+#undef SC_DISPATCH
+#undef SC_LAUNCH
   SWIN_LAUNCH_CHECK();
   return 0;
 }
