@@ -136,6 +136,9 @@ typedef struct swin_gemm_args {
   const float* row_scale; /* per-image drop-path multiplier (B) or NULL                                 */
   int rows_per_image;   /* RESIDUAL: H*W ; SCATTER_RESIDUAL: nW*N                                      */
   int H, W, ws, shift;  /* SCATTER_RESIDUAL geometry                                                   */
+  float* colsum_a;      /* optional, ATOMIC_ADD with a_trans=1 only: colsum_a[m] += sum_k A[m,k] (fp32, caller zero-fills).
+                           For dW = dY^T X this is the bias gradient sum_t dY[t,:], produced on the tensor cores by one
+                           extra N=16 MMA per k-step against a constant all-ones smem tile (no extra pass over dY).     */
 } swin_gemm_args;
 int swin_gemm(const swin_gemm_args* a, void* stream);
 

@@ -34,7 +34,7 @@ class GemmArgs(C.Structure):
                 ("epilogue", c_int), ("bias", vp),
                 ("D", vp), ("d_dtype", c_int), ("ldd", c_i64),
                 ("D2", vp), ("aux", vp), ("row_scale", vp), ("rows_per_image", c_int),
-                ("H", c_int), ("W", c_int), ("ws", c_int), ("shift", c_int)]
+                ("H", c_int), ("W", c_int), ("ws", c_int), ("shift", c_int), ("colsum_a", vp)]
 
 
 class AttnArgs(C.Structure):

@@ -71,8 +71,8 @@ __global__ void attn_simt_bwd_kernel(AttnSimtParams p) {
   float* sk = sq + N * 33;
   float* sv = sk + N * 33;
   float* sdo = sv + N * 33;
-  float* sp = sdo + N * 33;        // [N][N+1]
-  float* sds = sp + N * (N + 1);   // [N][N+1]
+  float* sp = sdo + N * 33;        // [N][N+1]  P; dS is recomputed from P, dO, V and delta (keeps window 12 within smem)
+  float* sdelta = sp + N * (N + 1);// [N]
   const float* base = p.qkv + (size_t)b * N * 3 * p.C + h * HD;
   const float* dobase = p.dout + (size_t)b * N * p.C + h * HD;
   for (int e = threadIdx.x; e < N * HD; e += blockDim.x) {
@@ -100,15 +100,17 @@ __global__ void attn_simt_bwd_kernel(AttnSimtParams p) {
       if (mrow) s += mrow[j];
       float pr = expf(s - l);
       sp[i * (N + 1) + j] = pr;
-      sds[i * (N + 1) + j] = dp;       // temporarily dP
       delta = fmaf(pr, dp, delta);
     }
+    sdelta[i] = delta;
     float dq[HD];
 #pragma unroll
     for (int d = 0; d < HD; ++d) dq[d] = 0.f;
     for (int j = 0; j < N; ++j) {
-      float ds = sp[i * (N + 1) + j] * (sds[i * (N + 1) + j] - delta);
-      sds[i * (N + 1) + j] = ds;
+      float dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) dp = fmaf(sdo[i * 33 + d], sv[j * 33 + d], dp);
+      float ds = sp[i * (N + 1) + j] * (dp - delta);
       atomicAdd(p.dbias + ((size_t)h * N + i) * N + j, ds);
 #pragma unroll
       for (int d = 0; d < HD; ++d) dq[d] = fmaf(ds, sk[j * 33 + d], dq[d]);
@@ -124,7 +126,11 @@ __global__ void attn_simt_bwd_kernel(AttnSimtParams p) {
 #pragma unroll
     for (int d = 0; d < HD; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
     for (int r = 0; r < N; ++r) {
-      float ds = sds[r * (N + 1) + j], pr = sp[r * (N + 1) + j];
+      float dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) dp = fmaf(sdo[r * 33 + d], sv[j * 33 + d], dp);
+      const float pr = sp[r * (N + 1) + j];
+      const float ds = pr * (dp - sdelta[r]);
 #pragma unroll
       for (int d = 0; d < HD; ++d) {
         dk[d] = fmaf(ds, sq[r * 33 + d], dk[d]);
@@ -168,7 +174,7 @@ int attn_simt_bwd(const swin_attn_args* a, cudaStream_t st) {
   int rc = attn_simt_common(a, &p, true);
   if (rc) return rc;
   if (p.B_ == 0) return 0;
-  size_t smem = ((size_t)4 * p.N * 33 + (size_t)2 * p.N * (p.N + 1)) * sizeof(float);
+  size_t smem = ((size_t)4 * p.N * 33 + (size_t)p.N * (p.N + 1) + p.N) * sizeof(float);
   SWIN_REQUIRE(smem <= 200 * 1024, "attn_bwd(fp32): window too large for shared memory");
   int threads = ceil_div(p.N, 32) * 32;
   cudaFuncSetAttribute(attn_simt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -56,6 +56,16 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
   }
 }
 
+// colsum_a for the fp32 path: one thread per m, strided loop over k (A stored (K,M): coalesced across m)
+__global__ void simt_colsum_a_kernel(const float* __restrict__ A, long long lda, int M, int K, int k_chunk, float* __restrict__ out) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int k0 = blockIdx.y * k_chunk, k1 = min(K, k0 + k_chunk);
+  float s = 0.f;
+  for (int k = k0; k < k1; ++k) s += A[(long long)k * lda + m];
+  atomicAdd(out + m, s);
+}
+
 int gemm_simt(const swin_gemm_args* a, cudaStream_t st) {
   EpiParams p;
   int rc = make_epi_params(a, &p);
@@ -78,6 +88,13 @@ int gemm_simt(const swin_gemm_args* a, cudaStream_t st) {
   dim3 grid(gx, gy, splits);
   gemm_simt_kernel<<<grid, 256, 0, st>>>((const float*)a->A, sam, sak, (const float*)a->B, sbn, sbk, a->K, kps, p);
   SWIN_LAUNCH_CHECK();
+  if (a->colsum_a != nullptr) {
+    SWIN_REQUIRE(a->epilogue == SWIN_EPI_ATOMIC_ADD && a->a_trans, "gemm: colsum_a needs ATOMIC_ADD and a_trans=1");
+    const int kc = ceil_div(a->K, 4 * kNumSMs) < 64 ? 64 : ceil_div(a->K, 4 * kNumSMs);
+    dim3 g2(ceil_div(a->M, 128), ceil_div(a->K, kc));
+    simt_colsum_a_kernel<<<g2, 128, 0, st>>>((const float*)a->A, a->lda, a->M, a->K, kc, a->colsum_a);
+    SWIN_LAUNCH_CHECK();
+  }
   return 0;
 }
 

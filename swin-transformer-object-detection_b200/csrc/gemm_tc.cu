@@ -22,6 +22,7 @@ struct GemmTcParams {
   int stages;
   uint32_t a_bytes, b_bytes;   // TMA bytes per stage (expect_tx)
   uint32_t epi_bytes_per_warp; // epilogue staging per warp in dynamic smem (4 KB; 8 KB for fp32 class-2 double buffers)
+  float* colsum_a;             // split-K dW only: bias gradient via an all-ones N=16 MMA into TMEM columns [256,272)
   int tma_epi;                 // 1: STORE/GELU with bf16 outputs go out through TMA stores (tmD / tmD2)
   uint32_t stage_bytes;        // smem stride per stage: a_bytes + b_bytes rounded up to the 1024-byte swizzle-atom alignment
   EpiParams epi;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 8];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(8) uint64_t aux_bars[kEpiWarps][2];
+  __shared__ __align__(1024) __nv_bfloat16 ones_tile[(EPI_CLASS == 0 && A_MN && B_MN) ? 64 * 64 : 8];   // all-ones B operand (MN-major)
   __shared__ long long epi_rowdst[kEpiWarps][32];
   __shared__ float epi_rowscale[kEpiWarps][32];
 
@@ -119,8 +121,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   auto empty_bar = [&](int s) { return smem_u32(&bars[kMaxStages + s]); };
   auto tfull_bar = [&](int s) { return smem_u32(&bars[2 * kMaxStages + s]); };
   auto tempty_bar = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 4 + s]); };
-  const uint32_t acc_stride = p.block_n <= 128 ? 128u : 256u;      // TMEM columns per accumulator stage
-  const uint32_t num_acc = 512u / acc_stride;                       // 4 or 2 stages in flight
+  const bool do_colsum = (EPI_CLASS == 0 && A_MN && B_MN) && p.colsum_a != nullptr;
+  // TMEM columns per accumulator stage; with the bias-gradient MMA the unit owns all 512 columns (sum in [256,272))
+  const uint32_t acc_stride = do_colsum ? 512u : (p.block_n <= 128 ? 128u : 256u);
+  const uint32_t num_acc = 512u / acc_stride;                       // 4, 2 or 1 stages in flight
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -131,6 +135,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_slot), 512); tmem_relinquish(); }
+  if (EPI_CLASS == 0 && A_MN && B_MN) {
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) ones_tile[i] = __float2bfloat16(1.0f);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -194,6 +202,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             const uint64_t ad = A_MN ? umma_desc(sa + k * 2048, 8192, 1024, kSw128) : umma_desc(sa + k * 32, 16, 1024, kSw128);
             const uint64_t bd = B_MN ? umma_desc(sb + k * 2048, 8192, 1024, kSw128) : umma_desc(sb + k * 32, 16, 1024, kSw128);
             umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (do_colsum)      // sum_k A[m,k] * 1  -> 16 identical columns at [256,272)
+              umma_bf16(d_tmem + 256, ad, umma_desc(smem_u32(ones_tile) + k * 2048, 8192, 1024, kSw128), umma_idesc_bf16(16, A_MN, B_MN),
+                        (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(s));          // smem slot reusable once these MMAs retire
         }
@@ -415,6 +426,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         }
         __syncwarp();
       }
+      if (do_colsum && n_blk == 0 && ew < 4) {        // one warp per lane quarter: row sums of A^T = bias gradient
+        uint32_t cs[16];
+        tmem_ld16(taddr + 256, cs);
+        tmem_ld_wait();
+        const int m = row_base + lane;
+        if (m < p.epi.M) atomicAdd(p.colsum_a + m, __uint_as_float(cs[0]));
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -457,6 +475,11 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
     if (p.splits > maxs) p.splits = maxs;
     if (p.splits < 1) p.splits = 1;
   }
+  p.colsum_a = nullptr;
+  if (a->colsum_a != nullptr) {
+    SWIN_REQUIRE(a->epilogue == SWIN_EPI_ATOMIC_ADD && a_mn && b_mn, "gemm: colsum_a needs ATOMIC_ADD with a_trans = b_trans = 1");
+    p.colsum_a = a->colsum_a;
+  }
   p.kb_per_split = ceil_div(p.kb_total, p.splits);
   p.splits = ceil_div(p.kb_total, p.kb_per_split);
   p.a_bytes = TBM * TBK * 2;
@@ -496,7 +519,7 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
       rc = make_tmap_bf16_2d(&tmD2, a->aux, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
       p.tma_epi = 2;
-    } else if (a->epilogue == SWIN_EPI_RESIDUAL && (220u * 1024 - 8192u * kEpiWarps - 1024) / stage_bytes >= 4) {
+    } else if (a->epilogue == SWIN_EPI_RESIDUAL && (212u * 1024 - 8192u * kEpiWarps - 1024) / stage_bytes >= 4) {
       rc = make_tmap_f32_2d(&tmD, a->D, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
       rc = make_tmap_f32_2d(&tmD2, a->aux, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -507,7 +530,7 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   p.epi_bytes_per_warp = (p.tma_epi == 2 && a->epilogue == SWIN_EPI_RESIDUAL) ? 8192u : 4096u;
   const uint32_t epi_bytes = p.epi_bytes_per_warp * kEpiWarps;
   {
-    const uint32_t ring_budget = 220 * 1024 - epi_bytes - 1024;     // dynamic smem: ring + epilogue staging + alignment slack
+    const uint32_t ring_budget = 212 * 1024 - epi_bytes - 1024;     // dynamic smem: ring + epilogue staging + alignment slack
     int st2 = (int)(ring_budget / stage_bytes);
     if (st2 < p.stages) p.stages = st2;
   }
@@ -519,7 +542,7 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
     static bool attr_done = false;                                                                                \
     if (!attr_done) {                                                                                             \
       cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AM, BM, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           220 * 1024);                                                           \
+                                           212 * 1024);                                                           \
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }      \
       attr_done = true;                                                                                           \
     }                                                                                                             \

@@ -91,9 +91,9 @@ class SwinBlockFn(torch.autograd.Function):
         dfc2w = torch.zeros_like(fc2w, dtype=torch.float32)
         ops.gemm(dy2, h, Cc, hid, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc2w)
         du = ops.gemm(dy2, _w(fc2w, dt), T, hid, Cc, b_trans=True, epilogue=L.EPI_DGELU, aux=u)
-        dfc1b = ops.colsum(du)
         dfc1w = torch.zeros_like(fc1w, dtype=torch.float32)
-        ops.gemm(du, xn, hid, Cc, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc1w)
+        dfc1b = torch.zeros((hid,), dtype=torch.float32, device=du.device)      # = colsum(du), from the same GEMM
+        ops.gemm(du, xn, hid, Cc, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc1w, colsum_a=dfc1b)
         dxn = ops.gemm(du, _w(fc1w, dt), T, Cc, hid, b_trans=True)
         # LN2 backward + residual-gradient add; the same kernel also emits dY of the proj Linear (drop-path scaled,
         # cast and partitioned into window slots) and its column sums (= d proj.bias)
@@ -105,9 +105,9 @@ class SwinBlockFn(torch.autograd.Function):
         do = ops.gemm(dy1, _w(projw, dt), Tp, Cc, Cc, b_trans=True)
         dqkv, dbias = ops.window_attn_bwd(qkv.view(-1, N, 3 * Cc), o, do.view(-1, N, Cc), lse, bias, mask, Tp // N, nH, ws, scale, mask_nz, canon)
         dtable = ops.rel_bias_reduce(dbias, ws)
-        dqkvb = ops.colsum(dqkv) if has_qkvb else None
+        dqkvb = torch.zeros((3 * Cc,), dtype=torch.float32, device=dqkv.device) if has_qkvb else None
         dqkvw = torch.zeros_like(qkvw, dtype=torch.float32)
-        ops.gemm(dqkv, xw, 3 * Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dqkvw)
+        ops.gemm(dqkv, xw, 3 * Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dqkvw, colsum_a=dqkvb)
         dxw = ops.gemm(dqkv.view(Tp, 3 * Cc), _w(qkvw, dt), Tp, Cc, 3 * Cc, b_trans=True)
         dx, dn1w, dn1b = ops.ln_bwd(1, dxw, x, n1w.detach(), mean1, rstd1, dx1, B, H, W, Cc, ws, shift)
         return (dx, dn1w, dn1b, dtable, dqkvw, dqkvb, dprojw, dprojb, dn2w, dn2b, dfc1w, dfc1b, dfc2w, dfc2b,

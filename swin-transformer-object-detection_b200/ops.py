@@ -232,9 +232,9 @@ def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_trans: 
          epilogue: int = L.EPI_STORE, bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
          out_dtype: Optional[int] = None, out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
          row_scale: Optional[torch.Tensor] = None, rows_per_image: int = 0, geom=(0, 0, 0, 0),
-         out_rows: Optional[int] = None) -> torch.Tensor:
+         out_rows: Optional[int] = None, colsum_a: Optional[torch.Tensor] = None) -> torch.Tensor:
     """acc = A(M,K) . B(N,K)^T with a fused epilogue; see include/swin_b200.h."""
-    _chk(A, Bm, bias, out, out2, aux, row_scale)
+    _chk(A, Bm, bias, out, out2, aux, row_scale, colsum_a)
     dt = _DT[A.dtype]
     assert Bm.dtype == A.dtype
     if out is None:
@@ -243,7 +243,7 @@ def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_trans: 
     a = L.GemmArgs(dtype=dt, M=M, N=N, K=K, A=_p(A), a_trans=int(a_trans), lda=A.stride(-2) if A.dim() >= 2 else K,
                    B=_p(Bm), b_trans=int(b_trans), ldb=Bm.stride(-2), epilogue=epilogue, bias=_p(bias), D=_p(out),
                    d_dtype=_DT[out.dtype], ldd=N, D2=_p(out2), aux=_p(aux), row_scale=_p(row_scale),
-                   rows_per_image=rows_per_image, H=geom[0], W=geom[1], ws=geom[2], shift=geom[3])
+                   rows_per_image=rows_per_image, H=geom[0], W=geom[1], ws=geom[2], shift=geom[3], colsum_a=_p(colsum_a))
     _count()
     if _TIMER is not None and dt == L.BF16:
         _TIMER.begin("gemm_tc", 2.0 * M * N * K)

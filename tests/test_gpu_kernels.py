@@ -262,9 +262,11 @@ def test_gemm_epilogues(dtype):
     assert rel(out, res.double().cpu() + ysc.view(T, C)) < (1e-5 if dtype == "f32" else 2e-3)
     # ATOMIC_ADD split-K weight gradient: dW = dY^T X
     dW = torch.zeros(4 * C, C, device=DEV)
+    db = torch.zeros(4 * C, device=DEV)
     dY = torch.randn(T, 4 * C, generator=g).to(td).to(DEV)
-    ops.gemm(dY, X, 4 * C, C, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dW)
+    ops.gemm(dY, X, 4 * C, C, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dW, colsum_a=db)
     assert rel(dW, dY.double().cpu().t() @ X.double().cpu()) < 1e-5
+    assert rel(db, dY.double().cpu().sum(0)) < 1e-5          # bias gradient from the all-ones MMA
 
 
 def test_gemm_bf16_matches_fp32_kernel_on_device():
@@ -275,9 +277,12 @@ def test_gemm_bf16_matches_fp32_kernel_on_device():
     X = torch.randn(T, Ci, device=DEV).bfloat16()
     d16 = torch.zeros(Co, Ci, device=DEV)
     d32 = torch.zeros(Co, Ci, device=DEV)
-    ops.gemm(dY, X, Co, Ci, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=d16)
-    ops.gemm(dY.float(), X.float(), Co, Ci, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=d32)
+    b16 = torch.zeros(Co, device=DEV)
+    b32 = torch.zeros(Co, device=DEV)
+    ops.gemm(dY, X, Co, Ci, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=d16, colsum_a=b16)
+    ops.gemm(dY.float(), X.float(), Co, Ci, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=d32, colsum_a=b32)
     assert rel(d16, d32) < 1e-4
+    assert rel(b16, dY.double().sum(0)) < 1e-5 and rel(b32, dY.double().sum(0)) < 1e-5
 
 
 # ---------------------------------------------------------------- window attention core
@@ -346,3 +351,19 @@ def test_window_attention_closed_form_canonical_mask_equals_tensor_mask(H, W):
     d1, b1 = ops.window_attn_bwd(qkv, o1, dout, l1, bias, mask, B_, nH, ws, 32 ** -0.5, nz)
     d2, b2 = ops.window_attn_bwd(qkv, o1, dout, l1, bias, mask, B_, nH, ws, 32 ** -0.5, nz, canon=(nwh, nww))
     assert torch.equal(d1, d2) and rel(b2, b1) < 1e-5
+
+
+def test_window_attention_core_window12_fp32():
+    """BASELINE config 5 also sweeps window 12: served by the fp32 kernels (forward and backward)."""
+    ops, L = _ops()
+    ws, N, nH, B_ = 12, 144, 2, 4
+    g = torch.Generator(device="cpu").manual_seed(12)
+    qkv = torch.randn(B_, N, 3 * nH * 32, generator=g)
+    bias = torch.randn(nH, N, N, generator=g) * 0.5
+    mask = torch.from_numpy(so.shift_mask_np(20, 33, ws, 6)[2:6])          # nW = 4
+    cot = torch.randn(B_, N, nH * 32, generator=g)
+    o_r, lse_r, dqkv_r, dbias_r = _attn_ref(qkv, bias, mask, nH, 32 ** -0.5, cot)
+    o, lse = ops.window_attn_fwd(qkv.to(DEV), bias.to(DEV), mask.to(DEV), B_, nH, ws, 32 ** -0.5)
+    assert rel(o, o_r) < 1e-5 and rel(lse, lse_r) < 1e-5
+    dqkv, dbias = ops.window_attn_bwd(qkv.to(DEV), o, cot.to(DEV), lse, bias.to(DEV), mask.to(DEV), B_, nH, ws, 32 ** -0.5)
+    assert rel(dqkv, dqkv_r) < 1e-5 and rel(dbias, dbias_r) < 1e-5
