@@ -94,7 +94,8 @@ __device__ __forceinline__ void load_bias_tile(float* sBias, const float* __rest
 // ------------------------------------------------------------------------------------------ forward
 constexpr uint32_t kFwdTiles = 3 * kTileBytes;     // Q,K,V per buffer
 
-__global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnTcParams p) {
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                                       const __grid_constant__ CUtensorMap tmOut, AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[5];              // load[2], s[2], o
   __shared__ uint32_t tmem_slot;
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __gr
     }
     sRed[0][hf][r] = mx;
     TMARK(2);
+    if (tid == 0) tma_store_wait_read<0>();      // the previous item's O tile (staged in sP) has been drained by TMA
     __syncthreads();
     TMARK(3);
     float sum = 0.f;
@@ -254,26 +256,36 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __gr
     uint32_t o[16];
     tmem_ld16(tO + lane_off + wloc * 32 + hf * 16, o);
     tmem_ld_wait();
-    if (valid) {
-      const float inv = 1.0f / sum;
-      uint8_t* orow = reinterpret_cast<uint8_t*>(p.out + ((size_t)win * AN + i) * p.C + h * AHD + hf * 16);
+    {
+      // O rows -> bf16 tile in sP (free: the P.V MMA has completed), 64-byte-swizzle layout, window w at +4096;
+      // then one TMA store of 49 rows x 32 columns per window instead of per-thread strided stores
+      const float inv = valid ? 1.0f / sum : 0.f;
+      const uint32_t swz = (uint32_t)((r >> 1) & 3);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         float t[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) t[e] = __uint_as_float(o[8 * c + e]) * inv;
-        store_row_bf16x8(orow + 16 * c, t);
+        store_row_bf16x8(sP + r * 64 + (((uint32_t)(hf * 2 + c) ^ swz) << 4), t);
       }
-      if (hf == 0) p.lse[((size_t)win * p.nH + h) * AN + i] = (mx + log2f(sum)) * 0.6931471805599453f;   // natural-log LSE
+      if (valid && hf == 0) p.lse[((size_t)win * p.nH + h) * AN + i] = (mx + log2f(sum)) * 0.6931471805599453f;   // natural-log LSE
     }
     TMARK(7);
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     TMARK(8);
+    if (tid == 0) {
+#pragma unroll
+      for (int w = 0; w < 2; ++w)
+        if (2 * pair + w < p.B_) tma_store_2d(&tmOut, aP + w * 4096, h * AHD, (2 * pair + w) * AN);
+      tma_store_commit();
+    }
     // tile buffer `buf` (Q,K used by S(it), V by O(it)) is free again: fetch item it+2 into it
     if (tid == 0 && pair + 2 * stride < p.npairs) issue_loads(pair + 2 * stride, buf);
   }
   TPRINT("attn_fwd");
+  if (tid == 0) tma_store_wait_all<0>();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_slot, 256); }
 }
 
@@ -281,7 +293,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __gr
 constexpr uint32_t kBwdTiles = 4 * kTileBytes;     // Q,K,V,dO per buffer
 
 __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
-                                                                       const __grid_constant__ CUtensorMap tmDO, AttnTcParams p) {
+                                                                       const __grid_constant__ CUtensorMap tmDO,
+                                                                       const __grid_constant__ CUtensorMap tmDQKV, AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[4];
   __shared__ uint32_t tmem_slot;
@@ -416,6 +429,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
     }
     sRed[hf][r] = delta;
     TMARK(2);
+    if (tid == 0) tma_store_wait_read<0>();      // previous item's dQ/dK/dV tiles (staged in sP/sdS) drained
     __syncthreads();
     TMARK(3);
     delta = sRed[0][r] + sRed[1][r];
@@ -452,25 +466,38 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
     mbar_wait(bar_o, ph);
     tc_fence_after();
     TMARK(6);
-    uint32_t o[3][16];
-    tmem_ld16(tdQ + lane_off + wloc * 32 + hf * 16, o[0]);
-    tmem_ld16(tdK + lane_off + wloc * 32 + hf * 16, o[1]);
-    tmem_ld16(tdV + lane_off + wloc * 32 + hf * 16, o[2]);
-    tmem_ld_wait();
-    if (valid) {
+    {
+      // dQ / dK / dV rows -> three bf16 tiles (8 KB each, 64-byte swizzle) in the sP + sdS region, which is free now
+      // that the three MMAs have completed; then 49x32 TMA stores into the [q|k|v] column blocks of dqkv
+      const uint32_t swz = (uint32_t)((r >> 1) & 3);
 #pragma unroll
-      for (int part = 0; part < 3; ++part) {   // 0: dQ, 1: dK, 2: dV  (column blocks of dqkv)
-        uint8_t* orow = reinterpret_cast<uint8_t*>(p.dqkv + ((size_t)win * AN + i) * 3 * p.C + part * p.C + h * AHD + hf * 16);
-        store_row_bf16x8(orow, reinterpret_cast<const float*>(o[part]));
-        store_row_bf16x8(orow + 16, reinterpret_cast<const float*>(o[part] + 8));
+      for (int part = 0; part < 3; ++part) {   // 0: dQ, 1: dK, 2: dV
+        uint32_t o[16];
+        tmem_ld16((part == 0 ? tdQ : part == 1 ? tdK : tdV) + lane_off + wloc * 32 + hf * 16, o);
+        tmem_ld_wait();
+        uint8_t* trow = sP + part * 8192 + r * 64;
+        store_row_bf16x8(trow + (((uint32_t)(hf * 2 + 0) ^ swz) << 4), reinterpret_cast<const float*>(o));
+        store_row_bf16x8(trow + (((uint32_t)(hf * 2 + 1) ^ swz) << 4), reinterpret_cast<const float*>(o + 8));
       }
     }
     TMARK(7);
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     TMARK(8);
+    if (tid == 0) {
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        if (2 * pair + w >= p.B_) continue;
+#pragma unroll
+        for (int part = 0; part < 3; ++part)
+          tma_store_2d(&tmDQKV, aP + part * 8192 + w * 4096, part * p.C + h * AHD, (2 * pair + w) * AN);
+      }
+      tma_store_commit();
+    }
   }
   TPRINT("attn_bwd");
+  if (tid == 0) tma_store_wait_all<0>();
   if (i < AN) {
     float* dst = p.dbias + ((size_t)h * AN + i) * AN + jbase;
 #pragma unroll
@@ -521,7 +548,10 @@ int attn_tc_fwd(const swin_attn_args* a, cudaStream_t st) {
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
-  attn_tc_fwd_kernel<<<p.nH * p.ctas_per_head, kAttnThreads, smem, st>>>(tm, p);
+  CUtensorMap tmo;
+  rc = make_tmap_bf16_2d(&tmo, a->out, (uint64_t)p.C, (uint64_t)p.B_ * AN, (uint64_t)p.C * 2, AHD, AN, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  attn_tc_fwd_kernel<<<p.nH * p.ctas_per_head, kAttnThreads, smem, st>>>(tm, tmo, p);
   SWIN_LAUNCH_CHECK();
   return 0;
 }
@@ -543,7 +573,10 @@ int attn_tc_bwd(const swin_attn_args* a, cudaStream_t st) {
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
-  attn_tc_bwd_kernel<<<p.nH * p.ctas_per_head, kAttnThreads, smem, st>>>(tm, tmdo, p);
+  CUtensorMap tmdq;
+  rc = make_tmap_bf16_2d(&tmdq, a->dqkv, (uint64_t)3 * p.C, (uint64_t)p.B_ * AN, (uint64_t)3 * p.C * 2, AHD, AN, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  attn_tc_bwd_kernel<<<p.nH * p.ctas_per_head, kAttnThreads, smem, st>>>(tm, tmdo, tmdq, p);
   SWIN_LAUNCH_CHECK();
   return 0;
 }

@@ -40,6 +40,17 @@ def _w(param: torch.Tensor, dt: int) -> torch.Tensor:
     return w16
 
 
+def _zeros_flat(device, *shapes):
+    """Several zero-initialised fp32 tensors carved (16-byte aligned) out of ONE allocation / ONE memset."""
+    sizes = [(int(torch.Size(sh).numel()) + 3) // 4 * 4 for sh in shapes]
+    flat = torch.zeros((sum(sizes),), dtype=torch.float32, device=device)
+    out, off = [], 0
+    for sh, n in zip(shapes, sizes):
+        out.append(flat[off:off + int(torch.Size(sh).numel())].view(sh))
+        off += n
+    return out
+
+
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     t = t.detach()
     if t.dtype != torch.float32:
@@ -88,11 +99,10 @@ class SwinBlockFn(torch.autograd.Function):
         dx2 = _f32c(dx2)
         # ---- MLP branch
         dy2, dfc2b = ops.scale_cast(dx2, s2, 0, B, H, W, Cc, 1, 0, dt, want_colsum=True)  # (T, C) + bias grad in one pass
-        dfc2w = torch.zeros_like(fc2w, dtype=torch.float32)
+        dfc2w, dfc1w, dprojw, dqkvw, dfc1b, dqkvb_buf = _zeros_flat(
+            dx2.device, tuple(fc2w.shape), tuple(fc1w.shape), tuple(projw.shape), tuple(qkvw.shape), (hid,), (3 * Cc,))
         ops.gemm(dy2, h, Cc, hid, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc2w)
         du = ops.gemm(dy2, _w(fc2w, dt), T, hid, Cc, b_trans=True, epilogue=L.EPI_DGELU, aux=u)
-        dfc1w = torch.zeros_like(fc1w, dtype=torch.float32)
-        dfc1b = torch.zeros((hid,), dtype=torch.float32, device=du.device)      # = colsum(du), from the same GEMM
         ops.gemm(du, xn, hid, Cc, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc1w, colsum_a=dfc1b)
         dxn = ops.gemm(du, _w(fc1w, dt), T, Cc, hid, b_trans=True)
         # LN2 backward + residual-gradient add; the same kernel also emits dY of the proj Linear (drop-path scaled,
@@ -100,13 +110,11 @@ class SwinBlockFn(torch.autograd.Function):
         dx1, dn2w, dn2b, dy1, dprojb = ops.ln_bwd(0, dxn, x1, n2w.detach(), mean2, rstd2, dx2, B, H, W, Cc, 1, 0,
                                                   emit_windows=(ws, shift, s1))
         # ---- attention branch
-        dprojw = torch.zeros_like(projw, dtype=torch.float32)
         ops.gemm(dy1, o, Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dprojw)
         do = ops.gemm(dy1, _w(projw, dt), Tp, Cc, Cc, b_trans=True)
         dqkv, dbias = ops.window_attn_bwd(qkv.view(-1, N, 3 * Cc), o, do.view(-1, N, Cc), lse, bias, mask, Tp // N, nH, ws, scale, mask_nz, canon)
         dtable = ops.rel_bias_reduce(dbias, ws)
-        dqkvb = torch.zeros((3 * Cc,), dtype=torch.float32, device=dqkv.device) if has_qkvb else None
-        dqkvw = torch.zeros_like(qkvw, dtype=torch.float32)
+        dqkvb = dqkvb_buf if has_qkvb else None
         ops.gemm(dqkv, xw, 3 * Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dqkvw, colsum_a=dqkvb)
         dxw = ops.gemm(dqkv.view(Tp, 3 * Cc), _w(qkvw, dt), Tp, Cc, 3 * Cc, b_trans=True)
         dx, dn1w, dn1b = ops.ln_bwd(1, dxw, x, n1w.detach(), mean1, rstd1, dx1, B, H, W, Cc, ws, shift)
@@ -118,7 +126,7 @@ class WindowAttentionFn(torch.autograd.Function):
     """x_windows (B_, N, C) -> (B_, N, C): qkv Linear, attention core, proj Linear."""
 
     @staticmethod
-    def forward(ctx, xwin, table, qkvw, qkvb, projw, projb, mask, mask_nz, ws, nH, scale, dt):
+    def forward(ctx, xwin, table, qkvw, qkvb, projw, projb, mask, mask_nz, canon, ws, nH, scale, dt):
         B_, N, Cc = xwin.shape
         rows = B_ * N
         xin = _f32c(xwin)
@@ -126,16 +134,16 @@ class WindowAttentionFn(torch.autograd.Function):
         xw = xw.view(rows, Cc)
         qkv = ops.gemm(xw, _w(qkvw, dt), rows, 3 * Cc, Cc, bias=None if qkvb is None else qkvb.detach())
         bias = ops.rel_bias_expand(table.detach().contiguous(), ws)
-        o, lse = ops.window_attn_fwd(qkv.view(B_, N, 3 * Cc), bias, mask, B_, nH, ws, scale, mask_nz)
+        o, lse = ops.window_attn_fwd(qkv.view(B_, N, 3 * Cc), bias, mask, B_, nH, ws, scale, mask_nz, canon)
         y = ops.gemm(o.view(rows, Cc), _w(projw, dt), rows, Cc, Cc, bias=projb.detach(), out_dtype=L.F32)
         ctx.save_for_backward(table, qkvw, projw, mask, mask_nz, xw, qkv, bias, o, lse)
-        ctx.cfg = (B_, N, Cc, ws, nH, scale, dt, qkvb is not None, xwin.dtype)
+        ctx.cfg = (B_, N, Cc, ws, nH, scale, dt, qkvb is not None, xwin.dtype, canon)
         return y.view(B_, N, Cc).to(xwin.dtype)
 
     @staticmethod
     def backward(ctx, dy):
         table, qkvw, projw, mask, mask_nz, xw, qkv, bias, o, lse = ctx.saved_tensors
-        B_, N, Cc, ws, nH, scale, dt, has_qkvb, in_dtype = ctx.cfg
+        B_, N, Cc, ws, nH, scale, dt, has_qkvb, in_dtype, canon = ctx.cfg
         rows = B_ * N
         dyf = _f32c(dy)
         dy1 = dyf.view(rows, Cc) if dt == L.F32 else ops.scale_cast(dyf, None, 0, 1, rows, 1, Cc, 1, 0, dt)
@@ -143,13 +151,13 @@ class WindowAttentionFn(torch.autograd.Function):
         dprojw = torch.zeros_like(projw, dtype=torch.float32)
         ops.gemm(dy1, o.view(rows, Cc), Cc, Cc, rows, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dprojw)
         do = ops.gemm(dy1, _w(projw, dt), rows, Cc, Cc, b_trans=True)
-        dqkv, dbias = ops.window_attn_bwd(qkv.view(B_, N, 3 * Cc), o, do.view(B_, N, Cc), lse, bias, mask, B_, nH, ws, scale, mask_nz)
+        dqkv, dbias = ops.window_attn_bwd(qkv.view(B_, N, 3 * Cc), o, do.view(B_, N, Cc), lse, bias, mask, B_, nH, ws, scale, mask_nz, canon)
         dtable = ops.rel_bias_reduce(dbias, ws)
         dqkvb = ops.colsum(dqkv) if has_qkvb else None
         dqkvw = torch.zeros_like(qkvw, dtype=torch.float32)
         ops.gemm(dqkv.view(rows, 3 * Cc), xw, 3 * Cc, Cc, rows, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dqkvw)
         dx = ops.gemm(dqkv.view(rows, 3 * Cc), _w(qkvw, dt), rows, Cc, 3 * Cc, b_trans=True, out_dtype=L.F32)
-        return dx.view(B_, N, Cc).to(in_dtype), dtable, dqkvw, dqkvb, dprojw, dprojb, None, None, None, None, None, None
+        return dx.view(B_, N, Cc).to(in_dtype), dtable, dqkvw, dqkvb, dprojw, dprojb, None, None, None, None, None, None, None
 
 
 class PatchMergingFn(torch.autograd.Function):

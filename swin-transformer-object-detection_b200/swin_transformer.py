@@ -55,6 +55,40 @@ def window_reverse(windows: torch.Tensor, window_size: int, H: int, W: int) -> t
     return ops.window_reverse(windows.contiguous(), window_size, H, W)
 
 
+_CANON_CACHE = {}
+
+
+def _canonical_grid(mask: torch.Tensor, ws: int, shift: int):
+    """(nwh, nww) if ``mask`` is bit-for-bit the canonical SW-MSA mask (REF:370-389) of some window grid with nwh*nww ==
+    mask.shape[0], else (0, 0).  Masks made by BasicLayer.attn_mask carry the answer as an attribute; a mask that
+    arrives from elsewhere (e.g. built by reference code) is compared once against the candidate grids and the verdict
+    is cached per (storage, version), so the attention kernel can evaluate it in closed form instead of reading it."""
+    tag = getattr(mask, "_swin_canon", None)
+    if tag is not None:
+        return tag
+    if ws != 7 or shift != 3 or mask.dim() != 3 or mask.shape[1] != ws * ws:
+        return (0, 0)
+    key = (mask.data_ptr(), mask._version, tuple(mask.shape), str(mask.device))
+    hit = _CANON_CACHE.get(key)
+    if hit is not None:
+        return hit
+    if torch.cuda.is_current_stream_capturing():
+        return (0, 0)                      # cannot compare (needs a host read) while capturing: honour the tensor
+    nW, verdict = mask.shape[0], (0, 0)
+    for nwh in range(1, nW + 1):
+        if nW % nwh:
+            continue
+        nww = nW // nwh
+        cand = ops.shift_mask(nwh * ws, nww * ws, ws, shift, mask.device)
+        if torch.equal(cand, mask):
+            verdict = (nwh, nww)
+            break
+    if len(_CANON_CACHE) > 64:
+        _CANON_CACHE.clear()
+    _CANON_CACHE[key] = verdict
+    return verdict
+
+
 class DropPath(nn.Module):
     """Stochastic depth per sample (timm semantics used at REF:190,252,253).  ``sample_scale`` returns the
     (B,) multiplier floor(keep + U[0,1)) / keep that the fused residual epilogues apply; draws one uniform per
@@ -132,13 +166,15 @@ class WindowAttention(nn.Module):
         if self.training and any(p > 0 for p in self._drops):
             raise NotImplementedError("attention/projection dropout > 0 is not implemented in the fused kernels")
         mask_nz = None
+        canon = (0, 0)
         if mask is not None:
             mask = mask.detach().float().contiguous()
             mask_nz = getattr(mask, "_swin_nz", None)
             if mask_nz is None:
                 mask_nz = ops.mask_nonzero(mask)
+            canon = _canonical_grid(mask, self.window_size[0], self.window_size[0] // 2)
         return WindowAttentionFn.apply(x, self.relative_position_bias_table, self.qkv.weight, self.qkv.bias,
-                                       self.proj.weight, self.proj.bias, mask, mask_nz, self.window_size[0], self.num_heads,
+                                       self.proj.weight, self.proj.bias, mask, mask_nz, canon, self.window_size[0], self.num_heads,
                                        float(self.scale), self._dt)
 
 
@@ -180,7 +216,8 @@ class SwinTransformerBlock(nn.Module):
             if mask_nz is None:
                 mask_nz = ops.mask_nonzero(mask)
             # the mask built by BasicLayer.attn_mask is the canonical one: the kernel evaluates it in closed form
-            canon = getattr(mask_matrix, "_swin_canon", (0, 0)) if self.window_size == 7 and self.shift_size == 3 else (0, 0)
+            canon = _canonical_grid(mask_matrix if getattr(mask_matrix, "_swin_canon", None) is not None else mask,
+                                    self.window_size, self.shift_size)
         s1 = s2 = None
         if isinstance(self.drop_path, DropPath):
             s1 = self.drop_path.sample_scale(x)      # attention-branch draw first, then MLP (REF:252-253)

@@ -219,3 +219,25 @@ def test_use_checkpoint_matches_plain():
         sum(o.sum() for o in net(im)).backward()
         res.append((im.grad.clone(), net.layers[0].blocks[1].attn.qkv.weight.grad.clone()))
     assert so.rel_l2(res[1][0], res[0][0]) < 1e-5 and so.rel_l2(res[1][1], res[0][1]) < 1e-5
+
+
+def test_untagged_canonical_mask_is_detected_and_matches():
+    """A canonical mask that arrives as a plain tensor (as reference code would build it) takes the closed-form kernel
+    path after a one-off comparison; a perturbed mask must be honoured as given."""
+    import swin_b200
+    from swin_b200.swin_transformer import _canonical_grid
+    C, nH, ws, B, H, W = 64, 2, 7, 2, 10, 13
+    layer = swin_b200.BasicLayer(dim=C, depth=2, num_heads=nH, window_size=ws, drop_path=[0.0, 0.0], compute_dtype="bf16").to(DEV)
+    blk = layer.blocks[1]
+    blk.H, blk.W = H, W
+    x = torch.randn(B, H * W, C, device=DEV)
+    tagged = layer.attn_mask(H, W, x.device)
+    plain = torch.from_numpy(so.shift_mask_np(H, W, ws, 3)).to(DEV)
+    assert _canonical_grid(plain, ws, 3) == (2, 2)
+    y_tag = blk(x, tagged)
+    y_plain = blk(x, plain)
+    assert torch.equal(y_tag, y_plain)
+    odd = plain.clone()
+    odd[0, 0, 1] = -100.0
+    assert _canonical_grid(odd, ws, 3) == (0, 0)
+    assert not torch.equal(blk(x, odd), y_tag)
