@@ -12,8 +12,10 @@
 namespace swin {
 
 constexpr int TBM = 128, TBK = 64;
-constexpr int kEpiWarps = 8;                 // two per TMEM lane quarter, alternating 32-column chunks
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+constexpr int kEpiWarps = 8;                 // generic / class-2 epilogues: two warps per TMEM lane quarter
+constexpr int kEpiWarpsMax = 12;             // class 1 (STORE / GELU, ALU-heavy): three warps per lane quarter
+__host__ __device__ constexpr int epi_warps(int epi_class) { return epi_class == 1 ? kEpiWarpsMax : kEpiWarps; }
+__host__ __device__ constexpr int gemm_threads(int epi_class) { return 64 + 32 * epi_warps(epi_class); }
 constexpr int kMaxStages = 8;
 
 struct GemmTcParams {
@@ -100,13 +102,14 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, const float4* __re
 // EPI_CLASS: 0 = generic coalesced-lane epilogue; 1 = bf16 STORE/GELU through TMA stores; 2 = DGELU (bf16) / RESIDUAL (fp32):
 //            the aux tile is TMA-loaded, updated in place in the TMEM row layout and TMA-stored.
 template <bool A_MN, bool B_MN, int EPI_CLASS>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmD,
                                                                    const __grid_constant__ CUtensorMap tmD2, GemmTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 8];
   __shared__ uint32_t tmem_base_slot;
+  constexpr int kEW = epi_warps(EPI_CLASS);          // epilogue warps of this instantiation
   __shared__ __align__(8) uint64_t aux_bars[kEpiWarps][2];
   __shared__ __align__(1024) __nv_bfloat16 ones_tile[(EPI_CLASS == 0 && A_MN && B_MN) ? 64 * 64 : 8];   // all-ones B operand (MN-major)
   __shared__ long long epi_rowdst[kEpiWarps][32];
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 4; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
+    for (int s = 0; s < 4; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEW); }
     for (int w = 0; w < kEpiWarps; ++w) { mbar_init(smem_u32(&aux_bars[w][0]), 1); mbar_init(smem_u32(&aux_bars[w][1]), 1); }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
@@ -232,6 +235,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       // the two warps of a lane quarter take alternate 32-column chunks; which of them starts at chunk 0 flips every
       // tile so odd chunk counts (N = 96: 3 chunks) balance out across tiles
       const int chunk_sel = (ew >> 2) ^ (int)(u & 1);
+      constexpr int kGroups = kEW / 4;          // warps per lane quarter
       if (EPI_CLASS == 2) {
         // ---- DGELU (bf16: D = (acc+bias) * aux) / RESIDUAL (fp32: D = aux + row_scale * (acc+bias)):
         //      the aux tile of each 32x32 chunk is TMA-loaded one chunk ahead into a per-warp double buffer, updated in
@@ -345,9 +349,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         const uint32_t sbuf_a = smem_u32(sbuf);
         const uint32_t swz = (uint32_t)((lane >> 1) & 3);
         uint32_t v[32];
-        int c = chunk_sel * 32;
+        int c = (int)(((uint32_t)(ew >> 2) + u) % kGroups) * 32;        // rotate the starting warp every tile
         if (c < p.block_n) tmem_ld32(taddr + c, v);
-        for (; c < p.block_n; c += 64) {
+        for (; c < p.block_n; c += 32 * kGroups) {
           float4 b4[8];
           if (p.epi.bias != nullptr) {
 #pragma unroll
@@ -371,7 +375,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
               pu[2 * k] = pack_bf16(x0, x1); pu[2 * k + 1] = pack_bf16(x2, x3);
             }
           }
-          if (c + 64 < p.block_n) tmem_ld32(taddr + c + 64, v);      // next chunk's TMEM read overlaps the stores below
+          if (c + 32 * kGroups < p.block_n) tmem_ld32(taddr + c + 32 * kGroups, v);      // next chunk's TMEM read overlaps the stores below
           if (lane == 0) tma_store_wait_read<0>();                   // previous chunk's TMA stores have drained the staging tile
           __syncwarp();
 #pragma unroll
@@ -528,7 +532,7 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
     }
   }
   p.epi_bytes_per_warp = (p.tma_epi == 2 && a->epilogue == SWIN_EPI_RESIDUAL) ? 8192u : 4096u;
-  const uint32_t epi_bytes = p.epi_bytes_per_warp * kEpiWarps;
+  const uint32_t epi_bytes = p.epi_bytes_per_warp * (uint32_t)epi_warps(p.tma_epi);
   {
     const uint32_t ring_budget = 212 * 1024 - epi_bytes - 1024;     // dynamic smem: ring + epilogue staging + alignment slack
     int st2 = (int)(ring_budget / stage_bytes);
@@ -546,7 +550,7 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }      \
       attr_done = true;                                                                                           \
     }                                                                                                             \
-    gemm_tc_kernel<AM, BM, TE><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, tmD, tmD2, p);                         \
+    gemm_tc_kernel<AM, BM, TE><<<grid, gemm_threads(TE), smem, st>>>(tmA, tmB, tmD, tmD2, p);                         \
   } while (0)
 #define LAUNCH_TC2(AM, BM)                                                                                        \
   do {                                                                                                            \
