@@ -164,10 +164,16 @@ __device__ __forceinline__ long long merge_src(const LnGeom& lg, long long row, 
 
 template <typename T> struct Vec4IO;
 template <> struct Vec4IO<float> {
+  typedef float4 raw_t;
+  static __device__ __forceinline__ raw_t ldraw(const float* p, long long v) { return __ldg(reinterpret_cast<const float4*>(p) + v); }
+  static __device__ __forceinline__ float4 cvt(raw_t r) { return r; }
   static __device__ __forceinline__ float4 ld(const float* p, long long v) { return __ldg(reinterpret_cast<const float4*>(p) + v); }
   static __device__ __forceinline__ void st(float* p, long long v, float4 x) { reinterpret_cast<float4*>(p)[v] = x; }
 };
 template <> struct Vec4IO<__nv_bfloat16> {
+  typedef uint2 raw_t;
+  static __device__ __forceinline__ raw_t ldraw(const __nv_bfloat16* p, long long v) { return __ldg(reinterpret_cast<const uint2*>(p) + v); }
+  static __device__ __forceinline__ float4 cvt(raw_t u) { return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y)); }
   static __device__ __forceinline__ float4 ld(const __nv_bfloat16* p, long long v) {
     uint2 u = __ldg(reinterpret_cast<const uint2*>(p) + v);
     return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
@@ -214,18 +220,22 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
     }
     const bool act = inr && !pad;
     float4 r[VPL];
+    bool have[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {            // all loads first (clamped index), then the sums
+      const int v = gl + G * k;
+      long long srow = src0;
+      int off = v;
+      have[k] = act && v < vrow;
+      if (lg.mode == 2 && have[k]) { int q = v / vps; off = v - q * vps; srow = merge_src(lg, row, q); }
+      have[k] = have[k] && srow >= 0;
+      r[k] = Vec4IO<float>::ld(x, have[k] ? srow * vps + off : 0);
+    }
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
-      const int v = gl + G * k;
-      r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (act && v < vrow) {
-        long long srow = src0;
-        int off = v;
-        if (lg.mode == 2) { int q = v / vps; off = v - q * vps; srow = merge_src(lg, row, q); }
-        if (srow >= 0) r[k] = Vec4IO<float>::ld(x, srow * vps + off);
-        s += r[k].x + r[k].y + r[k].z + r[k].w;
-      }
+      if (!have[k]) r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      s += r[k].x + r[k].y + r[k].z + r[k].w;
     }
     const float mu = group_sum<G>(s) * inv_n;
     float q2 = 0.f;
@@ -290,29 +300,43 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const YT* __restrict__ dy, 
       dyrow = (long long)b * per_img_slots + token_to_slot(lg.g, (int)(row - (long long)b * per_img_tok));
     }
     const float mu = inr ? mean[row] : 0.f, rs = inr ? rstd[row] : 0.f;
+    // Phase A: every load of the row is issued unconditionally (clamped index, read-only path) before any use, so
+    // they overlap; a load-then-use sequence per vector gets serialised by in-order issue.
     float4 xh[VPL], gd[VPL], rr[VPL];
+    typename Vec4IO<YT>::raw_t draw[VPL];
     long long srow_k[VPL];
+    const float* rsrc = dres != nullptr ? dres : x;
+    const float rflag = dres != nullptr ? 1.0f : 0.0f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int v = gl + G * k;
+      const bool on = inr && v < vrow;
+      long long srow = row; int off = v;
+      if (lg.mode == 2 && on) { int q = v / vps; off = v - q * vps; srow = merge_src(lg, row, q); }
+      srow_k[k] = (on && srow >= 0) ? srow * vps + off : -1;
+      const long long xi = srow_k[k] >= 0 ? srow_k[k] : 0;
+      xh[k] = Vec4IO<float>::ld(x, xi);
+      rr[k] = Vec4IO<float>::ld(rsrc, xi);
+      draw[k] = Vec4IO<YT>::ldraw(dy, on ? dyrow * vrow + v : 0);
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int v = gl + G * k;
-      xh[k] = make_float4(0.f, 0.f, 0.f, 0.f); gd[k] = xh[k]; rr[k] = xh[k]; srow_k[k] = -1;
-      if (inr && v < vrow) {
-        long long srow = row; int off = v;
-        if (lg.mode == 2) { int q = v / vps; off = v - q * vps; srow = merge_src(lg, row, q); }
-        srow_k[k] = srow < 0 ? -1 : srow * vps + off;
-        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (srow >= 0) xv = Vec4IO<float>::ld(x, srow * vps + off);
-        if (srow >= 0 && dres != nullptr) rr[k] = Vec4IO<float>::ld(dres, srow * vps + off);   // issued with x/dy, before the reductions
-        float4 d = Vec4IO<YT>::ld(dy, dyrow * vrow + v);
-        float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + v);
-        xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        gd[k] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
-        s1 += gd[k].x + gd[k].y + gd[k].z + gd[k].w;
-        s2 += gd[k].x * xh[k].x + gd[k].y * xh[k].y + gd[k].z * xh[k].z + gd[k].w * xh[k].w;
-        ag[k].x += d.x * xh[k].x; ag[k].y += d.y * xh[k].y; ag[k].z += d.z * xh[k].z; ag[k].w += d.w * xh[k].w;
-        ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
-      }
+      const bool on = inr && v < vrow;
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + (on ? v : 0));
+      float4 d = Vec4IO<YT>::cvt(draw[k]);
+      if (!on) d = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 xv = srow_k[k] >= 0 ? xh[k] : make_float4(mu, mu, mu, mu);      // pad segment: x = 0 -> handled below
+      if (srow_k[k] < 0 && on) xh[k] = make_float4(-mu * rs, -mu * rs, -mu * rs, -mu * rs);   // merge-mode zero pad: xhat = (0 - mu) * rs
+      else xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      if (!on) xh[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rr[k] = make_float4(rr[k].x * rflag, rr[k].y * rflag, rr[k].z * rflag, rr[k].w * rflag);
+      gd[k] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+      s1 += gd[k].x + gd[k].y + gd[k].z + gd[k].w;
+      s2 += gd[k].x * xh[k].x + gd[k].y * xh[k].y + gd[k].z * xh[k].z + gd[k].w * xh[k].w;
+      ag[k].x += d.x * xh[k].x; ag[k].y += d.y * xh[k].y; ag[k].z += d.z * xh[k].z; ag[k].w += d.w * xh[k].w;
+      ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
     }
     const float m1 = group_sum<G>(s1) * inv_n, m2 = group_sum<G>(s2) * inv_n;
     long long slot2 = 0;
