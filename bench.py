@@ -86,25 +86,45 @@ class ClockSampler:
 
 
 class KernelTimer:
-    """CUDA-event pairs around every launch of one kernel class, on the launching (current) stream."""
+    """CUDA-event pairs around every library launch of an instrumented eager pass, on the launching (current) stream.
+    Each record carries the kernel's algorithmic flops and bytes (ops.py), so every class gets its own roofline."""
 
     def __init__(self):
-        self.pairs, self.flops = [], 0.0
+        self.recs = []          # (kind, flops, bytes, e0, e1)
 
-    def begin(self, kind, flops):
+    def begin(self, kind, flops=0.0, nbytes=0.0):
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        self.pairs.append((e0, e1))
-        self.flops += flops
+        self.recs.append((kind, flops, nbytes, e0, e1))
 
     def end(self):
-        self.pairs[-1][1].record()
+        self.recs[-1][4].record()
 
-    def summary(self):
+    def summary(self, prefix="gemm_tc"):
+        """(launches, ms, flops, bytes) summed over the records whose kind starts with ``prefix``."""
         torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) for a, b in self.pairs)
-        return len(self.pairs), ms, self.flops
+        sel = [r for r in self.recs if r[0].startswith(prefix)]
+        return len(sel), sum(r[3].elapsed_time(r[4]) for r in sel), sum(r[1] for r in sel), sum(r[2] for r in sel)
+
+    def table(self, steps, peak_tflops, peak_gbs):
+        """Per kernel kind: launches/step, ms/step, roofline ms/step = max(flops/peak, bytes/peak), achieved rates."""
+        torch.cuda.synchronize()
+        agg = {}
+        for kind, fl, nb, e0, e1 in self.recs:
+            a = agg.setdefault(kind, [0, 0.0, 0.0, 0.0])
+            a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += fl; a[3] += nb
+        rows = []
+        for kind, (n, ms, fl, nb) in agg.items():
+            roof = max(fl / (peak_tflops * 1e12), nb / (peak_gbs * 1e9)) * 1e3
+            rows.append((ms / steps, kind, n / steps, roof / steps, fl / (ms * 1e-3) / 1e12 if ms else 0.0, nb / (ms * 1e-3) / 1e9 if ms else 0.0))
+        rows.sort(reverse=True)
+        tot, troof = sum(r[0] for r in rows), sum(r[3] for r in rows)
+        out = [f"{'ms/step':>8s} {'roof ms':>8s} {'gap ms':>7s} {'n':>4s} {'TF/s':>7s} {'GB/s':>6s}  kernel (eager pass, CUDA events; roof = max(flops/{peak_tflops:.0f} TF/s, bytes/{peak_gbs:.0f} GB/s))"]
+        for ms, kind, n, roof, tf, gb in rows:
+            out.append(f"{ms:8.3f} {roof:8.3f} {ms - roof:7.3f} {n:4.0f} {tf:7.1f} {gb:6.0f}  {kind}")
+        out.append(f"{tot:8.3f} {troof:8.3f} {tot - troof:7.3f}       total of instrumented launches")
+        return "\n".join(out)
 
 
 def oracle_step_fn(batch: int):
@@ -162,6 +182,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--compute-dtype", default="bf16")
     ap.add_argument("--no-graph", action="store_true", help="eager dispatch instead of whole-step CUDA-graph replay")
+    ap.add_argument("--breakdown", default=None, help="write the per-kernel roofline table of the instrumented pass to this file")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling aid: warm up, then run exactly ONE step between cudaProfilerStart/Stop and exit "
                          "(use with ncu --profile-from-start off); prints no benchmark line")
@@ -277,11 +298,14 @@ def main():
     ops.set_kernel_timer(timer)
     timed(lambda: step(x_dev), K)
     ops.set_kernel_timer(None)
-    n_launch, gemm_ms, gemm_flops = timer.summary()
+    n_launch, gemm_ms, gemm_flops, _ = timer.summary("gemm_tc")
     clocks = sampler.stop() if rank == 0 else None
 
     peaks, peak_kind = measured_peaks()
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    if args.breakdown and rank == 0:
+        with open(args.breakdown, "w") as f:
+            f.write(timer.table(K, peak, float(peaks.get("hbm_gbs", 6650.0))) + "\n")
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all epilogues)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_kind + " (sustained: timed inside a long step)",

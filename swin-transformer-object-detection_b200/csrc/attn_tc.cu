@@ -66,14 +66,18 @@ __device__ __forceinline__ unsigned long long canon_mask_bits(int wi, int nwh, i
 // q*32..q*32+31 of the stacked tile) and column half hf = w >> 2 of the row's own 64-column window block, so two
 // threads cooperate on one row (row statistics are exchanged through smem).  This doubles the warps available to
 // hide the LDS / TMEM / MUFU latencies of the per-row softmax math.
-constexpr int kBiasLd = 52;                      // sBias row pitch (floats): 16-byte aligned rows, pre-scaled by log2(e)
+constexpr int kBiasLd = 68;                      // sBias row pitch (floats): 64 columns + 4 so that 8 consecutive rows' 16-byte
+                                                 // reads fall in distinct bank groups; pre-scaled by log2(e); columns >= 49 hold
+                                                 // kNegBig so padded keys drop out of the softmax with no per-element predicate
+constexpr float kNegBig = -1.0e30f;
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 constexpr int kAttnThreads = 256;
 
 __device__ __forceinline__ void load_bias_tile(float* sBias, const float* __restrict__ bias, int h) {
   const float kLog2e = 1.4426950408889634f;
   for (int e = threadIdx.x; e < AN * kBiasLd; e += blockDim.x) {
     const int i = e / kBiasLd, j = e - i * kBiasLd;
-    sBias[e] = j < AN ? bias[((size_t)h * AN + i) * AN + j] * kLog2e : 0.f;
+    sBias[e] = j < AN ? bias[((size_t)h * AN + i) * AN + j] * kLog2e : kNegBig;
   }
 }
 
@@ -185,53 +189,45 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __gr
     tmem_ld32(tS + lane_off + wloc * 64 + jbase, v);
     tmem_ld_wait();
     TMARK(1);
+    // Rows >= 49 of a window (and a whole missing window) run the same math on harmless finite values: their P rows only
+    // feed O rows that are never stored.  Columns >= 49 carry kNegBig from the bias tile, so they become exact zeros.
     float sv[32];
-    float mx = -INFINITY;
-    if (valid) {
-      const float4* b4 = reinterpret_cast<const float4*>(sBias + i * kBiasLd + jbase);
+    {
+      const float4* b4 = reinterpret_cast<const float4*>(sBias + (i < AN ? i : AN - 1) * kBiasLd + jbase);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        if (jbase + 4 * c < kBiasLd) {
-          const float4 bb = b4[c];
-          sv[4 * c + 0] = fmaf(__uint_as_float(v[4 * c + 0]), sc2, bb.x);
-          sv[4 * c + 1] = fmaf(__uint_as_float(v[4 * c + 1]), sc2, bb.y);
-          sv[4 * c + 2] = fmaf(__uint_as_float(v[4 * c + 2]), sc2, bb.z);
-          sv[4 * c + 3] = fmaf(__uint_as_float(v[4 * c + 3]), sc2, bb.w);
-        } else {
-          sv[4 * c + 0] = sv[4 * c + 1] = sv[4 * c + 2] = sv[4 * c + 3] = 0.f;
-        }
+        const float4 bb = b4[c];
+        sv[4 * c + 0] = fmaf(__uint_as_float(v[4 * c + 0]), sc2, bb.x);
+        sv[4 * c + 1] = fmaf(__uint_as_float(v[4 * c + 1]), sc2, bb.y);
+        sv[4 * c + 2] = fmaf(__uint_as_float(v[4 * c + 2]), sc2, bb.z);
+        sv[4 * c + 3] = fmaf(__uint_as_float(v[4 * c + 3]), sc2, bb.w);
       }
-      if (mrow != nullptr) {
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj)
-          if (jbase + jj < AN) sv[jj] = fmaf(__ldg(mrow + jbase + jj), kLog2e, sv[jj]);
-      }
-      if (mb != 0u) {
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj)
-          if ((mb >> jj) & 1u) sv[jj] -= 100.0f * kLog2e;
-      }
+    }
+    if (mrow != nullptr) {
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj)
-        if (jbase + jj < AN) mx = fmaxf(mx, sv[jj]);
+        if (jbase + jj < AN) sv[jj] = fmaf(__ldg(mrow + jbase + jj), kLog2e, sv[jj]);
     }
+    if (mb != 0u) {
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj)
+        if ((mb >> jj) & 1u) sv[jj] -= 100.0f * kLog2e;
+    }
+    float mx = sv[0];
+#pragma unroll
+    for (int jj = 1; jj < 32; ++jj) mx = fmaxf(mx, sv[jj]);
     sRed[0][hf][r] = mx;
     TMARK(2);
     if (tid == 0) tma_store_wait_read<0>();      // the previous item's O tile (staged in sP) has been drained by TMA
     __syncthreads();
     TMARK(3);
     float sum = 0.f;
-    if (valid) {
-      mx = fmaxf(sRed[0][0][r], sRed[0][1][r]);
+    mx = fmaxf(sRed[0][0][r], sRed[0][1][r]);
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        float e = 0.f;
-        if (jbase + jj < AN) { e = exp2f(sv[jj] - mx); sum += e; }
-        sv[jj] = e;
-      }
-    } else {
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj) sv[jj] = 0.f;
+    for (int jj = 0; jj < 32; ++jj) {
+      const float e = ex2_ftz(sv[jj] - mx);
+      sum += e;
+      sv[jj] = e;
     }
     sRed[1][hf][r] = sum;
     TMARK(4);
@@ -391,41 +387,36 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
     TMARK(1);
     // P for this thread's 32 columns (fp32, registers) and the partial D = sum_j P_ij dP_ij, taken from the SAME
     // P and dP that form dS so that sum_j dS_ij == 0 up to fp32 rounding
+    // (rows >= 49 / a missing window run on harmless finite values: their dO and Q rows are zero, so they add nothing to
+    //  dV / dK, their dQ rows are never stored and their bias gradients are never written; columns >= 49 carry kNegBig)
     float pr[32];
     float delta = 0.f;
-    if (valid) {
-      const float4* b4 = reinterpret_cast<const float4*>(sBias + i * kBiasLd + jbase);
+    {
+      const float4* b4 = reinterpret_cast<const float4*>(sBias + (i < AN ? i : AN - 1) * kBiasLd + jbase);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        if (jbase + 4 * c < kBiasLd) {
-          const float4 bb = b4[c];
-          pr[4 * c + 0] = fmaf(__uint_as_float(s[4 * c + 0]), sc2, bb.x);
-          pr[4 * c + 1] = fmaf(__uint_as_float(s[4 * c + 1]), sc2, bb.y);
-          pr[4 * c + 2] = fmaf(__uint_as_float(s[4 * c + 2]), sc2, bb.z);
-          pr[4 * c + 3] = fmaf(__uint_as_float(s[4 * c + 3]), sc2, bb.w);
-        } else {
-          pr[4 * c + 0] = pr[4 * c + 1] = pr[4 * c + 2] = pr[4 * c + 3] = 0.f;
-        }
+        const float4 bb = b4[c];
+        pr[4 * c + 0] = fmaf(__uint_as_float(s[4 * c + 0]), sc2, bb.x);
+        pr[4 * c + 1] = fmaf(__uint_as_float(s[4 * c + 1]), sc2, bb.y);
+        pr[4 * c + 2] = fmaf(__uint_as_float(s[4 * c + 2]), sc2, bb.z);
+        pr[4 * c + 3] = fmaf(__uint_as_float(s[4 * c + 3]), sc2, bb.w);
       }
-      if (mrow != nullptr) {
+    }
+    if (mrow != nullptr) {
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj)
-          if (jbase + jj < AN) pr[jj] = fmaf(__ldg(mrow + jbase + jj), kLog2e, pr[jj]);
-      }
-      if (mb != 0u) {
+      for (int jj = 0; jj < 32; ++jj)
+        if (jbase + jj < AN) pr[jj] = fmaf(__ldg(mrow + jbase + jj), kLog2e, pr[jj]);
+    }
+    if (mb != 0u) {
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj)
-          if ((mb >> jj) & 1u) pr[jj] -= 100.0f * kLog2e;
-      }
+      for (int jj = 0; jj < 32; ++jj)
+        if ((mb >> jj) & 1u) pr[jj] -= 100.0f * kLog2e;
+    }
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        float pv = 0.f;
-        if (jbase + jj < AN) { pv = exp2f(pr[jj] - lse2); delta = fmaf(pv, __uint_as_float(dp[jj]), delta); }
-        pr[jj] = pv;
-      }
-    } else {
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj) pr[jj] = 0.f;
+    for (int jj = 0; jj < 32; ++jj) {
+      const float pv = ex2_ftz(pr[jj] - lse2);
+      delta = fmaf(pv, __uint_as_float(dp[jj]), delta);
+      pr[jj] = pv;
     }
     sRed[hf][r] = delta;
     TMARK(2);

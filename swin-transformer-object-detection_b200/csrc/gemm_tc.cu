@@ -27,7 +27,45 @@ struct GemmTcParams {
   float* colsum_a;             // split-K dW only: bias gradient via an all-ones N=16 MMA into TMEM columns [256,272)
   int tma_epi;                 // 1: STORE/GELU with bf16 outputs go out through TMA stores (tmD / tmD2)
   uint32_t stage_bytes;        // smem stride per stage: a_bytes + b_bytes rounded up to the 1024-byte swizzle-atom alignment
+  int streamk;                 // split-K dW: every CTA owns an equal, contiguous range of the (tile, k-block) sequence
   EpiParams epi;
+};
+
+// Work decomposition shared by the three warp roles (they must walk the same sequence).
+//   static:    unit = (tile, k-split), round-robin over the CTAs (forward / dX GEMMs: splits == 1);
+//   stream-K:  the tiles' k-blocks are laid end to end (g = tile * kb_total + kb) and CTA b takes the contiguous range
+//              [b * total / G, (b+1) * total / G) — perfectly balanced whatever tiles x splits would have been; a range that
+//              crosses a tile boundary becomes two segments, each finished with the atomic-add epilogue.
+struct WorkIter {
+  int tile, kb0, kb1;
+  int unit, total_units, stride, splits, kb_per_split, kb_total;
+  long long g, g_end;
+  bool sk;
+  __device__ __forceinline__ explicit WorkIter(const GemmTcParams& p) {
+    sk = p.streamk != 0; kb_total = p.kb_total; splits = p.splits; kb_per_split = p.kb_per_split;
+    unit = blockIdx.x; stride = gridDim.x; total_units = p.m_tiles * p.n_tiles * p.splits;
+    const long long total = (long long)p.m_tiles * p.n_tiles * p.kb_total;
+    g = total * blockIdx.x / gridDim.x; g_end = total * (blockIdx.x + 1) / gridDim.x;
+    tile = kb0 = kb1 = 0;
+  }
+  __device__ __forceinline__ bool next() {
+    if (sk) {
+      if (g >= g_end) return false;
+      tile = (int)(g / kb_total);
+      kb0 = (int)(g - (long long)tile * kb_total);
+      const long long left = g_end - g;
+      const int take = (long long)(kb_total - kb0) < left ? kb_total - kb0 : (int)left;
+      kb1 = kb0 + take; g += take;
+      return true;
+    }
+    if (unit >= total_units) return false;
+    const int ks = unit % splits;
+    tile = unit / splits;
+    kb0 = ks * kb_per_split;
+    kb1 = min(kb_total, kb0 + kb_per_split);
+    unit += stride;
+    return true;
+  }
 };
 
 
@@ -147,18 +185,13 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  const int total_units = p.m_tiles * p.n_tiles * p.splits;
-
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        const int ks = unit % p.splits;
-        const int tile = unit / p.splits;
+      for (WorkIter w(p); w.next();) {
+        const int tile = w.tile, kb0 = w.kb0, kb1 = w.kb1;
         const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         const int m0 = m_blk * TBM, n0 = n_blk * p.block_n;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
@@ -186,10 +219,8 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(p.block_n, A_MN, B_MN);
       uint32_t it = 0, u = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++u) {
-        const int ks = unit % p.splits;
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      for (WorkIter w(p); w.next(); ++u) {
+        const int kb0 = w.kb0, kb1 = w.kb1;
         const uint32_t acc = u % num_acc, acc_ph = (u / num_acc) & 1;
         mbar_wait(tempty_bar(acc), acc_ph ^ 1);
         tc_fence_after();
@@ -226,8 +257,8 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
     float4* stage = reinterpret_cast<float4*>(smem_raw + (smem0 - smem_u32(smem_raw)) + (uint32_t)p.stages * stage_bytes + (uint32_t)ew * p.epi_bytes_per_warp);
     uint32_t u = 0;
     uint32_t aux_n = 0;                       // class 2: aux tiles requested so far by this warp (buffer = n & 1)
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++u) {
-      const int tile = unit / p.splits;
+    for (WorkIter w(p); w.next(); ++u) {
+      const int tile = w.tile;
       const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
       const int row_base = m_blk * TBM + q * 32;
       const int n0 = n_blk * p.block_n;
@@ -472,13 +503,7 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   p.n_tiles = a->N / p.block_n;
   p.kb_total = ceil_div(a->K, TBK);
   p.splits = 1;
-  if (a->epilogue == SWIN_EPI_ATOMIC_ADD) {
-    int tiles = p.m_tiles * p.n_tiles;
-    p.splits = ceil_div(2 * kNumSMs, tiles);
-    int maxs = ceil_div(p.kb_total, 4);
-    if (p.splits > maxs) p.splits = maxs;
-    if (p.splits < 1) p.splits = 1;
-  }
+  p.streamk = a->epilogue == SWIN_EPI_ATOMIC_ADD ? 1 : 0;
   p.colsum_a = nullptr;
   if (a->colsum_a != nullptr) {
     SWIN_REQUIRE(a->epilogue == SWIN_EPI_ATOMIC_ADD && a_mn && b_mn, "gemm: colsum_a needs ATOMIC_ADD with a_trans = b_trans = 1");
@@ -539,8 +564,8 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
     if (st2 < p.stages) p.stages = st2;
   }
   const size_t smem = (size_t)p.stages * stage_bytes + epi_bytes + 1024;
-  const int total_units = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = total_units < kNumSMs ? total_units : kNumSMs;
+  const long long total_units = p.streamk ? (long long)p.m_tiles * p.n_tiles * p.kb_total : (long long)p.m_tiles * p.n_tiles * p.splits;
+  const int grid = total_units < kNumSMs ? (int)total_units : kNumSMs;
 #define LAUNCH_TC(AM, BM, TE)                                                                                     \
   do {                                                                                                            \
     static bool attr_done = false;                                                                                \

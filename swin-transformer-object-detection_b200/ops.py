@@ -14,6 +14,8 @@ import torch
 from . import _lib as L
 
 _DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+_EPI_NAMES = {L.EPI_STORE: "store", L.EPI_GELU: "gelu", L.EPI_RESIDUAL: "residual", L.EPI_SCATTER_RESIDUAL: "scatter_residual",
+              L.EPI_DGELU: "dgelu", L.EPI_ATOMIC_ADD: "splitk_dW"}
 
 # ------------------------------------------------------------------ instrumentation (bench.py)
 LAUNCHES = 0          # kernels of libswin_b200.so enqueued by this process
@@ -29,6 +31,30 @@ def set_kernel_timer(timer) -> None:
 def _count(n: int = 1) -> None:
     global LAUNCHES
     LAUNCHES += n
+
+
+def _nb(*ts) -> float:
+    """Bytes of the given tensors (None skipped): the algorithmic HBM traffic of a kernel is the sum over the tensors
+    it must read once and write once."""
+    return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
+
+
+class _timed:
+    """``with _timed(kind, flops, bytes):`` brackets one kernel launch with the installed timer (no-op otherwise)."""
+    __slots__ = ("on",)
+
+    def __init__(self, kind: str, flops: float = 0.0, nbytes: float = 0.0):
+        self.on = _TIMER is not None
+        if self.on:
+            _TIMER.begin(kind, flops, nbytes)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            _TIMER.end()
+        return False
 
 
 def _stream() -> C.c_void_p:
@@ -157,7 +183,8 @@ def ln_fwd(mode: int, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, 
     a = L.LnArgs(mode=mode, B=B, H=H, W=W, C=Cc, ws=ws, shift=shift, eps=eps, y_dtype=y_dtype, x=_p(x), gamma=_p(gamma),
                  beta=_p(beta), y=_p(y), mean=_p(mean), rstd=_p(rstd))
     _count()
-    L.check(L.lib().swin_ln_fwd(C.byref(a), _stream()), "ln_fwd")
+    with _timed(f"ln_fwd mode{mode} C={Cc}", 0.0, _nb(x, y)):
+        L.check(L.lib().swin_ln_fwd(C.byref(a), _stream()), "ln_fwd")
     return y, mean, rstd
 
 
@@ -179,7 +206,8 @@ def ln_bwd(mode: int, dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, me
         dy2 = torch.zeros((B * (Hp // ws2) * (Wp // ws2) * ws2 * ws2, Cc), dtype=dy.dtype, device=x.device)   # pad slots stay 0
         a.dy2, a.dy2_scale, a.dy2_colsum, a.ws2, a.shift2 = _p(dy2), _p(scale2), _p(dgb[2]), ws2, shift2
     _count()
-    L.check(L.lib().swin_ln_bwd(C.byref(a), _stream()), "ln_bwd")
+    with _timed(f"ln_bwd mode{mode} C={Cc}{' +emit' if emit_windows is not None else ''}", 0.0, _nb(dy, x, dres, dx, dy2)):
+        L.check(L.lib().swin_ln_bwd(C.byref(a), _stream()), "ln_bwd")
     if emit_windows is not None:
         return dx, dgb[0], dgb[1], dy2, dgb[2]
     return dx, dgb[0], dgb[1]
@@ -193,7 +221,8 @@ def ln_nchw_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, H: int
     mean = torch.empty((B * Lx,), dtype=torch.float32, device=x.device)
     rstd = torch.empty((B * Lx,), dtype=torch.float32, device=x.device)
     _count()
-    L.check(L.lib().swin_ln_nchw_fwd(_p(x), _p(gamma), _p(beta), _p(out), _p(mean), _p(rstd), B, Lx, Cc, eps, _stream()), "ln_nchw_fwd")
+    with _timed(f"ln_nchw_fwd C={Cc}", 0.0, _nb(x, out)):
+        L.check(L.lib().swin_ln_nchw_fwd(_p(x), _p(gamma), _p(beta), _p(out), _p(mean), _p(rstd), B, Lx, Cc, eps, _stream()), "ln_nchw_fwd")
     return out, mean, rstd
 
 
@@ -203,7 +232,8 @@ def ln_nchw_bwd(dout: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: 
     dx = torch.empty_like(x)
     dgb = torch.zeros((2, Cc), dtype=torch.float32, device=x.device)
     _count()
-    L.check(L.lib().swin_ln_nchw_bwd(_p(dout), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dgb[0]), _p(dgb[1]), B, Lx, Cc,
+    with _timed(f"ln_nchw_bwd C={Cc}", 0.0, _nb(dout, x, dx)):
+        L.check(L.lib().swin_ln_nchw_bwd(_p(dout), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dgb[0]), _p(dgb[1]), B, Lx, Cc,
                                      _stream()), "ln_nchw_bwd")
     return dx, dgb[0], dgb[1]
 
@@ -215,7 +245,8 @@ def patch_gather(img: torch.Tensor, patch: int, dtype: int) -> torch.Tensor:
     Hh, Ww = -(-Hi // patch), -(-Wi // patch)
     cols = torch.empty((B * Hh * Ww, Cin * patch * patch), dtype=torch_dtype(dtype), device=img.device)
     _count()
-    L.check(L.lib().swin_patch_gather(_p(img), _p(cols), B, Cin, Hi, Wi, patch, dtype, _stream()), "patch_gather")
+    with _timed("patch_gather", 0.0, _nb(img, cols)):
+        L.check(L.lib().swin_patch_gather(_p(img), _p(cols), B, Cin, Hi, Wi, patch, dtype, _stream()), "patch_gather")
     return cols
 
 
@@ -223,7 +254,8 @@ def patch_scatter(dcols: torch.Tensor, B: int, Cin: int, Hi: int, Wi: int, patch
     _chk(dcols)
     dimg = torch.empty((B, Cin, Hi, Wi), dtype=torch.float32, device=dcols.device)
     _count()
-    L.check(L.lib().swin_patch_scatter(_p(dcols), _p(dimg), B, Cin, Hi, Wi, patch, _DT[dcols.dtype], _stream()), "patch_scatter")
+    with _timed("patch_scatter", 0.0, _nb(dcols, dimg)):
+        L.check(L.lib().swin_patch_scatter(_p(dcols), _p(dimg), B, Cin, Hi, Wi, patch, _DT[dcols.dtype], _stream()), "patch_scatter")
     return dimg
 
 
@@ -246,9 +278,12 @@ def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_trans: 
                    rows_per_image=rows_per_image, H=geom[0], W=geom[1], ws=geom[2], shift=geom[3], colsum_a=_p(colsum_a))
     _count()
     if _TIMER is not None and dt == L.BF16:
-        _TIMER.begin("gemm_tc", 2.0 * M * N * K)
-        L.check(L.lib().swin_gemm(C.byref(a), _stream()), "gemm")
-        _TIMER.end()
+        # algorithmic bytes: both operands once, the output once (+ a second output / the aux tile where the epilogue has one);
+        # the split-K weight gradient writes N x M fp32 once
+        nbytes = _nb(A, Bm, out2, aux) + (_nb(out) if out_rows is None else float(M) * N * out.element_size())
+        kind = f"gemm_tc {_EPI_NAMES.get(epilogue, epilogue)}{'/At' if a_trans else ''}{'/Bt' if b_trans else ''} M={M} N={N} K={K}"
+        with _timed(kind, 2.0 * M * N * K, nbytes):
+            L.check(L.lib().swin_gemm(C.byref(a), _stream()), "gemm")
     else:
         L.check(L.lib().swin_gemm(C.byref(a), _stream()), "gemm")
     return out
@@ -259,7 +294,8 @@ def colsum(X: torch.Tensor) -> torch.Tensor:
     X2 = X.reshape(-1, X.shape[-1])
     out = torch.zeros((X2.shape[1],), dtype=torch.float32, device=X.device)
     _count()
-    L.check(L.lib().swin_colsum(_p(X2), X2.shape[0], X2.shape[1], X2.shape[1], _DT[X.dtype], _p(out), _stream()), "colsum")
+    with _timed("colsum", 0.0, _nb(X2)):
+        L.check(L.lib().swin_colsum(_p(X2), X2.shape[0], X2.shape[1], X2.shape[1], _DT[X.dtype], _p(out), _stream()), "colsum")
     return out
 
 
@@ -277,7 +313,8 @@ def scale_cast(x: torch.Tensor, row_scale: Optional[torch.Tensor], mode: int, B:
     y = torch.empty((rows, Cc), dtype=torch_dtype(y_dtype), device=x.device)
     cs = torch.zeros((Cc,), dtype=torch.float32, device=x.device) if want_colsum else None
     _count()
-    L.check(L.lib().swin_scale_cast(_p(x), _p(y), _p(row_scale), mode, B, H, W, Cc, ws, shift, y_dtype, _p(cs), _stream()), "scale_cast")
+    with _timed(f"scale_cast mode{mode} C={Cc}", 0.0, _nb(x, y)):
+        L.check(L.lib().swin_scale_cast(_p(x), _p(y), _p(row_scale), mode, B, H, W, Cc, ws, shift, y_dtype, _p(cs), _stream()), "scale_cast")
     return (y, cs) if want_colsum else y
 
 
@@ -300,7 +337,8 @@ def window_attn_fwd(qkv: torch.Tensor, bias: torch.Tensor, mask: Optional[torch.
     a = L.AttnArgs(dtype=_DT[qkv.dtype], B_=B_, nH=nH, ws=ws, nW=0 if mask is None else mask.shape[0], scale=scale,
                    qkv=_p(qkv), bias=_p(bias), mask=_p(mask), mask_nz=_p(mask_nz), canon_nwh=canon[0], canon_nww=canon[1], out=_p(out), lse=_p(lse))
     _count()
-    L.check(L.lib().swin_window_attn_fwd(C.byref(a), _stream()), "window_attn_fwd")
+    with _timed(f"attn_fwd nH={nH}", 307328.0 * B_ * nH if ws == 7 else 0.0, _nb(qkv, out)):
+        L.check(L.lib().swin_window_attn_fwd(C.byref(a), _stream()), "window_attn_fwd")
     return out, lse
 
 
@@ -315,5 +353,6 @@ def window_attn_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, ls
                    qkv=_p(qkv), bias=_p(bias), mask=_p(mask), mask_nz=_p(mask_nz), canon_nwh=canon[0], canon_nww=canon[1], out=_p(out), lse=_p(lse), dout=_p(dout), dqkv=_p(dqkv),
                    dbias=_p(dbias))
     _count()
-    L.check(L.lib().swin_window_attn_bwd(C.byref(a), _stream()), "window_attn_bwd")
+    with _timed(f"attn_bwd nH={nH}", 768320.0 * B_ * nH if ws == 7 else 0.0, _nb(qkv, dout, dqkv)):
+        L.check(L.lib().swin_window_attn_bwd(C.byref(a), _stream()), "window_attn_bwd")
     return dqkv, dbias

@@ -10,7 +10,7 @@ only = sys.argv[1] if len(sys.argv) > 1 else None
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 
 
-def run(name, M, N, K, epi=L.EPI_STORE, a_trans=False, b_trans=False, out_f32=False):
+def run(name, M, N, K, epi=L.EPI_STORE, a_trans=False, b_trans=False, out_f32=False, do_flush=True):
     if only and only != name:
         return
     A = torch.randn((K, M) if a_trans else (M, K), device=dev).bfloat16()
@@ -29,7 +29,8 @@ def run(name, M, N, K, epi=L.EPI_STORE, a_trans=False, b_trans=False, out_f32=Fa
         bias = None
     ts = []
     for _ in range(reps):
-        flush.zero_()
+        if do_flush:
+            flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         ops.gemm(A, B, M, N, K, a_trans=a_trans, b_trans=b_trans, epilogue=epi, bias=bias, out=out, **kw)
@@ -59,3 +60,7 @@ run("dgelu_s2", T2, 1536, 384, L.EPI_DGELU, b_trans=True)
 run("dW_fc2_s2", 384, 1536, T2, L.EPI_ATOMIC_ADD, a_trans=True, b_trans=True)
 run("square_8k", 8192, 8192, 8192)
 run("square_4k_f32out", 4096, 4096, 4096, out_f32=True)
+run("sq4k_tt", 4096, 4096, 4096, a_trans=True, b_trans=True)
+run("dW_s2_small_flush", 384, 1536, 16800, L.EPI_ATOMIC_ADD, a_trans=True, b_trans=True)
+run("dW_s2_small_L2hot", 384, 1536, 16800, L.EPI_ATOMIC_ADD, a_trans=True, b_trans=True, do_flush=False)
+run("dW_fc1_s2", 1536, 384, T2, L.EPI_ATOMIC_ADD, a_trans=True, b_trans=True)
