@@ -152,6 +152,11 @@ int swin_scale_cast(const float* x, void* y, const float* row_scale, int mode, i
                     int shift, int y_dtype, float* colsum, void* stream);
 /* fp32 -> bf16 copy (weights shadow copies), n elements */
 int swin_cast_bf16(const float* x, void* y, int64_t n, void* stream);
+/* Data-parallel gradient bucket fill (replaces torch DDP's per-parameter bucket copies, mmdet/apis/train.py:91-99):
+ * copies n <= SWIN_GATHER_MAX fp32 tensors src[e] (numel[e] elements) to bucket + dst_off[e] (dst_off multiples of 4
+ * floats) in ONE launch.  src/dst_off/numel are HOST arrays, consumed before the call returns. */
+#define SWIN_GATHER_MAX 64
+int swin_grad_gather(const void* const* src, const int64_t* dst_off, const int64_t* numel, int n, float* bucket, void* stream);
 
 /* ---------------------------------------------------------------- window attention core, REF:129-150
  * qkv (B_, N, 3C): columns [q|k|v] x [head] x [32].  bias (nH,N,N) fp32 (swin_rel_bias_expand).

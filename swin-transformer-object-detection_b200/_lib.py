@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("SWIN_B200_LIB") or os.path.join(_HERE, "libswin_b200.
 CSRC = os.path.join(_HERE, "csrc")
 
 F32, BF16 = 0, 1
+GATHER_MAX = 64
 EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_SCATTER_RESIDUAL, EPI_DGELU, EPI_ATOMIC_ADD = range(6)
 
 c_int, c_i64, c_f32, vp = C.c_int, C.c_int64, C.c_float, C.c_void_p
@@ -66,6 +67,7 @@ SYMBOLS = {
     "swin_colsum": (c_int, [vp, c_int, c_int, c_i64, c_int, vp, vp]),
     "swin_scale_cast": (c_int, [vp, vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp]),
     "swin_cast_bf16": (c_int, [vp, vp, c_i64, vp]),
+    "swin_grad_gather": (c_int, [vp, vp, vp, c_int, vp, vp]),
     "swin_window_attn_fwd": (c_int, [C.POINTER(AttnArgs), vp]),
     "swin_window_attn_bwd": (c_int, [C.POINTER(AttnArgs), vp]),
 }

@@ -561,6 +561,40 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
+// gradient gather: up to SWIN_GATHER_MAX fp32 tensors copied into their slots of one flat bucket by ONE launch
+// (the data-parallel all-reduce bucket, ddp.py).  Block b serves the chunk (entry, 4096-float piece) found by scanning
+// the per-entry cumulative chunk counts passed by value.
+// ------------------------------------------------------------------------------------------
+struct GatherTable {
+  const float* src[SWIN_GATHER_MAX];
+  long long dst_off[SWIN_GATHER_MAX];     // float offset inside the bucket (multiple of 4)
+  int chunk_end[SWIN_GATHER_MAX];         // cumulative number of 4096-float chunks up to and including entry e
+  int numel[SWIN_GATHER_MAX];
+  int n;
+};
+constexpr int kGatherChunk = 4096;
+
+__global__ void __launch_bounds__(256) grad_gather_kernel(const __grid_constant__ GatherTable t, float* __restrict__ bucket) {
+  const int total = t.chunk_end[t.n - 1];
+  for (int c = blockIdx.x; c < total; c += gridDim.x) {
+    int e = 0;
+    while (c >= t.chunk_end[e]) ++e;
+    const int first = e == 0 ? 0 : t.chunk_end[e - 1];
+    const long long base = (long long)(c - first) * kGatherChunk;
+    const int n = min(kGatherChunk, (int)(t.numel[e] - base));
+    const float* __restrict__ src = t.src[e] + base;
+    float* __restrict__ dst = bucket + t.dst_off[e] + base;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      const int n4 = n >> 2;
+      for (int v = threadIdx.x; v < n4; v += blockDim.x) reinterpret_cast<float4*>(dst)[v] = __ldg(reinterpret_cast<const float4*>(src) + v);
+      for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    } else {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // column sums (bias gradients): block = 256 threads = 8 row-lanes x 32 column-vectors(4 wide)
 // ------------------------------------------------------------------------------------------
 template <typename T>
@@ -702,6 +736,27 @@ extern "C" int swin_cast_bf16(const float* x, void* y, int64_t n, void* stream) 
   long long blocks = ceil_div64(n4 > 0 ? n4 : 1, 256);
   int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
   cast_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n4, n);
+  SWIN_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int swin_grad_gather(const void* const* src, const int64_t* dst_off, const int64_t* numel, int n, float* bucket, void* stream) {
+  SWIN_REQUIRE(n >= 0 && n <= SWIN_GATHER_MAX, "grad_gather: at most %d tensors per call (got %d)", SWIN_GATHER_MAX, n);
+  if (n == 0) return 0;
+  SWIN_REQUIRE(src && dst_off && numel && bucket && aligned16(bucket), "grad_gather: null / misaligned pointer");
+  GatherTable t;
+  int chunks = 0, live = 0;
+  for (int e = 0; e < n; ++e) {
+    SWIN_REQUIRE(numel[e] >= 0 && numel[e] < (1ll << 31) && dst_off[e] >= 0 && dst_off[e] % 4 == 0, "grad_gather: bad entry %d", e);
+    if (numel[e] == 0) continue;
+    SWIN_REQUIRE(src[e] != nullptr && (reinterpret_cast<uintptr_t>(src[e]) & 3) == 0, "grad_gather: entry %d null / misaligned", e);
+    chunks += (int)ceil_div64(numel[e], kGatherChunk);
+    t.src[live] = (const float*)src[e]; t.dst_off[live] = dst_off[e]; t.numel[live] = (int)numel[e]; t.chunk_end[live] = chunks;
+    ++live;
+  }
+  if (live == 0) return 0;
+  t.n = live;
+  const int grid = chunks < kNumSMs * 8 ? chunks : kNumSMs * 8;
+  grad_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, bucket);
   SWIN_LAUNCH_CHECK();
   return 0;
 }

@@ -3,13 +3,16 @@ overlapped with backward.
 
 Replaces what the reference gets from ``MMDistributedDataParallel`` (torch DDP) at
 ``mmdet/apis/train.py:91-99``: one process per GPU, gradients averaged across ranks every step,
-``broadcast_buffers=False``.  Design (B200 / NVSwitch): gradients live as views into a few flat
-fp32 buckets (~32 MB, sized for launch latency, not link count); parameters are assigned to buckets
-in reverse execution order (stage 3 first) so a bucket completes early in backward; when the last
-gradient of a bucket has been accumulated (``register_post_accumulate_grad_hook``) the bucket is
-all-reduced (AVG) on a dedicated communication stream while backward keeps running on the compute
-stream.  ``finish()`` makes the compute stream wait for the communication stream.
-Works with backend "gloo" on CPU tensors for tests (synchronous there).
+``broadcast_buffers=False``.  Design (B200 / NVSwitch): a few flat fp32 buckets (~32 MB, sized for launch
+latency, not link count); parameters are assigned to buckets in reverse execution order (stage 3 first) so a
+bucket completes early in backward.  ``zero_grad()`` drops the gradients (``p.grad = None``) so autograd keeps the
+tensor each backward kernel produced without a copy; when the last gradient of a bucket has arrived
+(``register_post_accumulate_grad_hook``) ONE ``swin_grad_gather`` launch packs the bucket (torch DDP issues one copy
+or add per parameter: 189 launches per step here), the parameters' ``.grad`` are re-pointed at their bucket views,
+and the bucket is all-reduced (AVG) on a dedicated communication stream while backward keeps running on the compute
+stream.  ``finish()`` makes the compute stream wait for the communication stream.  With a single process there is
+nothing to exchange: gradients stay where the kernels wrote them (no bucket traffic at all).
+Works with backend "gloo" on CPU tensors for tests (synchronous there, plain torch copies).
 """
 from __future__ import annotations
 
@@ -44,20 +47,25 @@ class BucketedGradAllReduce:
             cur_n += p.numel()
         if cur:
             groups.append(cur)
+        self.groups = groups
+        self._offsets: List[List[int]] = []
+        self._views = {}
         for bi, grp in enumerate(groups):
-            n = sum(p.numel() for p in grp)
-            flat = torch.zeros(n, dtype=torch.float32, device=grp[0].device)
-            off = 0
+            offs, off = [], 0
             for p in grp:
-                p.grad = flat[off:off + p.numel()].view_as(p)     # gradient-as-bucket-view
-                off += p.numel()
+                offs.append(off)
+                off += (p.numel() + 3) // 4 * 4               # 16-byte aligned slots (vectorised gather)
+            flat = torch.zeros(off, dtype=torch.float32, device=grp[0].device)
+            for p, o in zip(grp, offs):
+                self._views[p] = flat[o:o + p.numel()].view_as(p)
                 self._bucket_of[p] = bi
+                p.grad = None
             self.buckets.append(flat)
+            self._offsets.append(offs)
         self._sizes = [len(gp) for gp in groups]
         self._pending = list(self._sizes)
         self._cuda = params[0].is_cuda if params else False
         self.comm_stream = torch.cuda.Stream() if self._cuda else None
-        self._handles = []
         self._launched = 0
         for p in params:
             p.register_post_accumulate_grad_hook(self._on_grad)
@@ -69,10 +77,40 @@ class BucketedGradAllReduce:
         if self._pending[bi] == 0:
             self._launch(bi)
 
+    def _pack(self, bi: int) -> None:
+        """Gradients of bucket ``bi`` -> the flat bucket (one kernel launch on CUDA); ``.grad`` becomes the bucket view."""
+        flat, grp, offs = self.buckets[bi], self.groups[bi], self._offsets[bi]
+        src, dst = [], []
+        missing = False
+        for p, o in zip(grp, offs):
+            g = p.grad
+            if g is None:
+                missing = True
+                continue
+            view = self._views[p]
+            if g.data_ptr() == view.data_ptr():
+                continue                                   # accumulated in place into the bucket already
+            if g.dtype != torch.float32 or not g.is_contiguous():
+                g = g.float().contiguous()
+            src.append(g.detach())
+            dst.append(o)
+        if missing:
+            flat.zero_()                                   # parameters unused this step contribute zeros
+        if src:
+            if self._cuda:
+                from . import ops
+                ops.grad_gather(src, dst, flat)
+            else:
+                for g, o in zip(src, dst):
+                    flat[o:o + g.numel()].copy_(g.reshape(-1))
+        for p in grp:
+            p.grad = self._views[p]
+
     def _launch(self, bi: int) -> None:
         self._launched += 1
         if self.world == 1:
             return
+        self._pack(bi)
         flat = self.buckets[bi]
         if self._cuda:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
@@ -94,6 +132,6 @@ class BucketedGradAllReduce:
         self._pending = list(self._sizes)
 
     def zero_grad(self) -> None:
-        """Zero the flat buckets (keeps the grad views attached)."""
-        for flat in self.buckets:
-            flat.zero_()
+        """Drop the gradients (``set_to_none``): the next backward stores each kernel's output tensor as ``.grad`` directly."""
+        for p in self.params:
+            p.grad = None

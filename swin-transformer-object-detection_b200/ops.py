@@ -327,6 +327,21 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def grad_gather(tensors, offsets, bucket: torch.Tensor) -> None:
+    """Copies fp32 ``tensors[i]`` (contiguous) to ``bucket[offsets[i] : offsets[i] + numel]``, GATHER_MAX tensors per launch."""
+    _chk(bucket, *tensors)
+    assert bucket.dtype == torch.float32
+    for i0 in range(0, len(tensors), L.GATHER_MAX):
+        ts, offs = tensors[i0:i0 + L.GATHER_MAX], offsets[i0:i0 + L.GATHER_MAX]
+        n = len(ts)
+        src = (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+        off = (C.c_int64 * n)(*offs)
+        num = (C.c_int64 * n)(*[t.numel() for t in ts])
+        _count()
+        with _timed("grad_gather", 0.0, 2.0 * _nb(*ts)):
+            L.check(L.lib().swin_grad_gather(src, off, num, n, _p(bucket), _stream()), "grad_gather")
+
+
 # ------------------------------------------------------------------ window attention core
 def window_attn_fwd(qkv: torch.Tensor, bias: torch.Tensor, mask: Optional[torch.Tensor], B_: int, nH: int, ws: int,
                     scale: float, mask_nz: Optional[torch.Tensor] = None, canon=(0, 0)):

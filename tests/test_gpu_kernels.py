@@ -157,6 +157,27 @@ def test_scale_cast_and_colsum():
     assert torch.equal(ops.cast_bf16(w), w.bfloat16())
 
 
+def test_scale_cast_grad_gather():
+    """Bucket packing of the data-parallel all-reduce: many ragged fp32 tensors -> one flat bucket, bit-exact; more tensors
+    than one launch takes (GATHER_MAX), sizes that are not multiples of 4, a source that is only 4-byte aligned."""
+    ops, L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    sizes = [1, 3, 4, 169 * 3, 96, 4097, 8192 + 5, 288 * 96, 7] + [int(x) for x in torch.randint(1, 5000, (L.GATHER_MAX + 9,), generator=g)]
+    base = torch.randn(sum(sizes) + 8, generator=g).to(DEV)
+    srcs, offs, off, pos = [], [], 0, 1            # pos starts at 1: the first source is not 16-byte aligned
+    for n in sizes:
+        srcs.append(base[pos:pos + n])
+        pos += n
+        offs.append(off)
+        off += (n + 3) // 4 * 4
+    bucket = torch.full((off,), -7.0, device=DEV)
+    ops.grad_gather(srcs, offs, bucket)
+    want = torch.full((off,), -7.0, device=DEV)
+    for t, o in zip(srcs, offs):
+        want[o:o + t.numel()] = t
+    assert torch.equal(bucket, want)
+
+
 @pytest.mark.parametrize("C,H,W", [(96, 9, 13), (768, 5, 7), (32, 40, 33)])
 def test_ln_nchw_fwd_bwd(C, H, W):
     ops, _ = _ops()
