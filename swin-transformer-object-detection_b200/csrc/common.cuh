@@ -35,10 +35,37 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Division by a launch-time constant as multiply-high + shift (valid for 0 <= n < 2^31): the gather / scatter index
+// math runs once per row in HBM-bound kernels whose issue slots, not their bytes, were the limit (ncu: 75 % issue-slot
+// utilisation at 64 % of HBM peak with hardware-emulated integer division).
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (uint32_t)(d < 1 ? 1 : d); f.mul = 0; f.shr = 0;
+  if (f.d > 1) {
+    int l = 0;
+    while ((1u << l) < f.d) ++l;                       // ceil(log2 d)
+    const int p = 31 + l;
+    f.mul = (uint32_t)((((uint64_t)1 << p) + f.d - 1) / f.d);
+    f.shr = (uint32_t)(p - 32);
+  }
+  return f;
+}
+__host__ __device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+#ifdef __CUDA_ARCH__
+  return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
+#else
+  return n / (int)f.d;
+#endif
+}
+
 // Geometry of one stage's window grid (REF:214-231 / :371-372).
 struct WinGeom {
   int B, H, W, C, ws, shift;
   int Hp, Wp, nwh, nww, nW, N;
+  FastDiv dN, dnww, dws, dW, dslots, dtok;     // dividers: N, nww, ws, W, nW*N (slots per image), H*W (tokens per image)
 };
 inline WinGeom make_geom(int B, int H, int W, int C, int ws, int shift) {
   WinGeom g;
@@ -46,26 +73,35 @@ inline WinGeom make_geom(int B, int H, int W, int C, int ws, int shift) {
   g.nwh = (H + ws - 1) / ws; g.nww = (W + ws - 1) / ws;
   g.Hp = g.nwh * ws; g.Wp = g.nww * ws;
   g.nW = g.nwh * g.nww; g.N = ws * ws;
+  g.dN = make_fastdiv(g.N); g.dnww = make_fastdiv(g.nww); g.dws = make_fastdiv(ws); g.dW = make_fastdiv(W);
+  g.dslots = make_fastdiv(g.nW * g.N); g.dtok = make_fastdiv(H * W);
   return g;
 }
 
 // slot (window-token index inside ONE image, [0, nW*N)) -> source token h*W+w, or -1 for zero padding.
 __host__ __device__ __forceinline__ int slot_to_token(const WinGeom& g, int slot) {
-  int w = slot / g.N, t = slot - w * g.N;
-  int wh = w / g.nww, ww = w - wh * g.nww;
-  int i = t / g.ws, j = t - i * g.ws;
+  int w = fdiv(slot, g.dN), t = slot - w * g.N;
+  int wh = fdiv(w, g.dnww), ww = w - wh * g.nww;
+  int i = fdiv(t, g.dws), j = t - i * g.ws;
   int hs = wh * g.ws + i + g.shift; if (hs >= g.Hp) hs -= g.Hp;
   int wsrc = ww * g.ws + j + g.shift; if (wsrc >= g.Wp) wsrc -= g.Wp;
   return (hs < g.H && wsrc < g.W) ? hs * g.W + wsrc : -1;
 }
 // token (h*W+w) -> slot inside the image (inverse of the above on valid tokens).
 __host__ __device__ __forceinline__ int token_to_slot(const WinGeom& g, int tok) {
-  int h = tok / g.W, w = tok - h * g.W;
+  int h = fdiv(tok, g.dW), w = tok - h * g.W;
   int hh = h - g.shift; if (hh < 0) hh += g.Hp;
   int wq = w - g.shift; if (wq < 0) wq += g.Wp;
-  int wh = hh / g.ws, i = hh - wh * g.ws;
-  int ww = wq / g.ws, j = wq - ww * g.ws;
+  int wh = fdiv(hh, g.dws), i = hh - wh * g.ws;
+  int ww = fdiv(wq, g.dws), j = wq - ww * g.ws;
   return (wh * g.nww + ww) * g.N + i * g.ws + j;
+}
+// global row (image-major) -> (image, row inside the image) for window-slot rows / token rows
+__device__ __forceinline__ int split_slot_row(const WinGeom& g, int row, int* inner) {
+  const int b = fdiv(row, g.dslots); *inner = row - b * (g.nW * g.N); return b;
+}
+__device__ __forceinline__ int split_tok_row(const WinGeom& g, int row, int* inner) {
+  const int b = fdiv(row, g.dtok); *inner = row - b * (g.H * g.W); return b;
 }
 
 __device__ __forceinline__ float gelu_erf(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f)); }

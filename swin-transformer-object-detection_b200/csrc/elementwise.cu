@@ -21,34 +21,35 @@ enum { MAP_PARTITION = 0, MAP_REVERSE = 1, MAP_GATHER = 2, MAP_SCATTER = 3 };
 // One launch covers `rows` destination rows; src row index (or -1 => zeros) comes from the map.
 template <int MAP>
 __global__ void __launch_bounds__(256) row_map_copy_kernel(const int4* __restrict__ src, int4* __restrict__ dst,
-                                                           WinGeom g, int vpr, int L, long long rows) {
+                                                           WinGeom g, int vpr, int L, int rows) {
+  // rows < 2^30 and rows * vpr < 2^31 (checked by the launcher): all index math is 32-bit with multiply-high divisions
   const int groups_per_block = blockDim.x / L;
   const int gl = threadIdx.x % L;
-  long long row = (long long)blockIdx.x * groups_per_block + threadIdx.x / L;
-  const long long stride = (long long)gridDim.x * groups_per_block;
+  int row = blockIdx.x * groups_per_block + threadIdx.x / L;
+  const int stride = gridDim.x * groups_per_block;
   const int per_img_slots = g.nW * g.N;
   const int per_img_tok = g.H * g.W;
   for (; row < rows; row += stride) {
-    long long srow;
+    int srow, in;
     if (MAP == MAP_GATHER) {            // dst = window slots, src = tokens
-      int b = (int)(row / per_img_slots);
-      int t = slot_to_token(g, (int)(row - (long long)b * per_img_slots));
-      srow = t < 0 ? -1 : (long long)b * per_img_tok + t;
+      int b = split_slot_row(g, row, &in);
+      int t = slot_to_token(g, in);
+      srow = t < 0 ? -1 : b * per_img_tok + t;
     } else if (MAP == MAP_SCATTER) {    // dst = tokens, src = window slots (always valid)
-      int b = (int)(row / per_img_tok);
-      srow = (long long)b * per_img_slots + token_to_slot(g, (int)(row - (long long)b * per_img_tok));
+      int b = split_tok_row(g, row, &in);
+      srow = b * per_img_slots + token_to_slot(g, in);
     } else if (MAP == MAP_PARTITION) {  // H,W already padded (H==Hp), shift 0
-      int b = (int)(row / per_img_slots);
-      srow = (long long)b * per_img_tok + slot_to_token(g, (int)(row - (long long)b * per_img_slots));
+      int b = split_slot_row(g, row, &in);
+      srow = b * per_img_tok + slot_to_token(g, in);
     } else {                            // MAP_REVERSE
-      int b = (int)(row / per_img_tok);
-      srow = (long long)b * per_img_slots + token_to_slot(g, (int)(row - (long long)b * per_img_tok));
+      int b = split_tok_row(g, row, &in);
+      srow = b * per_img_slots + token_to_slot(g, in);
     }
-    int4* d = dst + row * vpr;
+    int4* d = dst + (long long)row * vpr;
     if (srow < 0) {
       for (int v = gl; v < vpr; v += L) d[v] = make_int4(0, 0, 0, 0);
     } else {
-      const int4* s = src + srow * vpr;
+      const int4* s = src + (long long)srow * vpr;
       for (int v = gl; v < vpr; v += L) d[v] = __ldg(s + v);
     }
   }
@@ -61,12 +62,13 @@ static int launch_row_map(const void* src, void* dst, const WinGeom& g, int elem
   SWIN_REQUIRE(aligned16(src) && aligned16(dst), "pointers must be 16-byte aligned");
   SWIN_REQUIRE(g.B > 0 && g.H > 0 && g.W > 0 && g.ws > 0 && g.shift >= 0 && g.shift < g.ws, "bad geometry");
   if (rows == 0) return 0;
+  SWIN_REQUIRE(rows < (1ll << 30) && rows * (g.C * elem_bytes / 16) < (1ll << 31), "tensor too large for the gather kernels' 32-bit indices");
   int vpr = g.C * elem_bytes / 16;
   int L = lanes_per_row(vpr);
   int gpb = 256 / L;
   long long blocks = (rows + gpb - 1) / gpb;
   int grid = (int)(blocks < (long long)kNumSMs * 16 ? blocks : (long long)kNumSMs * 16);
-  row_map_copy_kernel<MAP><<<grid, 256, 0, st>>>((const int4*)src, (int4*)dst, g, vpr, L, rows);
+  row_map_copy_kernel<MAP><<<grid, 256, 0, st>>>((const int4*)src, (int4*)dst, g, vpr, L, (int)rows);
   SWIN_LAUNCH_CHECK();
   return 0;
 }
@@ -143,7 +145,8 @@ struct LnGeom {
   int C;           // segment width
   int nseg;        // 1 or 4
   int H2, W2;      // merge
-  long long rows;  // iteration rows (see kernels)
+  FastDiv dper2, dW2, dvps;   // dividers: H2*W2, W2, C/4
+  int rows;        // iteration rows (see kernels); < 2^30, and rows * row width < 2^31 float4 (checked in ln_geom)
   float eps;
   // backward, mode 0 only: optional second output  y2[slot(token)] = y2_scale[b] * dx[token]  (window-slot layout,
   // dtype of dy) + its column sums: the dY of the proj Linear, produced while dx is still in registers
@@ -154,12 +157,12 @@ struct LnGeom {
 };
 
 // merged row (b, oh, ow) segment q -> source token row or -1   (REF:288-292 order (0,0),(1,0),(0,1),(1,1))
-__device__ __forceinline__ long long merge_src(const LnGeom& lg, long long row, int q) {
+__device__ __forceinline__ int merge_src(const LnGeom& lg, int row, int q) {
   int per = lg.H2 * lg.W2;
-  int b = (int)(row / per), r = (int)(row - (long long)b * per);
-  int oh = r / lg.W2, ow = r - oh * lg.W2;
+  int b = fdiv(row, lg.dper2), r = row - b * per;
+  int oh = fdiv(r, lg.dW2), ow = r - oh * lg.W2;
   int h = 2 * oh + (q & 1), w = 2 * ow + (q >> 1);
-  return (h < lg.g.H && w < lg.g.W) ? ((long long)b * lg.g.H + h) * lg.g.W + w : -1;
+  return (h < lg.g.H && w < lg.g.W) ? (b * lg.g.H + h) * lg.g.W + w : -1;
 }
 
 template <typename T> struct Vec4IO;
@@ -205,17 +208,18 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
   const int vps = lg.C >> 2;                 // float4 per segment
   const int vrow = vps * lg.nseg;            // float4 per LN row
   const float inv_n = 1.0f / (float)(lg.C * lg.nseg);
-  const int per_img_slots = lg.g.nW * lg.g.N, per_img_tok = lg.g.H * lg.g.W;
-  for (long long base = ((long long)blockIdx.x * wpb + (threadIdx.x >> 5)) * R; base < lg.rows; base += (long long)gridDim.x * wpb * R) {
-    const long long row = base + gi;
+  const int per_img_tok = lg.g.H * lg.g.W;
+  for (int base = (blockIdx.x * wpb + (threadIdx.x >> 5)) * R; base < lg.rows; base += gridDim.x * wpb * R) {
+    const int row = base + gi;
     const bool inr = row < lg.rows;
-    long long stat_row = row, src0 = row;
+    int stat_row = row, src0 = row;
     bool pad = false;
     if (lg.mode == 1 && inr) {
-      int b = (int)(row / per_img_slots);
-      int t = slot_to_token(lg.g, (int)(row - (long long)b * per_img_slots));
+      int in;
+      int b = split_slot_row(lg.g, row, &in);
+      int t = slot_to_token(lg.g, in);
       pad = t < 0;                           // zero padding AFTER the norm (REF:211 then :218)
-      src0 = (long long)b * per_img_tok + (pad ? 0 : t);
+      src0 = b * per_img_tok + (pad ? 0 : t);
       stat_row = src0;
     }
     const bool act = inr && !pad;
@@ -224,12 +228,12 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {            // all loads first (clamped index), then the sums
       const int v = gl + G * k;
-      long long srow = src0;
+      int srow = src0;
       int off = v;
       have[k] = act && v < vrow;
-      if (lg.mode == 2 && have[k]) { int q = v / vps; off = v - q * vps; srow = merge_src(lg, row, q); }
+      if (lg.mode == 2 && have[k]) { int q = fdiv(v, lg.dvps); off = v - q * vps; srow = merge_src(lg, row, q); }
       have[k] = have[k] && srow >= 0;
-      r[k] = Vec4IO<float>::ld(x, have[k] ? srow * vps + off : 0);
+      r[k] = Vec4IO<float>::ld(x, have[k] ? (long long)(srow * vps + off) : 0);
     }
     float s = 0.f;
 #pragma unroll
@@ -262,7 +266,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
           o.z = (r[k].z - mu) * rs * gm.z + bt.z;
           o.w = (r[k].w - mu) * rs * gm.w + bt.w;
         }
-        Vec4IO<YT>::st(y, row * vrow + v, o);
+        Vec4IO<YT>::st(y, (long long)(row * vrow + v), o);
       }
     }
   }
@@ -285,39 +289,40 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const YT* __restrict__ dy, 
   const int vrow = vps * lg.nseg;
   const int width = vrow * 4;
   const float inv_n = 1.0f / (float)width;
-  const int per_img_slots = lg.g.nW * lg.g.N, per_img_tok = lg.g.H * lg.g.W;
+  const int per_img_slots = lg.g.nW * lg.g.N;
   for (int i = threadIdx.x; i < 2 * width; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
   float4 ag[VPL], ab[VPL], a2[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) { ag[k] = make_float4(0.f, 0.f, 0.f, 0.f); ab[k] = ag[k]; a2[k] = ag[k]; }
-  for (long long base = ((long long)blockIdx.x * wpb + (threadIdx.x >> 5)) * R; base < lg.rows; base += (long long)gridDim.x * wpb * R) {
-    const long long row = base + gi;
+  for (int base = (blockIdx.x * wpb + (threadIdx.x >> 5)) * R; base < lg.rows; base += gridDim.x * wpb * R) {
+    const int row = base + gi;
     const bool inr = row < lg.rows;
-    long long dyrow = row;
+    int dyrow = row;
     if (lg.mode == 1 && inr) {
-      int b = (int)(row / per_img_tok);
-      dyrow = (long long)b * per_img_slots + token_to_slot(lg.g, (int)(row - (long long)b * per_img_tok));
+      int in;
+      int b = split_tok_row(lg.g, row, &in);
+      dyrow = b * per_img_slots + token_to_slot(lg.g, in);
     }
     const float mu = inr ? mean[row] : 0.f, rs = inr ? rstd[row] : 0.f;
     // Phase A: every load of the row is issued unconditionally (clamped index, read-only path) before any use, so
     // they overlap; a load-then-use sequence per vector gets serialised by in-order issue.
     float4 xh[VPL], gd[VPL], rr[VPL];
     typename Vec4IO<YT>::raw_t draw[VPL];
-    long long srow_k[VPL];
+    int srow_k[VPL];
     const float* rsrc = dres != nullptr ? dres : x;
     const float rflag = dres != nullptr ? 1.0f : 0.0f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int v = gl + G * k;
       const bool on = inr && v < vrow;
-      long long srow = row; int off = v;
-      if (lg.mode == 2 && on) { int q = v / vps; off = v - q * vps; srow = merge_src(lg, row, q); }
+      int srow = row; int off = v;
+      if (lg.mode == 2 && on) { int q = fdiv(v, lg.dvps); off = v - q * vps; srow = merge_src(lg, row, q); }
       srow_k[k] = (on && srow >= 0) ? srow * vps + off : -1;
       const long long xi = srow_k[k] >= 0 ? srow_k[k] : 0;
       xh[k] = Vec4IO<float>::ld(x, xi);
       rr[k] = Vec4IO<float>::ld(rsrc, xi);
-      draw[k] = Vec4IO<YT>::ldraw(dy, on ? dyrow * vrow + v : 0);
+      draw[k] = Vec4IO<YT>::ldraw(dy, on ? (long long)(dyrow * vrow + v) : 0);
     }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -339,12 +344,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const YT* __restrict__ dy, 
       ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
     }
     const float m1 = group_sum<G>(s1) * inv_n, m2 = group_sum<G>(s2) * inv_n;
-    long long slot2 = 0;
+    int slot2 = 0;
     float sc2 = 1.0f;
     if (lg.y2 != nullptr && inr) {
-      const int tok_per_img = lg.g2.H * lg.g2.W;
-      const int b2 = (int)(row / tok_per_img);
-      slot2 = (long long)b2 * (lg.g2.nW * lg.g2.N) + token_to_slot(lg.g2, (int)(row - (long long)b2 * tok_per_img));
+      int in2;
+      const int b2 = split_tok_row(lg.g2, row, &in2);
+      slot2 = b2 * (lg.g2.nW * lg.g2.N) + token_to_slot(lg.g2, in2);
       if (lg.y2_scale != nullptr) sc2 = lg.y2_scale[b2];
     }
 #pragma unroll
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const YT* __restrict__ dy, 
         Vec4IO<float>::st(dx, srow_k[k], o);
         if (lg.y2 != nullptr) {
           o.x *= sc2; o.y *= sc2; o.z *= sc2; o.w *= sc2;
-          Vec4IO<YT>::st(reinterpret_cast<YT*>(lg.y2), slot2 * vrow + (gl + G * k), o);
+          Vec4IO<YT>::st(reinterpret_cast<YT*>(lg.y2), (long long)(slot2 * vrow + (gl + G * k)), o);
           a2[k].x += o.x; a2[k].y += o.y; a2[k].z += o.z; a2[k].w += o.w;
         }
       }
@@ -408,10 +413,15 @@ static int ln_geom(const swin_ln_args* a, bool bwd, LnGeom* out) {
   lg.mode = a->mode; lg.C = a->C; lg.nseg = a->mode == 2 ? 4 : 1;
   lg.H2 = (a->H + 1) / 2; lg.W2 = (a->W + 1) / 2;
   lg.eps = a->eps;
-  long long tokens = (long long)a->B * a->H * a->W;
-  if (a->mode == 0) lg.rows = tokens;
-  else if (a->mode == 1) lg.rows = bwd ? tokens : (long long)a->B * lg.g.nW * lg.g.N;
-  else lg.rows = (long long)a->B * lg.H2 * lg.W2;
+  long long tokens = (long long)a->B * a->H * a->W, rows;
+  if (a->mode == 0) rows = tokens;
+  else if (a->mode == 1) rows = bwd ? tokens : (long long)a->B * lg.g.nW * lg.g.N;
+  else rows = (long long)a->B * lg.H2 * lg.W2;
+  const long long slots = (long long)a->B * lg.g.nW * lg.g.N;
+  SWIN_REQUIRE(rows < (1ll << 30) && (slots > tokens ? slots : tokens) * (a->C / 4) * lg.nseg < (1ll << 31),
+               "ln: tensor too large for the kernels' 32-bit row / vector indices");
+  lg.rows = (int)rows;
+  lg.dper2 = make_fastdiv(lg.H2 * lg.W2); lg.dW2 = make_fastdiv(lg.W2); lg.dvps = make_fastdiv(a->C / 4);
   SWIN_REQUIRE(a->y_dtype == SWIN_F32 || (a->y_dtype == SWIN_BF16), "ln: bad y dtype");
   lg.g2 = lg.g; lg.y2 = nullptr; lg.y2_scale = nullptr; lg.y2_colsum = nullptr;
   if (bwd && a->dy2 != nullptr) {
@@ -486,12 +496,12 @@ static int ln_bwd_dispatch(const swin_ln_args* a, const LnGeom& lg, cudaStream_t
 template <typename YT, int kMaxV>
 __global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict__ x, YT* __restrict__ y,
                                                          const float* __restrict__ row_scale, int mode, WinGeom g,
-                                                         long long rows, float* __restrict__ colsum) {
+                                                         int rows, float* __restrict__ colsum) {
   extern __shared__ float scol[];           // [C] block partial column sums (only when colsum != nullptr)
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int vrow = g.C >> 2;
-  const int per_img_slots = g.nW * g.N, per_img_tok = g.H * g.W;
+  const int per_img_tok = g.H * g.W;
   float4 acc[kMaxV];
 #pragma unroll
   for (int k = 0; k < kMaxV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -501,21 +511,21 @@ __global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict
   }
   // 4 rows per warp iteration: their loads are independent, so 4x the bytes are in flight per warp
   constexpr int RU = 4;
-  for (long long row0 = ((long long)blockIdx.x * wpb + (threadIdx.x >> 5)) * RU; row0 < rows; row0 += (long long)gridDim.x * wpb * RU) {
-    long long srow[RU];
+  for (int row0 = (blockIdx.x * wpb + (threadIdx.x >> 5)) * RU; row0 < rows; row0 += gridDim.x * wpb * RU) {
+    int srow[RU];
     float sc[RU];
 #pragma unroll
     for (int u = 0; u < RU; ++u) {
-      const long long row = row0 + u;
+      const int row = row0 + u;
       srow[u] = -2; sc[u] = 1.0f;
       if (row < rows) {
-        int b;
+        int b, in;
         if (mode == 1) {
-          b = (int)(row / per_img_slots);
-          int t = slot_to_token(g, (int)(row - (long long)b * per_img_slots));
-          srow[u] = t < 0 ? -1 : (long long)b * per_img_tok + t;
+          b = split_slot_row(g, row, &in);
+          int t = slot_to_token(g, in);
+          srow[u] = t < 0 ? -1 : b * per_img_tok + t;
         } else {
-          b = (int)(row / per_img_tok);
+          b = split_tok_row(g, row, &in);
           srow[u] = row;
         }
         if (row_scale) sc[u] = row_scale[b];
@@ -527,12 +537,12 @@ __global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict
       if (v < vrow) {
         float4 t[RU];
 #pragma unroll
-        for (int u = 0; u < RU; ++u) t[u] = srow[u] >= 0 ? Vec4IO<float>::ld(x, srow[u] * vrow + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < RU; ++u) t[u] = srow[u] >= 0 ? Vec4IO<float>::ld(x, (long long)(srow[u] * vrow + v)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int u = 0; u < RU; ++u) {
           if (srow[u] == -2) continue;
           t[u] = make_float4(t[u].x * sc[u], t[u].y * sc[u], t[u].z * sc[u], t[u].w * sc[u]);
-          Vec4IO<YT>::st(y, (row0 + u) * vrow + v, t[u]);
+          Vec4IO<YT>::st(y, (long long)((row0 + u) * vrow + v), t[u]);
           acc[k].x += t[u].x; acc[k].y += t[u].y; acc[k].z += t[u].z; acc[k].w += t[u].w;
         }
       }
@@ -710,12 +720,13 @@ extern "C" int swin_scale_cast(const float* x, void* y, const float* row_scale, 
   SWIN_REQUIRE(ws > 0 && shift >= 0 && shift < ws, "scale_cast: bad window geometry");
   WinGeom g = make_geom(B, H, W, C, ws, shift);
   long long rows = mode == 1 ? (long long)B * g.nW * g.N : (long long)B * H * W;
+  SWIN_REQUIRE(rows < (1ll << 30) && rows * (C / 4) < (1ll << 31), "scale_cast: tensor too large for 32-bit row / vector indices");
   long long blocks = ceil_div64(rows, 8 * 4 * 4);
   int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
   if (grid < 1) grid = 1;
   size_t smem = colsum ? (size_t)C * sizeof(float) : 0;
   const int kv = ceil_div(C / 4, 32);           // float4 vectors per lane (C <= 1024 -> <= 8)
-#define SC_LAUNCH(T, KV) scale_cast_kernel<T, KV><<<grid, 256, smem, (cudaStream_t)stream>>>(x, (T*)y, row_scale, mode, g, rows, colsum)
+#define SC_LAUNCH(T, KV) scale_cast_kernel<T, KV><<<grid, 256, smem, (cudaStream_t)stream>>>(x, (T*)y, row_scale, mode, g, (int)rows, colsum)
 #define SC_DISPATCH(T)                                                                          \
   do {                                                                                          \
     if (kv <= 1) SC_LAUNCH(T, 1); else if (kv <= 2) SC_LAUNCH(T, 2); else if (kv <= 3) SC_LAUNCH(T, 3); \

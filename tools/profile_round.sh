@@ -11,7 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start o
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"gemm_tc|attn_tc|ln_fwd|ln_bwd|ln_nchw|scale_cast|colsum|patch_unfold|rel_bias" -c 45 \
     -o gpurun_out/${R}_fwd_stage0 python bench.py --ncu-step --warmup 3 > gpurun_out/ncu_b.log 2>&1
 # backward, stage 0 (last kernels of the step)
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"gemm_tc|attn_tc|ln_fwd|ln_bwd|ln_nchw|scale_cast|colsum|patch_unfold|rel_bias" --launch-skip 255 -c 60 \
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"gemm_tc|attn_tc|ln_fwd|ln_bwd|ln_nchw|scale_cast|colsum|patch_unfold|rel_bias" --launch-skip 225 -c 60 \
     -o gpurun_out/${R}_bwd_stage0 python bench.py --ncu-step --warmup 3 > gpurun_out/ncu_c.log 2>&1
 # stage-2 block (tensor-bound GEMMs): forward kernels 60..75
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"gemm_tc|attn_tc|ln_fwd|ln_bwd|ln_nchw|scale_cast|colsum|patch_unfold|rel_bias" --launch-skip 60 -c 16 \
