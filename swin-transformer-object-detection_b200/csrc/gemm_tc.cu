@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 8];
   __shared__ uint32_t tmem_base_slot;
   constexpr int kEW = epi_warps(EPI_CLASS);          // epilogue warps of this instantiation
-  __shared__ __align__(8) uint64_t aux_bars[kEpiWarps][2];
+  __shared__ __align__(8) uint64_t aux_bars[kEpiWarps][4];
   __shared__ __align__(1024) __nv_bfloat16 ones_tile[(EPI_CLASS == 0 && A_MN && B_MN) ? 64 * 64 : 8];   // all-ones B operand (MN-major)
   __shared__ long long epi_rowdst[kEpiWarps][32];
   __shared__ float epi_rowscale[kEpiWarps][32];
@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 4; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEW); }
-    for (int w = 0; w < kEpiWarps; ++w) { mbar_init(smem_u32(&aux_bars[w][0]), 1); mbar_init(smem_u32(&aux_bars[w][1]), 1); }
+    for (int w = 0; w < kEpiWarps; ++w)
+      for (int b = 0; b < 4; ++b) mbar_init(smem_u32(&aux_bars[w][b]), 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -255,10 +256,13 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
       constexpr int kGroups = kEW / 4;          // warps per lane quarter
       if (EPI_CLASS == 2) {
         // ---- DGELU (bf16: D = (acc+bias) * aux) / RESIDUAL (fp32: D = aux + row_scale * (acc+bias)):
-        //      the aux tile of each 32x32 chunk is TMA-loaded one chunk ahead into a per-warp double buffer, updated in
-        //      place by the thread that owns the row (TMEM row layout) and TMA-stored from the same buffer.
+        //      the aux tile of each 32x32 chunk is TMA-loaded ahead of use into a per-warp ring (4 x 2 KB bf16 tiles: up to
+        //      three chunks ahead, i.e. a warp's whole share of a unit is requested before it waits for the accumulator;
+        //      2 x 4 KB fp32 tiles: one chunk ahead), updated in place by the thread that owns the row (TMEM row layout)
+        //      and TMA-stored from the same buffer.
         const bool resid = p.epi.epilogue == SWIN_EPI_RESIDUAL;
         const uint32_t tile_bytes = resid ? 4096u : 2048u;
+        const uint32_t nbuf = resid ? 2u : 4u;
         uint8_t* sbuf = reinterpret_cast<uint8_t*>(stage);
         const uint32_t sbuf_a = smem_u32(sbuf);
         const uint32_t abar0 = smem_u32(&aux_bars[ew][0]);
@@ -267,48 +271,44 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
           int rr = row_base + lane; if (rr >= p.epi.M) rr = p.epi.M - 1;
           rscale = p.epi.row_scale[rr / p.epi.rows_per_image];
         }
-        int c = chunk_sel * 32;
-        uint32_t cur = aux_n;
-        if (c < p.block_n) {
+        const int c0 = chunk_sel * 32;
+        const int nch = c0 < p.block_n ? (p.block_n - c0 + 63) / 64 : 0;       // this warp's chunks: c0, c0 + 64, ...
+        auto issue_aux = [&](int k) {
           if (lane == 0) {
-            tma_store_wait_read<0>();
-            const uint32_t b = aux_n & 1;
+            tma_store_wait_read<0>();                 // the store that last read the target buffer has drained it
+            const uint32_t b = aux_n % nbuf;
             mbar_expect_tx(abar0 + 8 * b, tile_bytes);
-            tma_load_2d(sbuf_a + b * tile_bytes, &tmD2, abar0 + 8 * b, n0 + c, row_base);
+            tma_load_2d(sbuf_a + b * tile_bytes, &tmD2, abar0 + 8 * b, n0 + c0 + 64 * k, row_base);
           }
           ++aux_n;
-        }
+        };
+        uint32_t cur = aux_n;
+        int issued = 0;
+        for (; issued < nch && issued < (int)nbuf - 1; ++issued) issue_aux(issued);
         mbar_wait(tfull_bar(acc), acc_ph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
         uint32_t v[32];
-        if (c < p.block_n) tmem_ld32(taddr + c, v);
-        for (; c < p.block_n; c += 64, ++cur) {
+        if (nch > 0) tmem_ld32(taddr + c0, v);
+        for (int k = 0; k < nch; ++k, ++cur) {
+          const int c = c0 + 64 * k;
           float4 b4[8];
           if (p.epi.bias != nullptr) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) b4[k] = __ldg(reinterpret_cast<const float4*>(p.epi.bias + n0 + c) + k);
+            for (int kk = 0; kk < 8; ++kk) b4[kk] = __ldg(reinterpret_cast<const float4*>(p.epi.bias + n0 + c) + kk);
           } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) b4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int kk = 0; kk < 8; ++kk) b4[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          const uint32_t b = cur & 1;
+          const uint32_t b = cur % nbuf;
           uint8_t* tile = sbuf + b * tile_bytes;
           tmem_ld_wait();
-          mbar_wait(abar0 + 8 * b, (cur >> 1) & 1);
+          mbar_wait(abar0 + 8 * b, (cur / nbuf) & 1);
           if (resid) {
             float4 ax[8];
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) ax[cc] = *reinterpret_cast<const float4*>(tile + lane * 128 + ((cc ^ (lane & 7)) << 4));
-            if (c + 64 < p.block_n) {                 // request the next chunk's aux tile (other buffer)
-              if (lane == 0) {
-                tma_store_wait_read<0>();
-                const uint32_t nb = aux_n & 1;
-                mbar_expect_tx(abar0 + 8 * nb, tile_bytes);
-                tma_load_2d(sbuf_a + nb * tile_bytes, &tmD2, abar0 + 8 * nb, n0 + c + 64, row_base);
-              }
-              ++aux_n;
-            }
+            if (issued < nch) { issue_aux(issued); ++issued; }     // request the next aux tile of this unit
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) {
               float4 o;
@@ -323,29 +323,21 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
             int4 ax[4];
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) ax[cc] = *reinterpret_cast<const int4*>(tile + lane * 64 + ((cc ^ swz) << 4));
-            if (c + 64 < p.block_n) {
-              if (lane == 0) {
-                tma_store_wait_read<0>();
-                const uint32_t nb = aux_n & 1;
-                mbar_expect_tx(abar0 + 8 * nb, tile_bytes);
-                tma_load_2d(sbuf_a + nb * tile_bytes, &tmD2, abar0 + 8 * nb, n0 + c + 64, row_base);
-              }
-              ++aux_n;
-            }
+            if (issued < nch) { issue_aux(issued); ++issued; }
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
               const uint32_t g[4] = {(uint32_t)ax[cc].x, (uint32_t)ax[cc].y, (uint32_t)ax[cc].z, (uint32_t)ax[cc].w};
               uint32_t o[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int k = 8 * cc + 2 * e;          // columns k, k+1
-                const float bx = (k & 3) == 0 ? b4[k >> 2].x : b4[k >> 2].z, by = (k & 3) == 0 ? b4[k >> 2].y : b4[k >> 2].w;
-                o[e] = pack_bf16((__uint_as_float(v[k]) + bx) * bf16_lo(g[e]), (__uint_as_float(v[k + 1]) + by) * bf16_hi(g[e]));
+                const int kx = 8 * cc + 2 * e;          // columns kx, kx+1
+                const float bx = (kx & 3) == 0 ? b4[kx >> 2].x : b4[kx >> 2].z, by = (kx & 3) == 0 ? b4[kx >> 2].y : b4[kx >> 2].w;
+                o[e] = pack_bf16((__uint_as_float(v[kx]) + bx) * bf16_lo(g[e]), (__uint_as_float(v[kx + 1]) + by) * bf16_hi(g[e]));
               }
               *reinterpret_cast<int4*>(tile + lane * 64 + ((cc ^ swz) << 4)) = make_int4(o[0], o[1], o[2], o[3]);
             }
           }
-          if (c + 64 < p.block_n) tmem_ld32(taddr + c + 64, v);
+          if (k + 1 < nch) tmem_ld32(taddr + c + 64, v);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) { tma_store_2d(&tmD, sbuf_a + b * tile_bytes, n0 + c, row_base); tma_store_commit(); }
@@ -559,7 +551,7 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
       p.tma_epi = 2;
     }
   }
-  p.epi_bytes_per_warp = (p.tma_epi == 2 && a->epilogue == SWIN_EPI_RESIDUAL) ? 8192u : 4096u;
+  p.epi_bytes_per_warp = p.tma_epi == 2 ? 8192u : 4096u;     // class 2: 2 x 4 KB (fp32) or 4 x 2 KB (bf16) aux ring per warp
   const uint32_t epi_bytes = p.epi_bytes_per_warp * (uint32_t)epi_warps(p.tma_epi);
   {
     const uint32_t ring_budget = 212 * 1024 - epi_bytes - 1024;     // dynamic smem: ring + epilogue staging + alignment slack
