@@ -96,106 +96,108 @@ __device__ __forceinline__ void load_bias_tile(float* sBias, const float* __rest
 #endif
 
 // ------------------------------------------------------------------------------------------ forward
-constexpr uint32_t kFwdTiles = 3 * kTileBytes;     // Q,K,V per buffer
+// 128 threads per CTA, thread = one row of the stacked 128-row tile (all 49 columns of its own window), four CTAs per SM:
+// an item is a strictly serial chain (TMA -> S MMA -> softmax -> P.V MMA -> O -> TMA store) whose latencies are hidden by
+// the other three resident CTAs rather than by intra-CTA pipelining; that needs <= 56 KB of smem (single-buffered tiles:
+// Q,K are re-filled as soon as S has been computed, V as soon as P.V has, so the next item's loads still overlap this
+// item's softmax), <= 128 registers and 128 TMEM columns (O overlays columns [0,64) of S once P is in smem).
+constexpr uint32_t kFwdTiles = 3 * kTileBytes;     // Q,K,V
+constexpr int kFwdThreads = 128;
+constexpr int kFwdBiasLd = 52;                     // bias row pitch of the forward kernel: 49 columns + 3 x kNegBig
 
-__global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
-                                                                       const __grid_constant__ CUtensorMap tmOut, AttnTcParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                                      const __grid_constant__ CUtensorMap tmOut, AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[5];              // load[2], s[2], o
+  __shared__ __align__(8) uint64_t bars[4];              // qk, v, s, o
   __shared__ uint32_t tmem_slot;
-  __shared__ float sRed[2][2][128];                       // [max|sum][half][row]
   uint8_t* sbase = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sT = sbase;                                   // 2 x {Q,K,V}
-  uint8_t* sP = sT + 2 * kFwdTiles;                      // 16 KB
+  uint8_t* sT = sbase;                                   // {Q,K,V}
+  uint8_t* sP = sT + kFwdTiles;                          // 16 KB: P, later the O staging tile
   float* sBias = reinterpret_cast<float*>(sP + kPBytes); // [49][52]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, hf = warp >> 2;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int h = blockIdx.x % p.nH, g = blockIdx.x / p.nH;
-  const uint32_t bar_load0 = smem_u32(&bars[0]), bar_s0 = smem_u32(&bars[2]), bar_o = smem_u32(&bars[4]);
+  const uint32_t bar_qk = smem_u32(&bars[0]), bar_v = smem_u32(&bars[1]), bar_s = smem_u32(&bars[2]), bar_o = smem_u32(&bars[3]);
 
-  zero_smem(sT, 2 * kFwdTiles + kPBytes);
-  load_bias_tile(sBias, p.bias, h);
+  zero_smem(sT, kFwdTiles + kPBytes);
+  {
+    const float kLog2e = 1.4426950408889634f;
+    for (int e = tid; e < AN * kFwdBiasLd; e += blockDim.x) {
+      const int bi = e / kFwdBiasLd, bj = e - bi * kFwdBiasLd;
+      sBias[e] = bj < AN ? p.bias[((size_t)h * AN + bi) * AN + bj] * kLog2e : kNegBig;
+    }
+  }
   if (tid == 0) {
-    mbar_init(bar_load0, 1); mbar_init(bar_load0 + 8, 1); mbar_init(bar_s0, 1); mbar_init(bar_s0 + 8, 1); mbar_init(bar_o, 1);
+    mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmQKV);
   }
-  if (warp == 0) { tmem_alloc(smem_u32(&tmem_slot), 256); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(smem_u32(&tmem_slot), 128); tmem_relinquish(); }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // two S accumulators (128 columns each): S of item i+1 is computed while item i is in its P.V / epilogue phase.
-  // O of item i overlays columns [0,64) of its own S buffer once P is in smem.
-  const uint32_t tmem0 = tmem_slot;
-  const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-
-  const int r = q * 32 + lane, wloc = r >> 6, i = r & 63;
-  const int jbase = hf * 32;
+  const uint32_t tS = tmem_slot, tO = tmem_slot;
+  const int r = tid, wloc = r >> 6, i = r & 63;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
   const uint32_t idesc_s = umma_idesc_bf16(128, false, false);
   const uint32_t idesc_o = umma_idesc_bf16(64, false, true);
-  const uint32_t aT = smem_u32(sT), aP = smem_u32(sP);
+  const uint32_t aQ = smem_u32(sT), aK = aQ + kTileBytes, aV = aK + kTileBytes, aP = smem_u32(sP);
   const float kLog2e = 1.4426950408889634f;
   const float sc2 = p.scale * kLog2e;
   const int stride = p.ctas_per_head;
 
-  auto issue_loads = [&](int pair, int buf) {
-    const uint32_t bar = bar_load0 + 8 * buf, base = aT + buf * kFwdTiles;
-    mbar_expect_tx(bar, 6 * kBoxBytes);
+  auto issue_qk = [&](int pair) {
+    mbar_expect_tx(bar_qk, 4 * kBoxBytes);
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
       const int row0 = (2 * pair + w) * AN;
-      tma_load_2d(base + w * 4096, &tmQKV, bar, h * AHD, row0);
-      tma_load_2d(base + kTileBytes + w * 4096, &tmQKV, bar, p.C + h * AHD, row0);
-      tma_load_2d(base + 2 * kTileBytes + w * 4096, &tmQKV, bar, 2 * p.C + h * AHD, row0);
+      tma_load_2d(aQ + w * 4096, &tmQKV, bar_qk, h * AHD, row0);
+      tma_load_2d(aK + w * 4096, &tmQKV, bar_qk, p.C + h * AHD, row0);
     }
   };
-  auto issue_s = [&](uint32_t item) {          // S(item) = Q K^T into S buffer item&1, once its tiles have landed
-    const uint32_t b = item & 1;
-    mbar_wait(bar_load0 + 8 * b, (item >> 1) & 1);
-    tc_fence_after();
-    const uint32_t aQ = aT + b * kFwdTiles, aK = aQ + kTileBytes;
+  auto issue_v = [&](int pair) {
+    mbar_expect_tx(bar_v, 2 * kBoxBytes);
 #pragma unroll
-    for (int k = 0; k < 2; ++k)
-      umma_bf16(tmem0 + 128 * b, umma_desc(aQ + k * 32, 16, 512, kSw64), umma_desc(aK + k * 32, 16, 512, kSw64), idesc_s, k);
-    umma_commit(bar_s0 + 8 * b);
+    for (int w = 0; w < 2; ++w) tma_load_2d(aV + w * 4096, &tmQKV, bar_v, 2 * p.C + h * AHD, (2 * pair + w) * AN);
   };
-  if (tid == 0 && g < p.npairs) {
-    issue_loads(g, 0);
-    if (g + stride < p.npairs) issue_loads(g + stride, 1);
-    issue_s(0);
-  }
-  TDECL
+  if (tid == 0 && g < p.npairs) { issue_qk(g); issue_v(g); }
 
   uint32_t it = 0;
   for (int pair = g; pair < p.npairs; pair += stride, ++it) {
-    const uint32_t ph = it & 1, buf = it & 1, sph = (it >> 1) & 1;
-    const uint32_t aV = aT + buf * kFwdTiles + 2 * kTileBytes;
-    const uint32_t tS = tmem0 + 128 * buf, tO = tS;
-    TITEM
+    const uint32_t ph = it & 1;
+    const bool has_next = pair + stride < p.npairs;
+    if (tid == 0) {                              // S = Q K^T as soon as Q, K have landed
+      mbar_wait(bar_qk, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        umma_bf16(tS, umma_desc(aQ + k * 32, 16, 512, kSw64), umma_desc(aK + k * 32, 16, 512, kSw64), idesc_s, k);
+      umma_commit(bar_s);
+    }
     const int win = 2 * pair + wloc;
     const bool valid = (i < AN) && (win < p.B_);
     const float* mrow = nullptr;
-    uint32_t mb = 0u;                          // closed-form mask bits of this thread's 32 columns
+    unsigned long long mb = 0ULL;                // closed-form mask bits of this row (bit j: -100)
     if (p.mask != nullptr && valid) {
       const int mw = win % p.nW;
-      if (p.canon_nwh > 0) mb = (uint32_t)(canon_mask_bits(mw, p.canon_nwh, p.canon_nww, i) >> jbase);
+      if (p.canon_nwh > 0) mb = canon_mask_bits(mw, p.canon_nwh, p.canon_nww, i);
       else if (p.mask_nz == nullptr || p.mask_nz[mw]) mrow = p.mask + ((size_t)mw * AN + i) * AN;
     }
-    mbar_wait(bar_s0 + 8 * buf, sph);
+    mbar_wait(bar_s, ph);
     tc_fence_after();
-    TMARK(0);
-    uint32_t v[32];
-    tmem_ld32(tS + lane_off + wloc * 64 + jbase, v);
-    tmem_ld_wait();
-    TMARK(1);
+    if (tid == 0 && has_next) issue_qk(pair + stride);      // the Q, K tiles are free again
     // Rows >= 49 of a window (and a whole missing window) run the same math on harmless finite values: their P rows only
-    // feed O rows that are never stored.  Columns >= 49 carry kNegBig from the bias tile, so they become exact zeros.
-    float sv[32];
+    // feed O rows that are never stored.  Columns 49..51 carry kNegBig from the bias tile, so they become exact zeros.
+    uint32_t v[52];
+    tmem_ld32(tS + lane_off + wloc * 64, v);
+    tmem_ld16(tS + lane_off + wloc * 64 + 32, v + 32);
+    tmem_ld4(tS + lane_off + wloc * 64 + 48, v + 48);
+    tmem_ld_wait();
+    float sv[52];
     {
-      const float4* b4 = reinterpret_cast<const float4*>(sBias + (i < AN ? i : AN - 1) * kBiasLd + jbase);
+      const float4* b4 = reinterpret_cast<const float4*>(sBias + (i < AN ? i : AN - 1) * kFwdBiasLd);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 13; ++c) {
         const float4 bb = b4[c];
         sv[4 * c + 0] = fmaf(__uint_as_float(v[4 * c + 0]), sc2, bb.x);
         sv[4 * c + 1] = fmaf(__uint_as_float(v[4 * c + 1]), sc2, bb.y);
@@ -205,84 +207,83 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_fwd_kernel(const __gr
     }
     if (mrow != nullptr) {
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj)
-        if (jbase + jj < AN) sv[jj] = fmaf(__ldg(mrow + jbase + jj), kLog2e, sv[jj]);
+      for (int jj = 0; jj < AN; ++jj) sv[jj] = fmaf(__ldg(mrow + jj), kLog2e, sv[jj]);
     }
-    if (mb != 0u) {
+    if (mb != 0ULL) {
+      const uint32_t lo = (uint32_t)mb, hi = (uint32_t)(mb >> 32);
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj)
-        if ((mb >> jj) & 1u) sv[jj] -= 100.0f * kLog2e;
+        if ((lo >> jj) & 1u) sv[jj] -= 100.0f * kLog2e;
+#pragma unroll
+      for (int jj = 32; jj < AN; ++jj)
+        if ((hi >> (jj - 32)) & 1u) sv[jj] -= 100.0f * kLog2e;
     }
     float mx = sv[0];
 #pragma unroll
-    for (int jj = 1; jj < 32; ++jj) mx = fmaxf(mx, sv[jj]);
-    sRed[0][hf][r] = mx;
-    TMARK(2);
-    if (tid == 0) tma_store_wait_read<0>();      // the previous item's O tile (staged in sP) has been drained by TMA
-    __syncthreads();
-    TMARK(3);
+    for (int jj = 1; jj < AN; ++jj) mx = fmaxf(mx, sv[jj]);
     float sum = 0.f;
-    mx = fmaxf(sRed[0][0][r], sRed[0][1][r]);
 #pragma unroll
-    for (int jj = 0; jj < 32; ++jj) {
+    for (int jj = 0; jj < 52; ++jj) {
       const float e = ex2_ftz(sv[jj] - mx);
       sum += e;
       sv[jj] = e;
     }
-    sRed[1][hf][r] = sum;
-    TMARK(4);
+    // P row -> compact 128x64 bf16 tile (SW128): chunks 0..5 = columns 0..47, chunk 6 = columns 48..51 + zeros, chunk 7 = zeros
 #pragma unroll
-    for (int c = 0; c < 4; ++c) store_row_bf16x8(sP + sw128_off(r, hf * 4 + c), sv + 8 * c);
+    for (int c = 0; c < 6; ++c) store_row_bf16x8(sP + sw128_off(r, c), sv + 8 * c);
+    {
+      int4 pk;
+      pk.x = pack_bf16(sv[48], sv[49]); pk.y = pack_bf16(sv[50], sv[51]); pk.z = 0; pk.w = 0;
+      *reinterpret_cast<int4*>(sP + sw128_off(r, 6)) = pk;
+      *reinterpret_cast<int4*>(sP + sw128_off(r, 7)) = make_int4(0, 0, 0, 0);
+    }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
-    TMARK(5);
-    if (tid == 0) {
+    if (tid == 0) {                              // O = P [V0 | V1]
+      mbar_wait(bar_v, ph);
       tc_fence_after();
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
         umma_bf16(tO, umma_desc(aP + kk * 32, 16, 1024, kSw128), umma_desc(aV + kk * 1024, 4096, 512, kSw64), idesc_o, kk);
       umma_commit(bar_o);
-      if (pair + stride < p.npairs) issue_s(it + 1);      // next item's S overlaps this item's P.V + epilogue
     }
-    sum = sRed[1][0][r] + sRed[1][1][r];
     mbar_wait(bar_o, ph);
     tc_fence_after();
-    TMARK(6);
-    uint32_t o[16];
-    tmem_ld16(tO + lane_off + wloc * 32 + hf * 16, o);
+    if (tid == 0 && has_next) issue_v(pair + stride);       // the V tile is free again
+    uint32_t o[32];
+    tmem_ld32(tO + lane_off + wloc * 32, o);
     tmem_ld_wait();
     {
-      // O rows -> bf16 tile in sP (free: the P.V MMA has completed), 64-byte-swizzle layout, window w at +4096;
-      // then one TMA store of 49 rows x 32 columns per window instead of per-thread strided stores
+      // O row -> bf16 tile in sP (free: the P.V MMA has completed), 64-byte-swizzle layout, window w at +4096; then one
+      // TMA store of 49 rows x 32 columns per window
       const float inv = valid ? 1.0f / sum : 0.f;
       const uint32_t swz = (uint32_t)((r >> 1) & 3);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < 4; ++c) {
         float t[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) t[e] = __uint_as_float(o[8 * c + e]) * inv;
-        store_row_bf16x8(sP + r * 64 + (((uint32_t)(hf * 2 + c) ^ swz) << 4), t);
+        store_row_bf16x8(sP + r * 64 + (((uint32_t)c ^ swz) << 4), t);
       }
-      if (valid && hf == 0) p.lse[((size_t)win * p.nH + h) * AN + i] = (mx + log2f(sum)) * 0.6931471805599453f;   // natural-log LSE
+      if (valid) p.lse[((size_t)win * p.nH + h) * AN + i] = (mx + log2f(sum)) * 0.6931471805599453f;   // natural-log LSE
     }
-    TMARK(7);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
-    TMARK(8);
     if (tid == 0) {
 #pragma unroll
       for (int w = 0; w < 2; ++w)
         if (2 * pair + w < p.B_) tma_store_2d(&tmOut, aP + w * 4096, h * AHD, (2 * pair + w) * AN);
       tma_store_commit();
+      // sP is rewritten with the next item's P only after every thread has passed bar_s of the next item, which this
+      // thread commits after this wait: the staged O tile has been read out by then
+      tma_store_wait_read<0>();
     }
-    // tile buffer `buf` (Q,K used by S(it), V by O(it)) is free again: fetch item it+2 into it
-    if (tid == 0 && pair + 2 * stride < p.npairs) issue_loads(pair + 2 * stride, buf);
   }
-  TPRINT("attn_fwd");
   if (tid == 0) tma_store_wait_all<0>();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_slot, 256); }
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_slot, 128); }
 }
 
 // ------------------------------------------------------------------------------------------ backward
@@ -526,13 +527,13 @@ static int attn_tc_common(const swin_attn_args* a, AttnTcParams* out, bool bwd, 
 
 int attn_tc_fwd(const swin_attn_args* a, cudaStream_t st) {
   AttnTcParams p;
-  int rc = attn_tc_common(a, &p, false, 2);
+  int rc = attn_tc_common(a, &p, false, 4);
   if (rc) return rc;
   if (p.B_ == 0) return 0;
   CUtensorMap tm;
   rc = make_tmap_bf16_2d(&tm, a->qkv, (uint64_t)3 * p.C, (uint64_t)p.B_ * AN, (uint64_t)3 * p.C * 2, AHD, AN, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
-  const size_t smem = 2 * kFwdTiles + kPBytes + AN * kBiasLd * sizeof(float) + 1024;
+  const size_t smem = kFwdTiles + kPBytes + (AN * kFwdBiasLd + 16) * sizeof(float) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -542,7 +543,7 @@ int attn_tc_fwd(const swin_attn_args* a, cudaStream_t st) {
   CUtensorMap tmo;
   rc = make_tmap_bf16_2d(&tmo, a->out, (uint64_t)p.C, (uint64_t)p.B_ * AN, (uint64_t)p.C * 2, AHD, AN, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
-  attn_tc_fwd_kernel<<<p.nH * p.ctas_per_head, kAttnThreads, smem, st>>>(tm, tmo, p);
+  attn_tc_fwd_kernel<<<p.nH * p.ctas_per_head, kFwdThreads, smem, st>>>(tm, tmo, p);
   SWIN_LAUNCH_CHECK();
   return 0;
 }

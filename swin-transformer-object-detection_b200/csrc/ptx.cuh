@@ -145,6 +145,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 }  // namespace swin
