@@ -86,7 +86,7 @@ typedef struct swin_ln_args {
   float* dbeta;
   /* bwd, mode 0, optional (NULL = off): dy2[slot(token)] = dy2_scale[b] * dx[token] in y_dtype, laid out as window
    * slots (B*nW, N, C) for (ws2, shift2) — the drop-path-scaled, partitioned dY of the proj Linear (REF:252 backward),
-   * emitted while dx is in registers.  Pad slots are NOT written (caller zero-fills dy2).  dy2_colsum (C) += column sums. */
+   * emitted while dx is in registers.  Pad slots are written as zeros by the kernel (dy2 needs no initialisation).  dy2_colsum (C) += column sums. */
   void* dy2;
   const float* dy2_scale;
   float* dy2_colsum;

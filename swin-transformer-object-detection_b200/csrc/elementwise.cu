@@ -2,6 +2,8 @@
 // the LayerNorm family (plain, fused with pad+roll+partition, fused with the PatchMerging gather),
 // casts, column sums and the relative-position-bias expand / reduce.
 // All accesses are 128-bit and coalesced per row; index arithmetic is done once per row.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace swin {
@@ -272,6 +274,28 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
   }
 }
 
+// Second output of the backward kernels (dY of the proj Linear in window-slot layout): tokens fill their own slots, and
+// the padding slots — the two rectangles hs >= H and ws >= W of the padded grid, 1-2 % of the rows — are zeroed here, so
+// the caller does not have to memset the whole tensor first.
+template <typename YT>
+__device__ __forceinline__ void zero_pad_slots(const WinGeom& g, YT* __restrict__ y2, int vrow) {
+  const int padH = g.Hp - g.H, padW = g.Wp - g.W;
+  const int per_img = padH * g.Wp + g.H * padW;
+  const int total = g.B * per_img;
+  const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int pidx = blockIdx.x * wpb + (threadIdx.x >> 5); pidx < total; pidx += gridDim.x * wpb) {
+    const int b = pidx / per_img;
+    int q = pidx - b * per_img, hs, wsrc;
+    if (q < padH * g.Wp) { hs = g.H + q / g.Wp; wsrc = q % g.Wp; }
+    else { q -= padH * g.Wp; hs = q / padW; wsrc = g.W + q % padW; }
+    int hh = hs - g.shift; if (hh < 0) hh += g.Hp;
+    int wq = wsrc - g.shift; if (wq < 0) wq += g.Wp;
+    const int wh = hh / g.ws, i = hh - wh * g.ws, ww = wq / g.ws, j = wq - ww * g.ws;
+    const long long slot = (long long)b * (g.nW * g.N) + (wh * g.nww + ww) * g.N + i * g.ws + j;
+    for (int v = lane; v < vrow; v += 32) Vec4IO<YT>::st(y2, slot * vrow + v, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+}
+
 // Backward.  Iteration rows: mode 0 -> LN rows; mode 1 -> TOKENS (dy read through token->slot);
 // mode 2 -> merged rows (dx scattered to the 4 source tokens; pad segments dropped).
 // dx = (dres) + rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += dy*xhat; dbeta += dy.
@@ -370,6 +394,193 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const YT* __restrict__ dy, 
       }
     }
   }
+  if (lg.y2 != nullptr) zero_pad_slots<YT>(lg.g2, reinterpret_cast<YT*>(lg.y2), vrow);
+  // block reduce of dgamma / dbeta partials, then one atomic per column per block
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v = gl + G * k;
+    if (v < vrow) {
+      atomicAdd(&sred[v * 4 + 0], ag[k].x); atomicAdd(&sred[v * 4 + 1], ag[k].y);
+      atomicAdd(&sred[v * 4 + 2], ag[k].z); atomicAdd(&sred[v * 4 + 3], ag[k].w);
+      atomicAdd(&sred[width + v * 4 + 0], ab[k].x); atomicAdd(&sred[width + v * 4 + 1], ab[k].y);
+      atomicAdd(&sred[width + v * 4 + 2], ab[k].z); atomicAdd(&sred[width + v * 4 + 3], ab[k].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < width; i += blockDim.x) {
+    atomicAdd(dgamma + i, sred[i]);
+    atomicAdd(dbeta + i, sred[width + i]);
+  }
+  if (lg.y2_colsum != nullptr) {               // column sums of the second output, reusing the first half of sred
+    __syncthreads();
+    for (int i = threadIdx.x; i < width; i += blockDim.x) sred[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int v = gl + G * k;
+      if (v < vrow) {
+        atomicAdd(&sred[v * 4 + 0], a2[k].x); atomicAdd(&sred[v * 4 + 1], a2[k].y);
+        atomicAdd(&sred[v * 4 + 2], a2[k].z); atomicAdd(&sred[v * 4 + 3], a2[k].w);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < width; i += blockDim.x) atomicAdd(lg.y2_colsum + i, sred[i]);
+  }
+}
+
+// Prefetching variant of the backward kernel for narrow rows (<= 4 float4 per lane): the row loads (x, residual gradient,
+// dy) of iteration i+1 are issued with cp.async into a per-warp, lane-private smem ring BEFORE iteration i is processed,
+// so two iterations' worth of bytes are in flight per warp without holding registers for them (the register-held
+// version is capped at 16 warps x 3.8 KB per SM by its 126 registers).  A lane only reads back slots it filled itself.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int VPL, typename YT> struct LnBwdStage {
+  static constexpr int kRaw = sizeof(typename Vec4IO<YT>::raw_t);            // 16 (fp32 dy) or 8 (bf16 dy)
+  static constexpr int kBytes = VPL * 32 * (16 + 16 + kRaw);                 // one stage of one warp
+};
+
+template <int VPL, int G, typename YT>
+__global__ void __launch_bounds__(256) ln_bwd_pf_kernel(const YT* __restrict__ dy, const float* __restrict__ x,
+                                                        const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                        const float* __restrict__ rstd, const float* __restrict__ dres,
+                                                        float* __restrict__ dx, float* __restrict__ dgamma,
+                                                        float* __restrict__ dbeta, LnGeom lg) {
+  extern __shared__ __align__(16) float sred[];            // [2][vrow*4] block partials, then the staging ring
+  typedef LnBwdStage<VPL, YT> Stg;
+  typedef typename Vec4IO<YT>::raw_t raw_t;
+  constexpr int R = 32 / G;
+  const int lane = threadIdx.x & 31, gl = lane % G, gi = lane / G;
+  const int wpb = blockDim.x >> 5;
+  const int vps = lg.C >> 2;
+  const int vrow = vps * lg.nseg;
+  const int width = vrow * 4;
+  const float inv_n = 1.0f / (float)width;
+  const int per_img_slots = lg.g.nW * lg.g.N;
+  uint8_t* stg = reinterpret_cast<uint8_t*>(sred) + (((size_t)2 * width * sizeof(float) + 15) & ~(size_t)15) +
+                 (size_t)(threadIdx.x >> 5) * 2 * Stg::kBytes;
+  for (int i = threadIdx.x; i < 2 * width; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  float4 ag[VPL], ab[VPL], a2[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) { ag[k] = make_float4(0.f, 0.f, 0.f, 0.f); ab[k] = ag[k]; a2[k] = ag[k]; }
+  const float* rsrc = dres != nullptr ? dres : x;
+  const bool has_res = dres != nullptr;
+  const int step = gridDim.x * wpb * R;
+  const int base0 = (blockIdx.x * wpb + (threadIdx.x >> 5)) * R;
+
+  // float4 offsets of this lane's VPL vectors of row `row` (-1: nothing to read / write) and its dy row
+  auto locate = [&](int row, bool inr, int* srow_k, int* dyrow) {
+    *dyrow = row;
+    if (lg.mode == 1 && inr) {
+      int in;
+      int b = split_tok_row(lg.g, row, &in);
+      *dyrow = b * per_img_slots + token_to_slot(lg.g, in);
+    }
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int v = gl + G * k;
+      const bool on = inr && v < vrow;
+      int srow = row, off = v;
+      if (lg.mode == 2 && on) { int q = fdiv(v, lg.dvps); off = v - q * vps; srow = merge_src(lg, row, q); }
+      srow_k[k] = (on && srow >= 0) ? srow * vps + off : -1;
+    }
+  };
+  auto issue = [&](int base, int st, float* mu_o, float* rs_o) {
+    const int row = base + gi;
+    const bool inr = row < lg.rows;
+    int sk[VPL], dyrow;
+    locate(row, inr, sk, &dyrow);
+    uint8_t* sb = stg + st * Stg::kBytes;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int v = gl + G * k;
+      const bool on = inr && v < vrow;
+      const long long xi = sk[k] >= 0 ? sk[k] : 0;
+      cp_async16(sb + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(x) + xi);
+      cp_async16(sb + VPL * 512 + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(rsrc) + xi);
+      const raw_t* dsrc = reinterpret_cast<const raw_t*>(dy) + (on ? (long long)(dyrow * vrow + v) : 0);
+      if (Stg::kRaw == 16) cp_async16(sb + VPL * 1024 + (k * 32 + lane) * 16, dsrc);
+      else cp_async8(sb + VPL * 1024 + (k * 32 + lane) * 8, dsrc);
+    }
+    *mu_o = inr ? __ldg(mean + row) : 0.f;
+    *rs_o = inr ? __ldg(rstd + row) : 0.f;
+  };
+
+  float mu_n = 0.f, rs_n = 0.f;
+  if (base0 < lg.rows) issue(base0, 0, &mu_n, &rs_n);
+  cp_async_commit();
+  int it = 0;
+  for (int base = base0; base < lg.rows; base += step, ++it) {
+    const float mu = mu_n, rs = rs_n;
+    if (base + step < lg.rows) issue(base + step, (it + 1) & 1, &mu_n, &rs_n);
+    cp_async_commit();
+    cp_async_wait<1>();                         // this iteration's group has landed (the prefetch may still be in flight)
+    const int row = base + gi;
+    const bool inr = row < lg.rows;
+    int srow_k[VPL], dyrow;
+    locate(row, inr, srow_k, &dyrow);
+    const uint8_t* sb = stg + (it & 1) * Stg::kBytes;
+    float4 xh[VPL], gd[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int v = gl + G * k;
+      const bool on = inr && v < vrow;
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + (on ? v : 0));
+      const float4 xv = *reinterpret_cast<const float4*>(sb + (k * 32 + lane) * 16);
+      raw_t draw;
+      if (Stg::kRaw == 16) draw = *reinterpret_cast<const raw_t*>(sb + VPL * 1024 + (k * 32 + lane) * 16);
+      else draw = *reinterpret_cast<const raw_t*>(sb + VPL * 1024 + (k * 32 + lane) * 8);
+      float4 d = Vec4IO<YT>::cvt(draw);
+      if (!on) d = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (srow_k[k] >= 0) xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      else if (on) xh[k] = make_float4(-mu * rs, -mu * rs, -mu * rs, -mu * rs);      // merge-mode zero pad: xhat = (0 - mu) * rs
+      else xh[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      gd[k] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+      s1 += gd[k].x + gd[k].y + gd[k].z + gd[k].w;
+      s2 += gd[k].x * xh[k].x + gd[k].y * xh[k].y + gd[k].z * xh[k].z + gd[k].w * xh[k].w;
+      ag[k].x += d.x * xh[k].x; ag[k].y += d.y * xh[k].y; ag[k].z += d.z * xh[k].z; ag[k].w += d.w * xh[k].w;
+      ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
+    }
+    const float m1 = group_sum<G>(s1) * inv_n, m2 = group_sum<G>(s2) * inv_n;
+    int slot2 = 0;
+    float sc2 = 1.0f;
+    if (lg.y2 != nullptr && inr) {
+      int in2;
+      const int b2 = split_tok_row(lg.g2, row, &in2);
+      slot2 = b2 * (lg.g2.nW * lg.g2.N) + token_to_slot(lg.g2, in2);
+      if (lg.y2_scale != nullptr) sc2 = lg.y2_scale[b2];
+    }
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      if (srow_k[k] >= 0) {
+        float4 o;
+        o.x = rs * (gd[k].x - m1 - xh[k].x * m2);
+        o.y = rs * (gd[k].y - m1 - xh[k].y * m2);
+        o.z = rs * (gd[k].z - m1 - xh[k].z * m2);
+        o.w = rs * (gd[k].w - m1 - xh[k].w * m2);
+        if (has_res) {
+          const float4 rr = *reinterpret_cast<const float4*>(sb + VPL * 512 + (k * 32 + lane) * 16);
+          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        }
+        Vec4IO<float>::st(dx, (long long)srow_k[k], o);
+        if (lg.y2 != nullptr) {
+          o.x *= sc2; o.y *= sc2; o.z *= sc2; o.w *= sc2;
+          Vec4IO<YT>::st(reinterpret_cast<YT*>(lg.y2), (long long)(slot2 * vrow + (gl + G * k)), o);
+          a2[k].x += o.x; a2[k].y += o.y; a2[k].z += o.z; a2[k].w += o.w;
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  if (lg.y2 != nullptr) zero_pad_slots<YT>(lg.g2, reinterpret_cast<YT*>(lg.y2), vrow);
   // block reduce of dgamma / dbeta partials, then one atomic per column per block
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
@@ -477,6 +688,23 @@ static int ln_bwd_dispatch(const swin_ln_args* a, const LnGeom& lg, cudaStream_t
   int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
   if (grid < 1) grid = 1;
   size_t smem = (size_t)2 * vrow * 4 * sizeof(float);
+  static const bool use_pf = getenv("SWIN_LN_BWD_NO_PREFETCH") == nullptr;
+#define LN_BWD_PF_CASE(V, GG)                                                                                      \
+  if (use_pf && G == GG && vpl <= V) {                                                                             \
+    const size_t smem_pf = ((smem + 15) & ~(size_t)15) + (size_t)8 * 2 * LnBwdStage<V, YT>::kBytes;                \
+    static bool attr_done = false;                                                                                 \
+    if (!attr_done) {                                                                                              \
+      cudaError_t e = cudaFuncSetAttribute(ln_bwd_pf_kernel<V, GG, YT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(ln_bwd): %s", cudaGetErrorString(e)); return (int)e; } \
+      attr_done = true;                                                                                            \
+    }                                                                                                              \
+    ln_bwd_pf_kernel<V, GG, YT><<<grid, 256, smem_pf, st>>>((const YT*)a->dy, a->x, a->gamma, a->mean, a->rstd, a->dres, \
+                                                           a->dx, a->dgamma, a->dbeta, lg);                        \
+    SWIN_LAUNCH_CHECK();                                                                                           \
+    return 0;                                                                                                      \
+  }
+  LN_BWD_PF_CASE(3, 8) LN_BWD_PF_CASE(4, 8) LN_BWD_PF_CASE(3, 16) LN_BWD_PF_CASE(4, 16) LN_BWD_PF_CASE(3, 32) LN_BWD_PF_CASE(4, 32)
+#undef LN_BWD_PF_CASE
 #define LN_BWD_CASE(V, GG)                                                                                         \
   if (G == GG && vpl <= V) {                                                                                       \
     ln_bwd_kernel<V, GG, YT><<<grid, 256, smem, st>>>((const YT*)a->dy, a->x, a->gamma, a->mean, a->rstd, a->dres, \

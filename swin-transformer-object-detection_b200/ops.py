@@ -203,7 +203,7 @@ def ln_bwd(mode: int, dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, me
         ws2, shift2, scale2 = emit_windows
         _chk(scale2)
         Hp, Wp = padded_hw(H, W, ws2)
-        dy2 = torch.zeros((B * (Hp // ws2) * (Wp // ws2) * ws2 * ws2, Cc), dtype=dy.dtype, device=x.device)   # pad slots stay 0
+        dy2 = torch.empty((B * (Hp // ws2) * (Wp // ws2) * ws2 * ws2, Cc), dtype=dy.dtype, device=x.device)   # the kernel zeroes the pad slots
         a.dy2, a.dy2_scale, a.dy2_colsum, a.ws2, a.shift2 = _p(dy2), _p(scale2), _p(dgb[2]), ws2, shift2
     _count()
     with _timed(f"ln_bwd mode{mode} C={Cc}{' +emit' if emit_windows is not None else ''}", 0.0, _nb(dy, x, dres, dx, dy2)):

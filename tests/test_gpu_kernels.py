@@ -130,11 +130,14 @@ def test_ln_bwd_emits_partitioned_proj_dy(ydt):
     s = torch.tensor([0.5, 1.25], device=DEV)
     _, mean, rstd = ops.ln_fwd(0, x, gm, bt, B, H, W, C, 1, 0, 1e-5, L.F32 if ydt == "f32" else L.BF16)
     dx0, dg0, db0 = ops.ln_bwd(0, dy, x, gm, mean, rstd, dres, B, H, W, C, 1, 0)
-    dx1, dg1, db1, dy2, cs2 = ops.ln_bwd(0, dy, x, gm, mean, rstd, dres, B, H, W, C, 1, 0, emit_windows=(ws, shift, s))
-    assert torch.equal(dx0, dx1) and rel(dg1, dg0) < 1e-5 and rel(db1, db0) < 1e-5
-    want, wcs = ops.scale_cast(dx0, s, 1, B, H, W, C, ws, shift, L.F32 if ydt == "f32" else L.BF16, want_colsum=True)
-    assert torch.equal(dy2, want)
-    assert rel(cs2, wcs) < 1e-5
+    for sh in (shift, 0):                       # shifted and unshifted window grids (pad slots must come back as exact zeros)
+        junk = torch.full((B * 2 * 2 * 49 * C,), 7.0, device=DEV)       # dirty the allocator block dy2 is likely to reuse
+        del junk
+        dx1, dg1, db1, dy2, cs2 = ops.ln_bwd(0, dy, x, gm, mean, rstd, dres, B, H, W, C, 1, 0, emit_windows=(ws, sh, s))
+        assert torch.equal(dx0, dx1) and rel(dg1, dg0) < 1e-5 and rel(db1, db0) < 1e-5
+        want, wcs = ops.scale_cast(dx0, s, 1, B, H, W, C, ws, sh, L.F32 if ydt == "f32" else L.BF16, want_colsum=True)
+        assert torch.equal(dy2, want)
+        assert rel(cs2, wcs) < 1e-5
 
 
 def test_scale_cast_and_colsum():
