@@ -284,13 +284,32 @@ def main():
     host_enqueue_ms = host_ms[0]
     value = world * B * K / (ms_total / 1e3)
 
-    # end to end through the public API: pinned host batch -> H2D every step, scalar loss read back every step
+    # end to end through the public API: every step uploads its batch from pinned host memory (H2D, 205 MB) and reads its
+    # scalar loss back (D2H).  The upload of step i+1 runs on a copy stream while step i computes (the usual input
+    # prefetch): it lands in a staging buffer and is moved into the graph's static input by a device-to-device copy.
+    copy_stream = torch.cuda.Stream()
+    x_stage = torch.empty_like(x_dev)
+    ev_ready, ev_free = torch.cuda.Event(), torch.cuda.Event()
+
+    def upload():
+        copy_stream.wait_event(ev_free)                      # the staging buffer has been consumed
+        with torch.cuda.stream(copy_stream):
+            x_stage.copy_(host, non_blocking=True)
+            ev_ready.record(copy_stream)
+
     def e2e_step():
-        x_dev.copy_(host, non_blocking=True)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev_ready)                             # this step's batch has arrived
+        x_dev.copy_(x_stage, non_blocking=True)
+        ev_free.record(cur)
+        upload()                                             # next step's batch streams in while this one computes
         return float(run_step().item())
+    ev_free.record(torch.cuda.current_stream())
+    upload()
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, K)
+    torch.cuda.synchronize()
     e2e_value = world * B * K / (ms_e2e / 1e3)
 
     # dominant kernel class (tcgen05 GEMMs: 92.7 % of the FLOPs) timed launch by launch in an instrumented pass
@@ -334,7 +353,8 @@ def main():
             "config": {"workload": WORKLOAD, "global_batch": world * B, "per_gpu_batch": B, "drop_path_rate": 0.1,
                        "parallelism": f"dp{world}", "dispatch": "cuda_graph" if graphed is not None else "eager", "l2": "inputs (205 MB/step) and activations (>10 GB/step) exceed the 126 MB L2",
                        "precision": "bf16 tcgen05 operands, fp32 accumulate/LN/softmax/residual stream, fp32 master weights"},
-            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": 4},
+            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": 4,
+                    "input_pipeline": "pinned host -> staging buffer on a copy stream (overlaps the previous step) -> device-to-device into the static input"},
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}))
     sys.stdout.flush()
     if world > 1:
