@@ -21,6 +21,7 @@ constexpr int kMaxStages = 8;
 struct GemmTcParams {
   int block_n;            // MMA N (multiple of 32, <= 256)
   int n_tiles, m_tiles, splits, kb_total, kb_per_split;
+  int K;                  // reduction length: the last k-block may hold fewer than TBK valid columns (e.g. K = 96)
   int stages;
   uint32_t a_bytes, b_bytes;   // TMA bytes per stage (expect_tx)
   uint32_t epi_bytes_per_warp; // epilogue staging per warp in dynamic smem (4 KB; 8 KB for fp32 class-2 double buffers)
@@ -218,8 +219,11 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t sa = smem0 + s * stage_bytes, sb = sa + p.a_bytes;
+          // only the 16-wide k-steps that hold data: TMA zero-fills the rest of a partial last block (K = 96 -> 64 + 32)
+          const int ksteps = min(TBK / 16, (p.K - kb * TBK + 15) / 16);
 #pragma unroll
           for (int k = 0; k < TBK / 16; ++k) {
+            if (k >= ksteps) break;
             const uint64_t ad = A_MN ? umma_desc(sa + k * 2048, 8192, 1024, kSw128) : umma_desc(sa + k * 32, 16, 1024, kSw128);
             const uint64_t bd = B_MN ? umma_desc(sb + k * 2048, 8192, 1024, kSw128) : umma_desc(sb + k * 32, 16, 1024, kSw128);
             umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
@@ -498,6 +502,7 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   p.m_tiles = ceil_div(a->M, TBM);
   p.n_tiles = a->N / p.block_n;
   p.kb_total = ceil_div(a->K, TBK);
+  p.K = a->K;
   p.splits = a->epilogue == SWIN_EPI_ATOMIC_ADD ? pick_splits(p.m_tiles * p.n_tiles, p.kb_total) : 1;
   p.colsum_a = nullptr;
   if (a->colsum_a != nullptr) {
