@@ -157,6 +157,16 @@ int swin_cast_bf16(const float* x, void* y, int64_t n, void* stream);
  * floats) in ONE launch.  src/dst_off/numel are HOST arrays, consumed before the call returns. */
 #define SWIN_GATHER_MAX 64
 int swin_grad_gather(const void* const* src, const int64_t* dst_off, const int64_t* numel, int n, float* bucket, void* stream);
+/* Fused multi-tensor AdamW step (row f3): torch.optim.AdamW arithmetic — p *= 1 - lr*wd; m = lerp(m, g, 1-b1);
+ * v = b2*v + (1-b2)*g*g; p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps) — for n <= SWIN_GATHER_MAX fp32 tensors
+ * in ONE launch; replaces the per-tensor optimizer.step() driven by mmdet/utils/optimizer.py:22-33 with the AdamW /
+ * paramwise weight-decay settings of configs/swin/mask_rcnn_swin_tiny_patch4_window7_mstrain_480-800_adamw_1x_coco.py:64-67.
+ * All table arguments are HOST arrays (consumed before the call returns) of device pointers / per-tensor values.
+ * w16 (array or NULL; entries may be NULL): bf16 shadow copy of the updated parameter written in the same pass.
+ * grad_scale multiplies every gradient first (1/world for SUM-reduced buckets, 1/loss_scale, ...). */
+int swin_adamw_step(void* const* param, const void* const* grad, void* const* exp_avg, void* const* exp_avg_sq, void* const* w16,
+                    const float* weight_decay, const int64_t* numel, int n, float lr, float beta1, float beta2, float eps,
+                    int step, float grad_scale, void* stream);
 
 /* ---------------------------------------------------------------- window attention core, REF:129-150
  * qkv (B_, N, 3C): columns [q|k|v] x [head] x [32].  bias (nH,N,N) fp32 (swin_rel_bias_expand).

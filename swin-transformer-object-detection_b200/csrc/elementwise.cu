@@ -2,6 +2,7 @@
 // the LayerNorm family (plain, fused with pad+roll+partition, fused with the PatchMerging gather),
 // casts, column sums and the relative-position-bias expand / reduce.
 // All accesses are 128-bit and coalesced per row; index arithmetic is done once per row.
+#include <math.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -833,6 +834,52 @@ __global__ void __launch_bounds__(256) grad_gather_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
+// fused multi-tensor AdamW (decoupled weight decay, bias-corrected moments: torch.optim.AdamW arithmetic), one launch for
+// up to SWIN_GATHER_MAX parameter tensors; optionally refreshes the bf16 shadow copy the GEMMs read, so the operand cast
+// of the next step costs nothing.  Same chunk table scheme as the gradient gather.
+// ------------------------------------------------------------------------------------------
+struct AdamWTable {
+  float* param[SWIN_GATHER_MAX];
+  const float* grad[SWIN_GATHER_MAX];
+  float* m[SWIN_GATHER_MAX];
+  float* v[SWIN_GATHER_MAX];
+  __nv_bfloat16* w16[SWIN_GATHER_MAX];
+  float decay[SWIN_GATHER_MAX];           // 1 - lr * weight_decay of the tensor
+  int chunk_end[SWIN_GATHER_MAX];
+  int numel[SWIN_GATHER_MAX];
+  int n;
+  float beta1, beta2, eps, step_size, inv_sqrt_bc2, grad_scale;
+};
+
+__global__ void __launch_bounds__(256) adamw_kernel(const __grid_constant__ AdamWTable t) {
+  const int total = t.chunk_end[t.n - 1];
+  for (int c = blockIdx.x; c < total; c += gridDim.x) {
+    int e = 0;
+    while (c >= t.chunk_end[e]) ++e;
+    const int first = e == 0 ? 0 : t.chunk_end[e - 1];
+    const long long base = (long long)(c - first) * kGatherChunk;
+    const int n = min(kGatherChunk, (int)(t.numel[e] - base));
+    float* __restrict__ pp = t.param[e] + base;
+    const float* __restrict__ gg = t.grad[e] + base;
+    float* __restrict__ mm = t.m[e] + base;
+    float* __restrict__ vv = t.v[e] + base;
+    __nv_bfloat16* __restrict__ ww = t.w16[e] ? t.w16[e] + base : nullptr;
+    const float decay = t.decay[e];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float g = gg[i] * t.grad_scale;
+      float pv = pp[i] * decay;
+      float m = mm[i], v = vv[i];
+      m = m + (g - m) * (1.0f - t.beta1);                  // exp_avg.lerp_(grad, 1 - beta1)
+      v = v * t.beta2 + (1.0f - t.beta2) * g * g;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+      const float denom = sqrtf(v) * t.inv_sqrt_bc2 + t.eps;
+      pv = pv - t.step_size * (m / denom);
+      pp[i] = pv; mm[i] = m; vv[i] = v;
+      if (ww) ww[i] = __float2bfloat16(pv);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // column sums (bias gradients): block = 256 threads = 8 row-lanes x 32 column-vectors(4 wide)
 // ------------------------------------------------------------------------------------------
 template <typename T>
@@ -996,6 +1043,37 @@ extern "C" int swin_grad_gather(const void* const* src, const int64_t* dst_off, 
   t.n = live;
   const int grid = chunks < kNumSMs * 8 ? chunks : kNumSMs * 8;
   grad_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, bucket);
+  SWIN_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int swin_adamw_step(void* const* param, const void* const* grad, void* const* exp_avg, void* const* exp_avg_sq,
+                               void* const* w16, const float* weight_decay, const int64_t* numel, int n, float lr, float beta1,
+                               float beta2, float eps, int step, float grad_scale, void* stream) {
+  SWIN_REQUIRE(n >= 0 && n <= SWIN_GATHER_MAX, "adamw: at most %d tensors per call (got %d)", SWIN_GATHER_MAX, n);
+  SWIN_REQUIRE(step >= 1 && lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "adamw: bad hyper-parameters");
+  if (n == 0) return 0;
+  SWIN_REQUIRE(param && grad && exp_avg && exp_avg_sq && weight_decay && numel, "adamw: null table");
+  AdamWTable t;
+  int chunks = 0, live = 0;
+  for (int e = 0; e < n; ++e) {
+    SWIN_REQUIRE(numel[e] >= 0 && numel[e] < (1ll << 31), "adamw: bad numel in entry %d", e);
+    if (numel[e] == 0) continue;
+    SWIN_REQUIRE(param[e] && grad[e] && exp_avg[e] && exp_avg_sq[e], "adamw: null tensor in entry %d", e);
+    chunks += (int)ceil_div64(numel[e], kGatherChunk);
+    t.param[live] = (float*)param[e]; t.grad[live] = (const float*)grad[e]; t.m[live] = (float*)exp_avg[e]; t.v[live] = (float*)exp_avg_sq[e];
+    t.w16[live] = w16 ? (__nv_bfloat16*)w16[e] : nullptr;
+    t.decay[live] = 1.0f - lr * weight_decay[e];
+    t.numel[live] = (int)numel[e]; t.chunk_end[live] = chunks;
+    ++live;
+  }
+  if (live == 0) return 0;
+  t.n = live;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  t.beta1 = beta1; t.beta2 = beta2; t.eps = eps; t.grad_scale = grad_scale;
+  t.step_size = (float)((double)lr / bc1);
+  t.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  const int grid = chunks < kNumSMs * 8 ? chunks : kNumSMs * 8;
+  adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t);
   SWIN_LAUNCH_CHECK();
   return 0;
 }

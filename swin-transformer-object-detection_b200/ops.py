@@ -342,6 +342,22 @@ def grad_gather(tensors, offsets, bucket: torch.Tensor) -> None:
             L.check(L.lib().swin_grad_gather(src, off, num, n, _p(bucket), _stream()), "grad_gather")
 
 
+def adamw_step(params, grads, exp_avgs, exp_avg_sqs, shadows, weight_decays, lr: float, beta1: float, beta2: float,
+               eps: float, step: int, grad_scale: float = 1.0) -> None:
+    """Fused AdamW over lists of fp32 CUDA tensors (``shadows[i]``: bf16 copy to refresh, or None), GATHER_MAX per launch."""
+    _chk(*params, *grads, *exp_avgs, *exp_avg_sqs, *[s for s in shadows if s is not None])
+    for i0 in range(0, len(params), L.GATHER_MAX):
+        sl = slice(i0, i0 + L.GATHER_MAX)
+        ps, gs, ms, vs, ws, wd = params[sl], grads[sl], exp_avgs[sl], exp_avg_sqs[sl], shadows[sl], weight_decays[sl]
+        n = len(ps)
+        arr = lambda ts: (C.c_void_p * n)(*[None if t is None else t.data_ptr() for t in ts])
+        _count()
+        with _timed("adamw_step", 0.0, 3.0 * _nb(*ps) + _nb(*gs) + 3.0 * _nb(*ps) + _nb(*[w for w in ws if w is not None])):
+            L.check(L.lib().swin_adamw_step(arr(ps), arr(gs), arr(ms), arr(vs), arr(ws), (C.c_float * n)(*wd),
+                                            (C.c_int64 * n)(*[t.numel() for t in ps]), n, lr, beta1, beta2, eps, step,
+                                            grad_scale, _stream()), "adamw_step")
+
+
 # ------------------------------------------------------------------ window attention core
 def window_attn_fwd(qkv: torch.Tensor, bias: torch.Tensor, mask: Optional[torch.Tensor], B_: int, nH: int, ws: int,
                     scale: float, mask_nz: Optional[torch.Tensor] = None, canon=(0, 0)):
