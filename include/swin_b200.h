@@ -163,10 +163,11 @@ int swin_grad_gather(const void* const* src, const int64_t* dst_off, const int64
  * paramwise weight-decay settings of configs/swin/mask_rcnn_swin_tiny_patch4_window7_mstrain_480-800_adamw_1x_coco.py:64-67.
  * All table arguments are HOST arrays (consumed before the call returns) of device pointers / per-tensor values.
  * w16 (array or NULL; entries may be NULL): bf16 shadow copy of the updated parameter written in the same pass.
+ * Hyper-parameters are doubles so that 1 - beta rounds to fp32 exactly as torch's Python-float scalars do.
  * grad_scale multiplies every gradient first (1/world for SUM-reduced buckets, 1/loss_scale, ...). */
 int swin_adamw_step(void* const* param, const void* const* grad, void* const* exp_avg, void* const* exp_avg_sq, void* const* w16,
-                    const float* weight_decay, const int64_t* numel, int n, float lr, float beta1, float beta2, float eps,
-                    int step, float grad_scale, void* stream);
+                    const float* weight_decay, const int64_t* numel, int n, double lr, double beta1, double beta2, double eps,
+                    int step, double grad_scale, void* stream);
 
 /* ---------------------------------------------------------------- window attention core, REF:129-150
  * qkv (B_, N, 3C): columns [q|k|v] x [head] x [32].  bias (nH,N,N) fp32 (swin_rel_bias_expand).

@@ -68,7 +68,7 @@ SYMBOLS = {
     "swin_scale_cast": (c_int, [vp, vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp]),
     "swin_cast_bf16": (c_int, [vp, vp, c_i64, vp]),
     "swin_grad_gather": (c_int, [vp, vp, vp, c_int, vp, vp]),
-    "swin_adamw_step": (c_int, [vp, vp, vp, vp, vp, vp, vp, c_int, c_f32, c_f32, c_f32, c_f32, c_int, c_f32, vp]),
+    "swin_adamw_step": (c_int, [vp, vp, vp, vp, vp, vp, vp, c_int, C.c_double, C.c_double, C.c_double, C.c_double, c_int, C.c_double, vp]),
     "swin_window_attn_fwd": (c_int, [C.POINTER(AttnArgs), vp]),
     "swin_window_attn_bwd": (c_int, [C.POINTER(AttnArgs), vp]),
 }

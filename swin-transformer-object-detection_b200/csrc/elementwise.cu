@@ -848,7 +848,7 @@ struct AdamWTable {
   int chunk_end[SWIN_GATHER_MAX];
   int numel[SWIN_GATHER_MAX];
   int n;
-  float beta1, beta2, eps, step_size, inv_sqrt_bc2, grad_scale;
+  float beta1, beta2, omb1, omb2, eps, step_size, inv_sqrt_bc2, grad_scale;   // omb = 1 - beta, rounded from double like torch's scalars
 };
 
 __global__ void __launch_bounds__(256) adamw_kernel(const __grid_constant__ AdamWTable t) {
@@ -869,8 +869,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(const __grid_constant__ Adam
       const float g = gg[i] * t.grad_scale;
       float pv = pp[i] * decay;
       float m = mm[i], v = vv[i];
-      m = m + (g - m) * (1.0f - t.beta1);                  // exp_avg.lerp_(grad, 1 - beta1)
-      v = v * t.beta2 + (1.0f - t.beta2) * g * g;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+      m = m + (g - m) * t.omb1;                  // exp_avg.lerp_(grad, 1 - beta1)
+      v = v * t.beta2 + t.omb2 * g * g;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
       const float denom = sqrtf(v) * t.inv_sqrt_bc2 + t.eps;
       pv = pv - t.step_size * (m / denom);
       pp[i] = pv; mm[i] = m; vv[i] = v;
@@ -1047,10 +1047,10 @@ extern "C" int swin_grad_gather(const void* const* src, const int64_t* dst_off, 
   return 0;
 }
 extern "C" int swin_adamw_step(void* const* param, const void* const* grad, void* const* exp_avg, void* const* exp_avg_sq,
-                               void* const* w16, const float* weight_decay, const int64_t* numel, int n, float lr, float beta1,
-                               float beta2, float eps, int step, float grad_scale, void* stream) {
+                               void* const* w16, const float* weight_decay, const int64_t* numel, int n, double lr, double beta1,
+                               double beta2, double eps, int step, double grad_scale, void* stream) {
   SWIN_REQUIRE(n >= 0 && n <= SWIN_GATHER_MAX, "adamw: at most %d tensors per call (got %d)", SWIN_GATHER_MAX, n);
-  SWIN_REQUIRE(step >= 1 && lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "adamw: bad hyper-parameters");
+  SWIN_REQUIRE(step >= 1 && lr >= 0.0 && beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0, "adamw: bad hyper-parameters");
   if (n == 0) return 0;
   SWIN_REQUIRE(param && grad && exp_avg && exp_avg_sq && weight_decay && numel, "adamw: null table");
   AdamWTable t;
@@ -1062,15 +1062,16 @@ extern "C" int swin_adamw_step(void* const* param, const void* const* grad, void
     chunks += (int)ceil_div64(numel[e], kGatherChunk);
     t.param[live] = (float*)param[e]; t.grad[live] = (const float*)grad[e]; t.m[live] = (float*)exp_avg[e]; t.v[live] = (float*)exp_avg_sq[e];
     t.w16[live] = w16 ? (__nv_bfloat16*)w16[e] : nullptr;
-    t.decay[live] = 1.0f - lr * weight_decay[e];
+    t.decay[live] = (float)(1.0 - lr * (double)weight_decay[e]);
     t.numel[live] = (int)numel[e]; t.chunk_end[live] = chunks;
     ++live;
   }
   if (live == 0) return 0;
   t.n = live;
-  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  t.beta1 = beta1; t.beta2 = beta2; t.eps = eps; t.grad_scale = grad_scale;
-  t.step_size = (float)((double)lr / bc1);
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  t.beta1 = (float)beta1; t.beta2 = (float)beta2; t.eps = (float)eps; t.grad_scale = (float)grad_scale;
+  t.omb1 = (float)(1.0 - beta1); t.omb2 = (float)(1.0 - beta2);
+  t.step_size = (float)(lr / bc1);
   t.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   const int grid = chunks < kNumSMs * 8 ? chunks : kNumSMs * 8;
   adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t);

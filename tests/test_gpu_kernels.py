@@ -377,6 +377,32 @@ def test_window_attention_closed_form_canonical_mask_equals_tensor_mask(H, W):
     assert torch.equal(d1, d2) and rel(b2, b1) < 1e-5
 
 
+@pytest.mark.parametrize("B_,nH,grid", [(16 * 1392, 3, (200, 334)), (16 * 1392 - 1, 3, None), (16 * 96, 12, (50, 84))])
+def test_window_attention_full_size_tcgen05_vs_fp32_kernels(B_, nH, grid):
+    """BASELINE full sizes (Swin-T stage 0 / stage 2 at B=16, 800x1333): the persistent tcgen05 kernels (every CTA walks
+    ~100 items; odd window count exercises the half-empty last tile) against the fp32 FFMA kernels on the same data."""
+    ops, L = _ops()
+    ws, N, C = 7, 49, nH * 32
+    g = torch.Generator(device=DEV).manual_seed(B_ + nH)
+    qkv = torch.randn(B_, N, 3 * C, generator=g, device=DEV)
+    bias = torch.randn(nH, N, N, generator=g, device=DEV) * 0.5
+    dout = torch.randn(B_, N, C, generator=g, device=DEV)
+    mask = nz = None
+    canon = (0, 0)
+    if grid is not None:
+        mask = ops.shift_mask(grid[0], grid[1], ws, 3, DEV)
+        nz = ops.mask_nonzero(mask)
+        canon = (-(-grid[0] // ws), -(-grid[1] // ws))
+    o32, l32 = ops.window_attn_fwd(qkv, bias, mask, B_, nH, ws, 32 ** -0.5, nz)
+    d32, b32 = ops.window_attn_bwd(qkv, o32, dout, l32, bias, mask, B_, nH, ws, 32 ** -0.5, nz)
+    q16, do16 = qkv.bfloat16(), dout.bfloat16()
+    o16, l16 = ops.window_attn_fwd(q16, bias, mask, B_, nH, ws, 32 ** -0.5, nz, canon)
+    assert rel(o16, o32) < 8e-3 and rel(l16, l32) < 2e-3
+    assert torch.isfinite(o16.float()).all()
+    d16, b16 = ops.window_attn_bwd(q16, o16, do16, l16, bias, mask, B_, nH, ws, 32 ** -0.5, nz, canon)
+    assert rel(d16, d32) < 1.5e-2 and rel(b16, b32) < 1.5e-2
+
+
 def test_window_attention_core_window12_fp32():
     """BASELINE config 5 also sweeps window 12: served by the fp32 kernels (forward and backward)."""
     ops, L = _ops()

@@ -17,6 +17,8 @@ for g in "$@"; do
     gemm16) run gemm16 300 tests/test_gpu_kernels.py -m gpu -k "gemm and bf16" ;;
     attn32) run attn32 300 tests/test_gpu_kernels.py -m gpu -k "window_attention_core and f32" ;;
     attn16) run attn16 300 tests/test_gpu_kernels.py -m gpu -k "window_attention_core and bf16" ;;
+    attnfull) run attnfull 300 tests/test_gpu_kernels.py -m gpu -k "full_size_tcgen05" ;;
+    optim) run optim 300 tests/test_optim.py -m gpu ;;
     model) run model 600 tests/test_gpu_model.py -m gpu ;;
     *) echo "unknown group $g" ;;
   esac
