@@ -326,8 +326,21 @@ def main():
         with open(args.breakdown, "w") as f:
             f.write(timer.table(K, peak, float(peaks.get("hbm_gbs", 6650.0))) + "\n")
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    # DRAM bytes of the GEMM class from the committed ncu launch list of this same command (tools/profile_step.sh), per launch
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("launches_per_step") and B == 16 and args.compute_dtype == "bf16":
+            traffic = tj["dram_bytes_per_step"] / tj["launches_per_step"]
+            traffic_src = "profiles/gemm_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over the 155 GEMM launches of one step)"
+    except Exception:
+        pass
+    _, _, _, gemm_bytes = timer.summary("gemm_tc")
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all epilogues)", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_kind + " (sustained: timed inside a long step)",
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": gemm_bytes / max(n_launch, 1),
+                "peak_source": peak_kind + " (sustained: timed inside a long step)",
                 "launches_per_step": n_launch // max(K, 1), "ms_per_step_in_kernel": gemm_ms / max(K, 1),
                 "whole_step_frac_of_tensor_roofline": (GFLOP_PER_IMG * 1e9 * B / (ms_step / 1e3)) / (peak * 1e12)}
 
