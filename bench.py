@@ -340,6 +340,9 @@ def main():
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all epilogues)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": gemm_bytes / max(n_launch, 1),
+                # the class is HBM-bound in stages 0-1 and tensor-bound in stages 2-3: its DRAM rate beside the tensor rate
+                "dram_gbs": (traffic * n_launch / (gemm_ms / 1e3) / 1e9) if (traffic and gemm_ms > 0) else None,
+                "dram_frac_of_hbm_peak": (traffic * n_launch / (gemm_ms / 1e3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0))) if (traffic and gemm_ms > 0) else None,
                 "peak_source": peak_kind + " (sustained: timed inside a long step)",
                 "launches_per_step": n_launch // max(K, 1), "ms_per_step_in_kernel": gemm_ms / max(K, 1),
                 "whole_step_frac_of_tensor_roofline": (GFLOP_PER_IMG * 1e9 * B / (ms_step / 1e3)) / (peak * 1e12)}

@@ -98,9 +98,12 @@ class SwinBlockFn(torch.autograd.Function):
         Tp = xw.shape[0] * N
         dx2 = _f32c(dx2)
         # ---- MLP branch
-        dy2, dfc2b = ops.scale_cast(dx2, s2, 0, B, H, W, Cc, 1, 0, dt, want_colsum=True)  # (T, C) + bias grad in one pass
-        dfc2w, dfc1w, dprojw, dqkvw, dfc1b, dqkvb_buf = _zeros_flat(
-            dx2.device, tuple(fc2w.shape), tuple(fc1w.shape), tuple(projw.shape), tuple(qkvw.shape), (hid,), (3 * Cc,))
+        # every accumulator of this block's backward (weight / bias / LayerNorm / bias-table gradients) comes out of ONE
+        # zero-filled allocation: one memset per block instead of seven
+        dfc2w, dfc1w, dprojw, dqkvw, dfc1b, dqkvb_buf, dfc2b_buf, dgb2, dgb1, dbias_buf, dtable_buf = _zeros_flat(
+            dx2.device, tuple(fc2w.shape), tuple(fc1w.shape), tuple(projw.shape), tuple(qkvw.shape), (hid,), (3 * Cc,),
+            (Cc,), (3, Cc), (3, Cc), (nH, N, N), tuple(table.shape))
+        dy2, dfc2b = ops.scale_cast(dx2, s2, 0, B, H, W, Cc, 1, 0, dt, want_colsum=True, colsum_out=dfc2b_buf)  # (T, C) + bias grad
         ops.gemm(dy2, h, Cc, hid, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc2w)
         du = ops.gemm(dy2, _w(fc2w, dt), T, hid, Cc, b_trans=True, epilogue=L.EPI_DGELU, aux=u)
         ops.gemm(du, xn, hid, Cc, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc1w, colsum_a=dfc1b)
@@ -108,16 +111,17 @@ class SwinBlockFn(torch.autograd.Function):
         # LN2 backward + residual-gradient add; the same kernel also emits dY of the proj Linear (drop-path scaled,
         # cast and partitioned into window slots) and its column sums (= d proj.bias)
         dx1, dn2w, dn2b, dy1, dprojb = ops.ln_bwd(0, dxn, x1, n2w.detach(), mean2, rstd2, dx2, B, H, W, Cc, 1, 0,
-                                                  emit_windows=(ws, shift, s1))
+                                                  emit_windows=(ws, shift, s1), dgb=dgb2)
         # ---- attention branch
         ops.gemm(dy1, o, Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dprojw)
         do = ops.gemm(dy1, _w(projw, dt), Tp, Cc, Cc, b_trans=True)
-        dqkv, dbias = ops.window_attn_bwd(qkv.view(-1, N, 3 * Cc), o, do.view(-1, N, Cc), lse, bias, mask, Tp // N, nH, ws, scale, mask_nz, canon)
-        dtable = ops.rel_bias_reduce(dbias, ws)
+        dqkv, dbias = ops.window_attn_bwd(qkv.view(-1, N, 3 * Cc), o, do.view(-1, N, Cc), lse, bias, mask, Tp // N, nH, ws, scale, mask_nz, canon,
+                                          dbias=dbias_buf)
+        dtable = ops.rel_bias_reduce(dbias, ws, out=dtable_buf)
         dqkvb = dqkvb_buf if has_qkvb else None
         ops.gemm(dqkv, xw, 3 * Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dqkvw, colsum_a=dqkvb)
         dxw = ops.gemm(dqkv.view(Tp, 3 * Cc), _w(qkvw, dt), Tp, Cc, 3 * Cc, b_trans=True)
-        dx, dn1w, dn1b = ops.ln_bwd(1, dxw, x, n1w.detach(), mean1, rstd1, dx1, B, H, W, Cc, ws, shift)
+        dx, dn1w, dn1b = ops.ln_bwd(1, dxw, x, n1w.detach(), mean1, rstd1, dx1, B, H, W, Cc, ws, shift, dgb=dgb1)
         return (dx, dn1w, dn1b, dtable, dqkvw, dqkvb, dprojw, dprojb, dn2w, dn2b, dfc1w, dfc1b, dfc2w, dfc2b,
                 None, None, None, None, None, None, None, None, None, None, None, None, None)
 

@@ -153,10 +153,12 @@ def rel_bias_expand(table: torch.Tensor, ws: int) -> torch.Tensor:
     return out
 
 
-def rel_bias_reduce(dbias: torch.Tensor, ws: int) -> torch.Tensor:
-    _chk(dbias)
+def rel_bias_reduce(dbias: torch.Tensor, ws: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out``: optional pre-zeroed ((2ws-1)^2, nH) fp32 buffer (the kernel accumulates into it)."""
+    _chk(dbias, out)
     nH = dbias.shape[0]
-    out = torch.zeros(((2 * ws - 1) ** 2, nH), dtype=torch.float32, device=dbias.device)
+    if out is None:
+        out = torch.zeros(((2 * ws - 1) ** 2, nH), dtype=torch.float32, device=dbias.device)
     _count()
     L.check(L.lib().swin_rel_bias_reduce(_p(dbias), _p(out), nH, ws, _stream()), "rel_bias_reduce")
     return out
@@ -189,13 +191,16 @@ def ln_fwd(mode: int, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, 
 
 
 def ln_bwd(mode: int, dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor,
-           dres: Optional[torch.Tensor], B: int, H: int, W: int, Cc: int, ws: int, shift: int, emit_windows=None):
+           dres: Optional[torch.Tensor], B: int, H: int, W: int, Cc: int, ws: int, shift: int, emit_windows=None,
+           dgb: Optional[torch.Tensor] = None):
     """Returns (dx fp32 like x, dgamma, dbeta).  With ``emit_windows=(ws2, shift2, row_scale)`` (mode 0 only) it also
     returns (dy2, colsum2): row_scale[b]*dx cast to dy's dtype and gathered into window slots, plus its column sums."""
     _chk(dy, x, gamma, mean, rstd, dres)
     dx = torch.empty_like(x)
     width = Cc * (4 if mode == 2 else 1)
-    dgb = torch.zeros((3, width), dtype=torch.float32, device=x.device)
+    if dgb is None:                 # (3, width) pre-zeroed accumulators: dgamma, dbeta, column sums of the emitted dY
+        dgb = torch.zeros((3, width), dtype=torch.float32, device=x.device)
+    _chk(dgb)
     a = L.LnArgs(mode=mode, B=B, H=H, W=W, C=Cc, ws=ws, shift=shift, eps=0.0, y_dtype=_DT[dy.dtype], x=_p(x), gamma=_p(gamma),
                  mean=_p(mean), rstd=_p(rstd), dy=_p(dy), dres=_p(dres), dx=_p(dx), dgamma=_p(dgb[0]), dbeta=_p(dgb[1]))
     dy2 = None
@@ -300,7 +305,7 @@ def colsum(X: torch.Tensor) -> torch.Tensor:
 
 
 def scale_cast(x: torch.Tensor, row_scale: Optional[torch.Tensor], mode: int, B: int, H: int, W: int, Cc: int, ws: int,
-               shift: int, y_dtype: int, want_colsum: bool = False):
+               shift: int, y_dtype: int, want_colsum: bool = False, colsum_out: Optional[torch.Tensor] = None):
     """fp32 -> y_dtype cast with per-image scale (mode 1: gathered into window slots).  With want_colsum also returns the
     fp32 column sums of the result (the bias gradient), computed in the same pass."""
     _chk(x, row_scale)
@@ -311,7 +316,10 @@ def scale_cast(x: torch.Tensor, row_scale: Optional[torch.Tensor], mode: int, B:
     else:
         rows = B * H * W
     y = torch.empty((rows, Cc), dtype=torch_dtype(y_dtype), device=x.device)
-    cs = torch.zeros((Cc,), dtype=torch.float32, device=x.device) if want_colsum else None
+    cs = None
+    if want_colsum:               # colsum_out: optional pre-zeroed (C,) fp32 accumulator
+        cs = colsum_out if colsum_out is not None else torch.zeros((Cc,), dtype=torch.float32, device=x.device)
+        _chk(cs)
     _count()
     with _timed(f"scale_cast mode{mode} C={Cc}", 0.0, _nb(x, y)):
         L.check(L.lib().swin_scale_cast(_p(x), _p(y), _p(row_scale), mode, B, H, W, Cc, ws, shift, y_dtype, _p(cs), _stream()), "scale_cast")
@@ -375,11 +383,13 @@ def window_attn_fwd(qkv: torch.Tensor, bias: torch.Tensor, mask: Optional[torch.
 
 def window_attn_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, bias: torch.Tensor,
                     mask: Optional[torch.Tensor], B_: int, nH: int, ws: int, scale: float,
-                    mask_nz: Optional[torch.Tensor] = None, canon=(0, 0)):
-    _chk(qkv, out, dout, lse, bias, mask, mask_nz)
+                    mask_nz: Optional[torch.Tensor] = None, canon=(0, 0), dbias: Optional[torch.Tensor] = None):
+    """``dbias``: optional pre-zeroed (nH, N, N) fp32 accumulator."""
+    _chk(qkv, out, dout, lse, bias, mask, mask_nz, dbias)
     N = ws * ws
     dqkv = torch.empty_like(qkv)
-    dbias = torch.zeros((nH, N, N), dtype=torch.float32, device=qkv.device)
+    if dbias is None:
+        dbias = torch.zeros((nH, N, N), dtype=torch.float32, device=qkv.device)
     a = L.AttnArgs(dtype=_DT[qkv.dtype], B_=B_, nH=nH, ws=ws, nW=0 if mask is None else mask.shape[0], scale=scale,
                    qkv=_p(qkv), bias=_p(bias), mask=_p(mask), mask_nz=_p(mask_nz), canon_nwh=canon[0], canon_nww=canon[1], out=_p(out), lse=_p(lse), dout=_p(dout), dqkv=_p(dqkv),
                    dbias=_p(dbias))

@@ -97,10 +97,15 @@ class DropPath(nn.Module):
     def __init__(self, drop_prob: float = 0.0):
         super().__init__()
         self.drop_prob = float(drop_prob)
+        self._pending = []          # scales pre-drawn for this forward by SwinTransformer (one batched draw per step)
 
     def sample_scale(self, x: torch.Tensor) -> Optional[torch.Tensor]:
         if self.drop_prob == 0.0 or not self.training:
             return None
+        if self._pending:
+            s = self._pending.pop(0)
+            if s.shape[0] == x.shape[0] and s.device == x.device:
+                return s
         keep = 1.0 - self.drop_prob
         r = keep + torch.rand((x.shape[0],) + (1,) * (x.ndim - 1), dtype=torch.float32, device=x.device)
         return (r.floor_() / keep).reshape(-1).contiguous()
@@ -393,8 +398,32 @@ class SwinTransformer(nn.Module):
         else:
             raise TypeError("pretrained must be a str or None")
 
+    def _predraw_drop_path(self, B: int, device) -> None:
+        """All stochastic-depth multipliers of one forward from ONE uniform draw: (2 per block with rate > 0, B) values
+        floor(keep + U) / keep, handed to the blocks' DropPath modules in execution order (attention branch, then MLP).
+        Same distribution as the reference's per-call draws (REF:190,252-253) with 4 launches per step instead of ~90."""
+        mods = [blk.drop_path for layer in self.layers for blk in layer.blocks
+                if isinstance(blk.drop_path, DropPath) and blk.drop_path.drop_prob > 0.0 and blk.drop_path.training]
+        for m in mods:
+            m._pending = []
+        if not mods:
+            return
+        rates = tuple(m.drop_prob for m in mods)
+        cache = getattr(self, "_keep_cache", None)
+        if cache is None or cache[0] != (rates, str(device)):       # built once, outside any CUDA-graph capture
+            keep = torch.tensor([1.0 - p for p in rates for _ in range(2)], dtype=torch.float32, device=device)
+            self._keep_cache = ((rates, str(device)), keep)
+        keep = self._keep_cache[1]
+        r = torch.rand((2 * len(mods), B), dtype=torch.float32, device=device)
+        scales = ((r + keep[:, None]).floor_() / keep[:, None]).contiguous()
+        for i, m in enumerate(mods):
+            m._pending = [scales[2 * i], scales[2 * i + 1]]
+
     def forward(self, x):
         _need_cuda(x, "SwinTransformer")
+        if self.training and not any(layer.use_checkpoint for layer in self.layers):
+            # (activation checkpointing re-runs the blocks under the saved RNG state, which only per-call draws reproduce)
+            self._predraw_drop_path(x.shape[0], x.device)
         x, Wh, Ww = self.patch_embed.tokens(x)
         if self.ape:
             pos = F.interpolate(self.absolute_pos_embed, size=(Wh, Ww), mode="bicubic")
