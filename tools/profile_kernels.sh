@@ -26,7 +26,9 @@ cap gemm_dW_fc1_s2   gemm_tc 1 1 python tools/gemm_bench.py dW_fc1_s2 2
 cap gemm_square_8k   gemm_tc 1 1 python tools/gemm_bench.py square_8k 2
 cap attn_s0          attn_tc 2 2 python tools/attn_bench.py 2 1
 cap ln_fwd_gather_s0 ln_fwd_kernel 2 1 python tools/ln_bench.py ln_fwd_gather_s0_shift3 2
-cap ln_bwd_emit_s0   ln_bwd_kernel 1 1 python tools/ln_bench.py ln_bwd_plain_emit_s0 2
+cap ln_bwd_emit_s0   ln_bwd 1 1 python tools/ln_bench.py ln_bwd_plain_emit_s0 2
+cap ln_bwd_gather_s0 ln_bwd 1 1 python tools/ln_bench.py ln_bwd_gather_s0_shift3 2
+cap gemm_dgelu_s0    gemm_tc 1 1 python tools/gemm_bench.py dgelu_s0 2
 cap window_gather_s0 row_map_copy 1 1 python tools/ln_bench.py window_gather_s0 2
 cap ln_fwd_merge_s0  ln_fwd_kernel 4 1 python tools/ln_bench.py ln_fwd_merge_s0 2
 ls -la gpurun_out/${R}_*; du -sh gpurun_out
