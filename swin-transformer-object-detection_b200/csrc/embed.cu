@@ -104,13 +104,16 @@ __global__ void __launch_bounds__(256) ln_nchw_fwd_kernel(const float* __restric
 }
 
 template <int VPL, int G>
-__global__ void __launch_bounds__(256) ln_nchw_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x,
+__global__ void __launch_bounds__(256, (VPL <= 3 ? 3 : (VPL <= 6 ? 2 : 1))) ln_nchw_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x,
                                                           const float* __restrict__ gamma, const float* __restrict__ mean,
                                                           const float* __restrict__ rstd, float* __restrict__ dx,
                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int L, int C,
-                                                          int tiles_per_block) {
-  extern __shared__ float tile[];            // [C][33] + [2][C] partials
-  float* sred = tile + (size_t)C * 33;
+                                                          int tiles_per_block, int nbuf) {
+  // dout arrives channel-major (NCHW): a [C][32-token] tile is transposed through smem.  With nbuf == 2 the NEXT tile's
+  // dout AND x rows are fetched with cp.async while the current one is processed.
+  extern __shared__ __align__(16) float tile_all[];        // nbuf x ([C][33] dout tile + [32][C] x rows) + [2][C] partials
+  const size_t buf_floats = (size_t)C * 33 + (nbuf == 2 ? (size_t)kTokTile * C + 2 * kTokTile : 0) + 4;      // +4 keeps the x rows 16-byte aligned
+  float* sred = tile_all + (size_t)nbuf * buf_floats;
   constexpr int R = 32 / G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G, gi = lane / G;
   const int b = blockIdx.y;
@@ -120,22 +123,67 @@ __global__ void __launch_bounds__(256) ln_nchw_bwd_kernel(const float* __restric
   float4 ag[VPL], ab[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) { ag[k] = make_float4(0.f, 0.f, 0.f, 0.f); ab[k] = ag[k]; }
+  const size_t xoff = ((size_t)C * 33 + 3) & ~(size_t)3;
+  auto fetch_tile = [&](int tb, int buf) {
+    const int t0 = (blockIdx.x * tiles_per_block + tb) * kTokTile;
+    if (tb >= tiles_per_block || t0 >= L) return;
+    float* base = tile_all + (size_t)buf * buf_floats;
+    if (nbuf == 2) {
+      const int t = t0 + lane;
+      const uint32_t nbytes = t < L ? 4u : 0u;           // src-size 0: zero fill
+      const float* src = dout + (long long)b * C * L + (t < L ? t : 0);
+      for (int c = warp; c < C; c += 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(base + c * 33 + lane)),
+                     "l"(src + (long long)c * L), "r"(nbytes) : "memory");
+    } else {                                             // wide rows: single buffer, plain loads (no room for a second tile)
+      const int t = t0 + lane;
+      for (int c = warp; c < C; c += 8) base[c * 33 + lane] = (t < L) ? __ldg(dout + ((long long)b * C + c) * L + t) : 0.f;
+    }
+    if (nbuf == 2) {
+      // x rows of the tile: 32 tokens x C floats, contiguous in global memory (token-major)
+      const int nvec = kTokTile * vrow;
+      const int live = min(kTokTile, L - t0) * vrow;       // vectors of real tokens (the tile's rows are contiguous)
+      const long long row0 = (long long)b * L + t0;
+      for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        const uint32_t nbytes = v < live ? 16u : 0u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(base + xoff + (size_t)v * 4)),
+                     "l"(reinterpret_cast<const float4*>(x + row0 * C) + (v < live ? v : 0)), "r"(nbytes) : "memory");
+      }
+      // per-token statistics of the tile (mean | rstd), 2 x 32 floats after the x rows
+      if (threadIdx.x < 2 * kTokTile) {
+        const int tt = threadIdx.x & (kTokTile - 1);
+        const float* sp = (threadIdx.x < kTokTile ? mean : rstd) + row0 + (t0 + tt < L ? tt : 0);
+        const uint32_t nb = t0 + tt < L ? 4u : 0u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(base + xoff + (size_t)nvec * 4 + threadIdx.x)),
+                     "l"(sp), "r"(nb) : "memory");
+      }
+    }
+  };
+  if (nbuf == 2) fetch_tile(0, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int tb = 0; tb < tiles_per_block; ++tb) {
     const int t0 = (blockIdx.x * tiles_per_block + tb) * kTokTile;
     if (t0 >= L) break;
-    __syncthreads();
-    {
-      const int t = t0 + lane;
-      for (int c = warp; c < C; c += 8) tile[c * 33 + lane] = (t < L) ? __ldg(dout + ((long long)b * C + c) * L + t) : 0.f;
+    if (nbuf == 2) {
+      fetch_tile(tb + 1, (tb + 1) & 1);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      fetch_tile(tb, 0);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const float* tile = tile_all + (size_t)(nbuf == 2 ? (tb & 1) : 0) * buf_floats;
+    const float4* xs = reinterpret_cast<const float4*>(tile + xoff);
 #pragma unroll 1
     for (int tt = warp * R + gi; tt < kTokTile; tt += 8 * R) {
       const int t = t0 + tt;
       const bool act = t < L;
       const long long rowi = (long long)b * L + (act ? t : 0);
-      const float mu = mean[rowi], rs = rstd[rowi];
-      const float4* xrow = reinterpret_cast<const float4*>(x + rowi * C);
+      const float* stat = tile + xoff + (size_t)kTokTile * vrow * 4;
+      const float mu = nbuf == 2 ? stat[tt] : mean[rowi], rs = nbuf == 2 ? stat[kTokTile + tt] : rstd[rowi];
+      const float4* xrow = nbuf == 2 ? xs + (size_t)tt * vrow : reinterpret_cast<const float4*>(x + rowi * C);
       float4 xh[VPL], gd[VPL];
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -145,7 +193,7 @@ __global__ void __launch_bounds__(256) ln_nchw_bwd_kernel(const float* __restric
         if (act && v < vrow) {
           const int c = 4 * v;
           const float4 d = make_float4(tile[(c + 0) * 33 + tt], tile[(c + 1) * 33 + tt], tile[(c + 2) * 33 + tt], tile[(c + 3) * 33 + tt]);
-          const float4 xv = __ldg(xrow + v);
+          const float4 xv = nbuf == 2 ? xrow[v] : __ldg(xrow + v);
           const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + v);
           xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
           gd[k] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
@@ -164,7 +212,9 @@ __global__ void __launch_bounds__(256) ln_nchw_bwd_kernel(const float* __restric
                                                                     rs * (gd[k].z - m1 - xh[k].z * m2), rs * (gd[k].w - m1 - xh[k].w * m2));
       }
     }
+    __syncthreads();                          // every warp is done with this tile before its buffer is refilled
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
@@ -249,18 +299,32 @@ extern "C" int swin_ln_nchw_bwd(const float* dout, const float* x, const float* 
   SWIN_REQUIRE(B > 0 && L > 0 && C > 0 && C % 4 == 0 && C <= 1024, "ln_nchw: bad shape (C %% 4 == 0, C <= 1024)");
   SWIN_REQUIRE(dout && x && gamma && mean && rstd && dx && dgamma && dbeta, "ln_nchw_bwd: null pointer");
   SWIN_REQUIRE(aligned16(x) && aligned16(dx) && aligned16(gamma), "ln_nchw_bwd: alignment");
-  size_t smem = ((size_t)C * 33 + 2 * C) * sizeof(float);
+  const int nbuf = C <= 192 ? 2 : 1;
+  size_t smem = ((size_t)nbuf * ((size_t)C * 33 + (nbuf == 2 ? (size_t)kTokTile * C + 2 * kTokTile : 0) + 4) + 2 * C) * sizeof(float);
   int tiles = ceil_div(L, kTokTile);
-  int tpb = ceil_div(tiles * B, kNumSMs * 16);     // a few tiles per block so the dgamma/dbeta atomics amortise
-  if (tpb < 1) tpb = 1;
+  // tiles per block: ~8-24 so the dgamma/dbeta atomics amortise, chosen so that the grid fills the resident-block capacity
+  // (<= 3 blocks per SM by registers, fewer when the tile buffers are large) in whole waves — 5.05 waves ran as 6
+  int bps = (int)((227 * 1024) / (smem + 1024));
+  if (bps > 3) bps = 3;
+  if (bps < 1) bps = 1;
+  const int cap = kNumSMs * bps;
+  int tpb = 1;
+  double best = -1.0;
+  for (int cand = 1; cand <= 32; ++cand) {
+    const long long blocks = (long long)ceil_div(tiles, cand) * B;
+    double eff = (double)blocks / (double)(ceil_div64(blocks, cap) * cap);
+    if (cand >= 8) eff += 0.05;                     // prefer enough tiles per block to amortise the closing atomics
+    if (blocks < cap && cand > 1) break;            // small problem: keep every SM busy rather than batching tiles
+    if (eff > best + 1e-9) { best = eff; tpb = cand; }
+  }
   dim3 grid(ceil_div(tiles, tpb), B);
   int G, vpl;
   nchw_shape(C / 4, &G, &vpl);
 #define NCHW_BWD(V, GG)                                                                                                   \
   if (G == GG && vpl <= V) {                                                                                              \
     static bool attr = false;                                                                                             \
-    if (!attr) { cudaFuncSetAttribute(ln_nchw_bwd_kernel<V, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; } \
-    ln_nchw_bwd_kernel<V, GG><<<grid, 256, smem, (cudaStream_t)stream>>>(dout, x, gamma, mean, rstd, dx, dgamma, dbeta, L, C, tpb); \
+    if (!attr) { cudaFuncSetAttribute(ln_nchw_bwd_kernel<V, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024); attr = true; } \
+    ln_nchw_bwd_kernel<V, GG><<<grid, 256, smem, (cudaStream_t)stream>>>(dout, x, gamma, mean, rstd, dx, dgamma, dbeta, L, C, tpb, nbuf); \
     SWIN_LAUNCH_CHECK();                                                                                                  \
     return 0;                                                                                                             \
   }
