@@ -503,12 +503,17 @@ __global__ void __launch_bounds__(256) ln_bwd_pf_kernel(const YT* __restrict__ d
     for (int k = 0; k < VPL; ++k) {
       const int v = gl + G * k;
       const bool on = inr && v < vrow;
-      const long long xi = sk[k] >= 0 ? sk[k] : 0;
-      cp_async16(sb + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(x) + xi);
-      cp_async16(sb + VPL * 512 + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(rsrc) + xi);
-      const raw_t* dsrc = reinterpret_cast<const raw_t*>(dy) + (on ? (long long)(dyrow * vrow + v) : 0);
-      if (Stg::kRaw == 16) cp_async16(sb + VPL * 1024 + (k * 32 + lane) * 16, dsrc);
-      else cp_async8(sb + VPL * 1024 + (k * 32 + lane) * 8, dsrc);
+      // idle lanes / pad segments issue nothing (their slots are never read): a clamped address would make every such
+      // lane hit one L2 line, and cp.async.cg bypasses L1 (measured on a forward variant: 40 % slower)
+      if (sk[k] >= 0) {
+        cp_async16(sb + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(x) + sk[k]);
+        cp_async16(sb + VPL * 512 + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(rsrc) + sk[k]);
+      }
+      if (on) {
+        const raw_t* dsrc = reinterpret_cast<const raw_t*>(dy) + (long long)(dyrow * vrow + v);
+        if (Stg::kRaw == 16) cp_async16(sb + VPL * 1024 + (k * 32 + lane) * 16, dsrc);
+        else cp_async8(sb + VPL * 1024 + (k * 32 + lane) * 8, dsrc);
+      }
     }
     *mu_o = inr ? __ldg(mean + row) : 0.f;
     *rs_o = inr ? __ldg(rstd + row) : 0.f;
