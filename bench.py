@@ -148,7 +148,7 @@ def oracle_step_fn(batch: int):
     return step
 
 
-def run_reference(args):
+def run_reference(args, emit=print):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -163,7 +163,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     v = 1.0 / dt
     sample = f"1 image 3x{IMG_HW[0]}x{IMG_HW[1]} fwd+bwd per step, fp32, {args.steps} steps"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "note": "CPU arm: bounded sample of the same workload"},
@@ -187,8 +187,21 @@ def main():
                     help="profiling aid: warm up, then run exactly ONE step between cudaProfilerStart/Stop and exit "
                          "(use with ncu --profile-from-start off); prints no benchmark line")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version banner there) are sent to
+    # stderr for the duration of the run, and the real stdout is restored for the final print
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: str) -> None:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(line)
+        sys.stdout.flush()
+        os.dup2(2, 1)
+
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch.distributed as dist
     import swin_b200
@@ -362,7 +375,7 @@ def main():
 
     if rank == 0:
         img_bytes = B * 3 * IMG_HW[0] * IMG_HW[1] * 4
-        print(json.dumps({
+        emit(json.dumps({
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.compute_dtype == "bf16" else "f32",
             "data": "synthetic",
