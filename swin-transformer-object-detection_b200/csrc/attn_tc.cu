@@ -9,7 +9,8 @@
 //          (N = (w', d)); row (w,i) keeps columns w'=w.
 // Q/K/V tiles arrive by TMA boxes of exactly 49 rows x 32 columns (64-byte swizzle) so the bytes
 // moved are the algorithmic ones; pad rows of the tiles are zeroed once and never written.
-// Tiles are double-buffered: the loads of item i+1 are in flight while item i computes.
+// Forward: 128-thread CTAs (thread = row), four per SM, single-buffered tiles refilled as soon as the MMA that read
+// them has completed.  Backward: 256-thread CTAs (two threads per row), two per SM, double-buffered tiles.
 // Backward recomputes S, forms dP = dO V^T, D = rowsum(P*dP), dS = P*(dP - D), and runs
 //     dV = P^T [dO_0|dO_1],  dK = dS^T [Q_0|Q_1],  dQ = dS [K_0|K_1]
 // with MN-major ("transposed") smem descriptors over the same compact P / dS tiles.
@@ -62,7 +63,7 @@ __device__ __forceinline__ unsigned long long canon_mask_bits(int wi, int nwh, i
   return m;
 }
 
-// Thread mapping shared by both kernels: 256 threads = 8 warps.  Warp w owns TMEM lane quarter q = w & 3 (rows
+// Thread mapping of the backward kernel: 256 threads = 8 warps.  Warp w owns TMEM lane quarter q = w & 3 (rows
 // q*32..q*32+31 of the stacked tile) and column half hf = w >> 2 of the row's own 64-column window block, so two
 // threads cooperate on one row (row statistics are exchanged through smem).  This doubles the warps available to
 // hide the LDS / TMEM / MUFU latencies of the per-row softmax math.
