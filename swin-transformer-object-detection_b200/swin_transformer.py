@@ -419,7 +419,9 @@ class SwinTransformer(nn.Module):
         for i, m in enumerate(mods):
             m._pending = [scales[2 * i], scales[2 * i + 1]]
 
-    def forward(self, x):
+    def forward_tokens(self, x):
+        """The block stack without the output norms: [(stage index, tokens (B, H*W, C) fp32, H, W)] for ``out_indices``
+        (REF:600-617).  ``forward`` applies norm{i} + NCHW on top; ``swin_b200.fpn`` feeds FPN laterals from it directly."""
         _need_cuda(x, "SwinTransformer")
         if self.training and not any(layer.use_checkpoint for layer in self.layers):
             # (activation checkpointing re-runs the blocks under the saved RNG state, which only per-call draws reproduce)
@@ -433,8 +435,14 @@ class SwinTransformer(nn.Module):
         for i, layer in enumerate(self.layers):
             x_out, H, W, x, Wh, Ww = layer(x, Wh, Ww)
             if i in self.out_indices:
-                n = getattr(self, f"norm{i}")
-                outs.append(OutNormFn.apply(x_out, n.weight, n.bias, H, W, float(n.eps)))
+                outs.append((i, x_out, H, W))
+        return outs
+
+    def forward(self, x):
+        outs = []
+        for i, x_out, H, W in self.forward_tokens(x):
+            n = getattr(self, f"norm{i}")
+            outs.append(OutNormFn.apply(x_out, n.weight, n.bias, H, W, float(n.eps)))
         return tuple(outs)
 
     def train(self, mode=True):

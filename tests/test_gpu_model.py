@@ -241,3 +241,40 @@ def test_untagged_canonical_mask_is_detected_and_matches():
     odd[0, 0, 1] = -100.0
     assert _canonical_grid(odd, ws, 3) == (0, 0)
     assert not torch.equal(blk(x, odd), y_tag)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_fused_fpn_laterals_match_outnorm_plus_conv1x1(mode):
+    """Row f2: norm{i} + FPN lateral 1x1 conv from the token-major stage outputs (no NCHW transpose) == the reference
+    composition lateral_conv(backbone(img)[i]) (swin_transformer.py:618-623 + necks/fpn.py:169-173), forward and backward."""
+    import swin_b200
+    from swin_b200.fpn import SwinFPNLaterals
+    torch.manual_seed(4)
+    torch.backends.cudnn.allow_tf32 = False            # the comparison convolution must be true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = swin_b200.SwinTransformer(drop_path_rate=0.0, compute_dtype=mode, **TINY).to(DEV).train()
+    chans = [TINY["embed_dim"] * 2 ** i for i in TINY["out_indices"]]
+    lats = torch.nn.ModuleList([torch.nn.Conv2d(c, 64, 1) for c in chans]).to(DEV)
+    img = torch.randn(2, 3, 50, 70, device=DEV)
+    cots = None
+    # reference composition: the backbone's standard NCHW outputs through torch's fp32 conv
+    outs_ref = [l(o) for l, o in zip(lats, net(img))]
+    cots = [torch.randn_like(o) for o in outs_ref]
+    sum((o * c).sum() for o, c in zip(outs_ref, cots)).backward()
+    names = ["patch_embed.proj.weight", "layers.0.blocks.0.attn.qkv.weight", "norm0.weight", "norm1.bias"]
+    params = dict(net.named_parameters())
+    g_ref = {n: params[n].grad.clone() for n in names}
+    gl_ref = [(l.weight.grad.clone(), l.bias.grad.clone()) for l in lats]
+    net.zero_grad(); lats.zero_grad()
+    fused = SwinFPNLaterals(net, lats)
+    outs = fused(img)
+    tol = 1e-4 if mode == "fp32" else 2e-2
+    for o, r in zip(outs, outs_ref):
+        assert o.shape == r.shape and o.is_contiguous(memory_format=torch.channels_last)
+        assert so.rel_l2(o, r) < tol
+    sum((o * c).sum() for o, c in zip(outs, cots)).backward()
+    for n in names:
+        assert so.rel_l2(params[n].grad, g_ref[n]) < tol, n
+    for l, (gw, gb) in zip(lats, gl_ref):
+        assert so.rel_l2(l.weight.grad, gw) < tol and so.rel_l2(l.bias.grad, gb) < tol
