@@ -5,6 +5,7 @@
 //                               tile's main loop through two TMEM accumulator stages.
 // Operands may be K-major or MN-major ("transposed") so forward (X W^T), dX (dY W) and the
 // split-K weight gradient (dY^T X) all run on the same kernel.
+#include <stdlib.h>
 #include "epilogue.cuh"
 #include "ptx.cuh"
 #include "tma_host.cuh"
@@ -28,6 +29,7 @@ struct GemmTcParams {
   float* colsum_a;             // split-K dW only: bias gradient via an all-ones N=16 MMA into TMEM columns [256,272)
   int tma_epi;                 // 1: STORE/GELU with bf16 outputs go out through TMA stores (tmD / tmD2)
   uint32_t stage_bytes;        // smem stride per stage: a_bytes + b_bytes rounded up to the 1024-byte swizzle-atom alignment
+  int ctas;                    // 1, or 2: CTA-pair tiles (cta_group::2, M = 256; b_bytes is this CTA's HALF of the B tile)
   EpiParams epi;
 };
 
@@ -42,7 +44,7 @@ struct WorkIter {
   int unit, total_units, stride, splits, kb_per_split, kb_total;
   __device__ __forceinline__ explicit WorkIter(const GemmTcParams& p) {
     kb_total = p.kb_total; splits = p.splits; kb_per_split = p.kb_per_split;
-    unit = blockIdx.x; stride = gridDim.x; total_units = p.m_tiles * p.n_tiles * p.splits;
+    unit = blockIdx.x / p.ctas; stride = gridDim.x / p.ctas; total_units = p.m_tiles * p.n_tiles * p.splits;   // m_tiles: tiles of 128 * ctas rows
     tile = kb0 = kb1 = 0;
   }
   __device__ __forceinline__ bool next() {
@@ -126,7 +128,14 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, const float4* __re
 
 // EPI_CLASS: 0 = generic coalesced-lane epilogue; 1 = bf16 STORE/GELU through TMA stores; 2 = DGELU (bf16) / RESIDUAL (fp32):
 //            the aux tile is TMA-loaded, updated in place in the TMEM row layout and TMA-stored.
-template <bool A_MN, bool B_MN, int EPI_CLASS>
+//
+// CTAS == 2: the two CTAs of a cluster (one TPC) work on ONE 256 x block_n tile with cta_group::2 MMAs.  Each CTA loads its
+// own 128 rows of A and HALF of the B tile (so a k-block costs 16 KB + block_n * 64 B of shared-memory fill per CTA instead
+// of 16 KB + block_n * 128 B, and the ring holds more k-blocks), keeps its 128 accumulator rows in its own TMEM and runs
+// the epilogue on them.  Protocol (the CUTLASS 2-SM one): every TMA of either CTA posts its bytes on the LEADER's full
+// barrier; the leader's MMA thread issues for both and its commits arrive on the empty / accumulator-full barriers of
+// BOTH CTAs (multicast); the epilogue warps of both CTAs arrive on the leader's accumulator-empty barrier.
+template <bool A_MN, bool B_MN, int EPI_CLASS, int CTAS>
 __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmD,
@@ -143,8 +152,10 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
   // 1024-byte aligned operand ring
   uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_bytes = p.stage_bytes;
-  const uint32_t tx_bytes = p.a_bytes + p.b_bytes;
+  const uint32_t tx_bytes = (p.a_bytes + p.b_bytes) * CTAS;      // the leader's full barrier collects both CTAs' loads
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  constexpr int TM = TBM * CTAS;                                // rows of a work tile
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto empty_bar = [&](int s) { return smem_u32(&bars[kMaxStages + s]); };
   auto tfull_bar = [&](int s) { return smem_u32(&bars[2 * kMaxStages + s]); };
@@ -156,20 +167,24 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 4; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEW); }
+    for (int s = 0; s < 4; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEW * CTAS); }
     for (int w = 0; w < kEpiWarps; ++w)
       for (int b = 0; b < 4; ++b) mbar_init(smem_u32(&aux_bars[w][b]), 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_slot), 512); tmem_relinquish(); }
+  if (CTAS == 2) cluster_sync_all();               // both CTAs' barriers exist before any remote arrive / TMEM pairing
+  if (warp == 1) {
+    if (CTAS == 2) { tmem_alloc_pair(smem_u32(&tmem_base_slot), 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(smem_u32(&tmem_base_slot), 512); tmem_relinquish(); }
+  }
   if (EPI_CLASS == 0 && A_MN && B_MN) {
     for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) ones_tile[i] = __float2bfloat16(1.0f);
     fence_proxy_async_smem();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
@@ -180,32 +195,55 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
       for (WorkIter w(p); w.next();) {
         const int tile = w.tile, kb0 = w.kb0, kb1 = w.kb1;
         const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
-        const int m0 = m_blk * TBM, n0 = n_blk * p.block_n;
+        // this CTA's rows of A and (CTA pair) its half of the B tile
+        const int m0 = m_blk * TM + (int)cta_rank * TBM, n0 = n_blk * p.block_n + (int)cta_rank * (p.block_n / 2) * (CTAS - 1);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), tx_bytes);
           const uint32_t sa = smem0 + s * stage_bytes, sb = sa + p.a_bytes;
-          if (!A_MN) {
-            tma_load_2d(sa, &tmA, full_bar(s), kb * TBK, m0);
+          if (CTAS == 1) {
+            mbar_expect_tx(full_bar(s), tx_bytes);
+            if (!A_MN) {
+              tma_load_2d(sa, &tmA, full_bar(s), kb * TBK, m0);
+            } else {
+              tma_load_2d(sa, &tmA, full_bar(s), m0, kb * TBK);
+              tma_load_2d(sa + 8192, &tmA, full_bar(s), m0 + 64, kb * TBK);
+            }
+            if (!B_MN) {
+              tma_load_2d(sb, &tmB, full_bar(s), kb * TBK, n0);
+            } else {
+              for (uint32_t b = 0; b * 8192 < p.b_bytes; ++b) tma_load_2d(sb + b * 8192, &tmB, full_bar(s), n0 + 64 * b, kb * TBK);
+            }
           } else {
-            tma_load_2d(sa, &tmA, full_bar(s), m0, kb * TBK);
-            tma_load_2d(sa + 8192, &tmA, full_bar(s), m0 + 64, kb * TBK);
-          }
-          if (!B_MN) {
-            tma_load_2d(sb, &tmB, full_bar(s), kb * TBK, n0);
-          } else {
-            for (uint32_t b = 0; b * 8192 < p.b_bytes; ++b) tma_load_2d(sb + b * 8192, &tmB, full_bar(s), n0 + 64 * b, kb * TBK);
+            if (cta_rank == 0) mbar_expect_tx(full_bar(s), tx_bytes);      // one arrival per phase: the leader's, expecting both CTAs' bytes
+            const uint32_t lbar = mapa_u32(full_bar(s), 0);                // the leader's full barrier
+            if (!A_MN) {
+              tma_load_2d_pair(sa, &tmA, lbar, kb * TBK, m0);
+            } else {
+              tma_load_2d_pair(sa, &tmA, lbar, m0, kb * TBK);
+              tma_load_2d_pair(sa + 8192, &tmA, lbar, m0 + 64, kb * TBK);
+            }
+            if (!B_MN) {
+              tma_load_2d_pair(sb, &tmB, lbar, kb * TBK, n0);
+            } else {
+              for (uint32_t b = 0; b * 8192 < p.b_bytes; ++b) tma_load_2d_pair(sb + b * 8192, &tmB, lbar, n0 + 64 * b, kb * TBK);
+            }
           }
         }
+      }
+      if (CTAS == 2) {
+        // producer tail: the leader's multicast commits arrive on THIS CTA's empty barriers; do not leave (and let the CTA
+        // retire) before the last arrival of every slot has landed
+        const uint32_t n_last = it < (uint32_t)p.stages ? it : (uint32_t)p.stages;
+        for (uint32_t j = it - n_last; j < it; ++j) mbar_wait(empty_bar(j % p.stages), (j / p.stages) & 1);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(p.block_n, A_MN, B_MN);
+    if (lane == 0 && cta_rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(p.block_n, A_MN, B_MN, TM);
       uint32_t it = 0, u = 0;
       for (WorkIter w(p); w.next(); ++u) {
         const int kb0 = w.kb0, kb1 = w.kb1;
@@ -226,14 +264,17 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
             if (k >= ksteps) break;
             const uint64_t ad = A_MN ? umma_desc(sa + k * 2048, 8192, 1024, kSw128) : umma_desc(sa + k * 32, 16, 1024, kSw128);
             const uint64_t bd = B_MN ? umma_desc(sb + k * 2048, 8192, 1024, kSw128) : umma_desc(sb + k * 32, 16, 1024, kSw128);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (do_colsum)      // sum_k A[m,k] * 1  -> 16 identical columns at [256,272)
-              umma_bf16(d_tmem + 256, ad, umma_desc(smem_u32(ones_tile) + k * 2048, 8192, 1024, kSw128), umma_idesc_bf16(16, A_MN, B_MN),
-                        (kb > kb0 || k > 0) ? 1u : 0u);
+            const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+            if (CTAS == 1) umma_bf16(d_tmem, ad, bd, idesc, accum); else umma_bf16_pair(d_tmem, ad, bd, idesc, accum);
+            if (do_colsum) {    // sum_k A[m,k] * 1  -> 16 identical columns per CTA at [256,272) (pair: N = 32, 16 from each CTA's ones tile)
+              const uint64_t od = umma_desc(smem_u32(ones_tile) + k * 2048, 8192, 1024, kSw128);
+              if (CTAS == 1) umma_bf16(d_tmem + 256, ad, od, umma_idesc_bf16(16, A_MN, B_MN), accum);
+              else umma_bf16_pair(d_tmem + 256, ad, od, umma_idesc_bf16(32, A_MN, B_MN, TM), accum);
+            }
           }
-          umma_commit(empty_bar(s));          // smem slot reusable once these MMAs retire
+          if (CTAS == 1) umma_commit(empty_bar(s)); else umma_commit_pair(empty_bar(s));          // smem slot reusable once these MMAs retire
         }
-        umma_commit(tfull_bar(acc));          // accumulator complete
+        if (CTAS == 1) umma_commit(tfull_bar(acc)); else umma_commit_pair(tfull_bar(acc));        // accumulator complete
       }
     }
     __syncwarp();
@@ -251,7 +292,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
     for (WorkIter w(p); w.next(); ++u) {
       const int tile = w.tile;
       const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
-      const int row_base = m_blk * TBM + q * 32;
+      const int row_base = m_blk * TM + (int)cta_rank * TBM + q * 32;
       const int n0 = n_blk * p.block_n;
       const uint32_t acc = u % num_acc, acc_ph = (u / num_acc) & 1;
       // the two warps of a lane quarter take alternate 32-column chunks; which of them starts at chunk 0 flips every
@@ -348,7 +389,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) { if (CTAS == 1) mbar_arrive(tempty_bar(acc)); else mbar_arrive_cluster(mapa_u32(tempty_bar(acc), 0)); }
         continue;
       }
       if (EPI_CLASS == 1) {
@@ -407,7 +448,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) { if (CTAS == 1) mbar_arrive(tempty_bar(acc)); else mbar_arrive_cluster(mapa_u32(tempty_bar(acc), 0)); }
         continue;
       }
       {
@@ -452,13 +493,16 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) { if (CTAS == 1) mbar_arrive(tempty_bar(acc)); else mbar_arrive_cluster(mapa_u32(tempty_bar(acc), 0)); }
     }
   }
   if (EPI_CLASS != 0 && warp >= 2 && lane == 0) tma_store_wait_all<0>();
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();      // pair: neither CTA retires while the other may still signal it
+  if (warp == 1) {
+    tc_fence_after();
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 static int pick_block_n(int N) {
@@ -468,18 +512,32 @@ static int pick_block_n(int N) {
   return 0;
 }
 
-// Split-K factor of the weight-gradient GEMM: tiles * splits should fill the SMs in whole rounds (one round if that wastes
+// CTA-pair mode (cta_group::2, 256-row tiles).  SWIN_GEMM_PAIR=0 disables it, 1 (default) applies the shape policy below,
+// 2 uses it wherever it is legal (tests).  The B half-tile of a CTA must be whole swizzle atoms: any multiple of 8 rows when
+// B is K-major, a multiple of 64 columns when it is MN-major.
+static int pair_mode() {
+  static const int v = [] { const char* e = getenv("SWIN_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  return v;
+}
+static int pick_pair_block_n(int N, bool b_mn) {
+  if (!b_mn) { const int bn = pick_block_n(N); return (bn > 0 && bn % 16 == 0) ? bn : 0; }
+  if (N % 256 == 0) return 256;
+  if (N % 128 == 0) return 128;
+  return 0;
+}
+
+// Split-K factor of the weight-gradient GEMM: tiles * splits should fill the SMs (or SM pairs) in whole rounds (one round if that wastes
 // < 10 % of the machine, else the better of one / two / three rounds), with at least 4 k-blocks per unit.
-static int pick_splits(int tiles, int kb_total) {
+static int pick_splits(int tiles, int kb_total, int slots) {
   int maxs = kb_total / 4;
   if (maxs < 1) maxs = 1;
   int best = 1; double best_eff = 0.0;
   for (int rounds = 1; rounds <= 3; ++rounds) {
-    int s = (rounds * kNumSMs) / tiles;
+    int s = (rounds * slots) / tiles;
     if (s < 1) s = 1;
     if (s > maxs) s = maxs;
     const int units = tiles * s;
-    const double eff = (double)units / (double)(ceil_div(units, kNumSMs) * kNumSMs);
+    const double eff = (double)units / (double)(ceil_div(units, slots) * slots);
     if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
     if (best_eff >= 0.9) break;
   }
@@ -499,11 +557,17 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   p.epi = ep;
   p.block_n = pick_block_n(a->N);
   SWIN_REQUIRE(p.block_n > 0, "gemm(bf16): unsupported N %d", a->N);
-  p.m_tiles = ceil_div(a->M, TBM);
+  p.ctas = 1;
+  {
+    const int mt = ceil_div(a->M, TBM), pbn = pick_pair_block_n(a->N, b_mn), mode = pair_mode();
+    // policy: an odd tile count wastes half a pair tile, acceptable from 8 tiles up
+    if (mode > 0 && pbn > 0 && mt >= 2 && (mode >= 2 || mt % 2 == 0 || mt >= 8)) { p.ctas = 2; p.block_n = pbn; }
+  }
+  p.m_tiles = ceil_div(a->M, TBM * p.ctas);
   p.n_tiles = a->N / p.block_n;
   p.kb_total = ceil_div(a->K, TBK);
   p.K = a->K;
-  p.splits = a->epilogue == SWIN_EPI_ATOMIC_ADD ? pick_splits(p.m_tiles * p.n_tiles, p.kb_total) : 1;
+  p.splits = a->epilogue == SWIN_EPI_ATOMIC_ADD ? pick_splits(p.m_tiles * p.n_tiles, p.kb_total, kNumSMs / p.ctas) : 1;
   p.colsum_a = nullptr;
   if (a->colsum_a != nullptr) {
     SWIN_REQUIRE(a->epilogue == SWIN_EPI_ATOMIC_ADD && a_mn && b_mn, "gemm: colsum_a needs ATOMIC_ADD with a_trans = b_trans = 1");
@@ -512,7 +576,8 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   p.kb_per_split = ceil_div(p.kb_total, p.splits);
   p.splits = ceil_div(p.kb_total, p.kb_per_split);
   p.a_bytes = TBM * TBK * 2;
-  const int bn_rows = b_mn ? ceil_div(p.block_n, 64) * 64 : p.block_n;
+  const int bn_cta = p.block_n / p.ctas;                       // B rows (columns of D) staged by one CTA
+  const int bn_rows = b_mn ? ceil_div(bn_cta, 64) * 64 : bn_cta;
   p.b_bytes = (uint32_t)bn_rows * TBK * 2;
   p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
   const uint32_t stage_bytes = p.stage_bytes;
@@ -525,7 +590,7 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   if (!a_mn) rc = make_tmap_bf16_2d(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, TBK, TBM, CU_TENSOR_MAP_SWIZZLE_128B);
   else       rc = make_tmap_bf16_2d(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda * 2, 64, TBK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  if (!b_mn) rc = make_tmap_bf16_2d(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb * 2, TBK, (uint32_t)p.block_n, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!b_mn) rc = make_tmap_bf16_2d(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb * 2, TBK, (uint32_t)bn_cta, CU_TENSOR_MAP_SWIZZLE_128B);
   else       rc = make_tmap_bf16_2d(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, 64, TBK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
 
@@ -565,27 +630,39 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   }
   const size_t smem = (size_t)p.stages * stage_bytes + epi_bytes + 1024;
   const int total_units = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = total_units < kNumSMs ? total_units : kNumSMs;
-#define LAUNCH_TC(AM, BM, TE)                                                                                     \
+  const int slots = kNumSMs / p.ctas;                          // CTAs, or CTA pairs (one per TPC)
+  const int grid = (total_units < slots ? total_units : slots) * p.ctas;
+#define LAUNCH_TC(AM, BM, TE, CT)                                                                                 \
   do {                                                                                                            \
     static bool attr_done = false;                                                                                \
     if (!attr_done) {                                                                                             \
-      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AM, BM, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AM, BM, TE, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            212 * 1024);                                                           \
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }      \
       attr_done = true;                                                                                           \
     }                                                                                                             \
-    gemm_tc_kernel<AM, BM, TE><<<grid, gemm_threads(TE), smem, st>>>(tmA, tmB, tmD, tmD2, p);                         \
+    cudaLaunchConfig_t cfg = {};                                                                                  \
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)gemm_threads(TE));                          \
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;                                                                 \
+    cudaLaunchAttribute lattr[1];                                                                                 \
+    lattr[0].id = cudaLaunchAttributeClusterDimension;                                                            \
+    lattr[0].val.clusterDim.x = CT; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = 1;                 \
+    cfg.attrs = lattr; cfg.numAttrs = CT > 1 ? 1 : 0;                                                             \
+    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<AM, BM, TE, CT>, tmA, tmB, tmD, tmD2, p);            \
+    if (le != cudaSuccess) { set_error("gemm_tc launch: %s", cudaGetErrorString(le)); return (int)le; }           \
   } while (0)
+#define LAUNCH_TC1(AM, BM, TE)                                                                                    \
+  do { if (p.ctas == 2) LAUNCH_TC(AM, BM, TE, 2); else LAUNCH_TC(AM, BM, TE, 1); } while (0)
 #define LAUNCH_TC2(AM, BM)                                                                                        \
   do {                                                                                                            \
-    if (p.tma_epi == 2) LAUNCH_TC(AM, BM, 2); else if (p.tma_epi == 1) LAUNCH_TC(AM, BM, 1); else LAUNCH_TC(AM, BM, 0); \
+    if (p.tma_epi == 2) LAUNCH_TC1(AM, BM, 2); else if (p.tma_epi == 1) LAUNCH_TC1(AM, BM, 1); else LAUNCH_TC1(AM, BM, 0); \
   } while (0)
   if (!a_mn && !b_mn) LAUNCH_TC2(false, false);
   else if (!a_mn && b_mn) LAUNCH_TC2(false, true);
   else if (a_mn && b_mn) LAUNCH_TC2(true, true);
   else LAUNCH_TC2(true, false);
 #undef LAUNCH_TC2
+#undef LAUNCH_TC1
 #undef LAUNCH_TC
   SWIN_LAUNCH_CHECK();
   return 0;
