@@ -12,6 +12,20 @@
 
 namespace swin {
 
+// Development builds (-DSWIN_GEMM_PROF, libswin_b200_prof.so): the roles of the first CTA (pair) accumulate the clocks they
+// spend blocked on each barrier, read back through swin_debug_gemm_prof().  Compiled out of the product library.
+#ifdef SWIN_GEMM_PROF
+__device__ unsigned long long g_gemm_prof[16];
+#define PROF_DECL unsigned long long prof_w0 = 0, prof_w1 = 0; const long long prof_t0 = clock64();
+#define PROF_WAIT(acc, stmt) do { const long long t__ = clock64(); stmt; acc += (unsigned long long)(clock64() - t__); } while (0)
+#define PROF_FLUSH(i0, i1, itot) do { if (blockIdx.x < CTAS) { atomicAdd(&g_gemm_prof[(i0)], prof_w0); atomicAdd(&g_gemm_prof[(i1)], prof_w1); \
+    atomicAdd(&g_gemm_prof[(itot)], (unsigned long long)(clock64() - prof_t0)); } } while (0)
+#else
+#define PROF_DECL
+#define PROF_WAIT(acc, stmt) stmt
+#define PROF_FLUSH(i0, i1, itot)
+#endif
+
 constexpr int TBM = 128, TBK = 64;
 constexpr int kEpiWarps = 8;                 // generic / class-2 epilogues: two warps per TMEM lane quarter
 constexpr int kEpiWarpsMax = 12;             // class 1 (STORE / GELU, ALU-heavy): three warps per lane quarter
@@ -49,10 +63,13 @@ struct WorkIter {
   }
   __device__ __forceinline__ bool next() {
     if (unit >= total_units) return false;
-    const int ks = unit % splits;
-    tile = unit / splits;
-    kb0 = ks * kb_per_split;
-    kb1 = min(kb_total, kb0 + kb_per_split);
+    if (splits == 1) { tile = unit; kb0 = 0; kb1 = kb_total; }
+    else {
+      const int ks = unit % splits;
+      tile = unit / splits;
+      kb0 = ks * kb_per_split;
+      kb1 = min(kb_total, kb0 + kb_per_split);
+    }
     unit += stride;
     return true;
   }
@@ -191,16 +208,16 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t it = 0, s = 0, ph = 0;
+      PROF_DECL
       for (WorkIter w(p); w.next();) {
         const int tile = w.tile, kb0 = w.kb0, kb1 = w.kb1;
         const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
         // this CTA's rows of A and (CTA pair) its half of the B tile
         const int m0 = m_blk * TM + (int)cta_rank * TBM, n0 = n_blk * p.block_n + (int)cta_rank * (p.block_n / 2) * (CTAS - 1);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
+          if (it != 0 && ++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+          PROF_WAIT(prof_w0, mbar_wait(empty_bar(s), ph ^ 1));
           const uint32_t sa = smem0 + s * stage_bytes, sb = sa + p.a_bytes;
           if (CTAS == 1) {
             mbar_expect_tx(full_bar(s), tx_bytes);
@@ -238,44 +255,66 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
         const uint32_t n_last = it < (uint32_t)p.stages ? it : (uint32_t)p.stages;
         for (uint32_t j = it - n_last; j < it; ++j) mbar_wait(empty_bar(j % p.stages), (j / p.stages) & 1);
       }
+      PROF_FLUSH(0 + 8 * cta_rank, 1 + 8 * cta_rank, 2 + 8 * cta_rank);       // [0] producer blocked on empty, [2] producer total
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0 && cta_rank == 0) {
+    // The whole warp walks the loop (every lane polls the barriers); ONE elected lane issues.  The issue path is the
+    // critical resource of this kernel (measured: the tensor pipe idles between MMAs whenever the issuing thread needs more
+    // cycles per tcgen05.mma than the MMA runs), so it is kept to two adds per instruction: the smem descriptors are a
+    // constant high word plus a low word that advances by a constant per stage and per 16-wide k-step, stage / phase /
+    // accumulator indices are carried incrementally (no runtime divisions), and elect.sync lets ptxas issue the
+    // single-thread instructions without its per-active-lane retry loop.
+    if (cta_rank == 0) {
       const uint32_t idesc = umma_idesc_bf16(p.block_n, A_MN, B_MN, TM);
-      uint32_t it = 0, u = 0;
-      for (WorkIter w(p); w.next(); ++u) {
+      const uint32_t idesc_ones = CTAS == 1 ? umma_idesc_bf16(16, A_MN, B_MN) : umma_idesc_bf16(32, A_MN, B_MN, TM);
+      // descriptor = hi:lo with hi = SBO 1024 | version 1 | 128B swizzle; lo = (addr >> 4) | LBO << 16 (16 B K-major, 8192 B MN-major)
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      constexpr uint32_t kStepA = A_MN ? (2048u >> 4) : (32u >> 4), kStepB = B_MN ? (2048u >> 4) : (32u >> 4);
+      const uint32_t a_lo0 = ((smem0 & 0x3FFFFu) >> 4) | ((A_MN ? (8192u >> 4) : 1u) << 16);
+      const uint32_t b_lo0 = (((smem0 + p.a_bytes) & 0x3FFFFu) >> 4) | ((B_MN ? (8192u >> 4) : 1u) << 16);
+      const uint32_t ones_lo = ((smem_u32(ones_tile) & 0x3FFFFu) >> 4) | ((8192u >> 4) << 16);
+      const uint32_t stage16 = stage_bytes >> 4;
+      const uint32_t last_ksteps = (uint32_t)(p.K - (p.kb_total - 1) * TBK + 15) / 16;     // 16-wide k-steps of the last (maybe partial) k-block
+      auto desc = [&](uint32_t lo) { return ((uint64_t)kDescHi << 32) | (uint64_t)lo; };
+      auto mma = [&](uint32_t d, uint32_t alo, uint32_t blo, uint32_t id, uint32_t accum) {
+        if (CTAS == 1) umma_bf16(d, desc(alo), desc(blo), id, accum); else umma_bf16_pair(d, desc(alo), desc(blo), id, accum);
+      };
+      uint32_t s = 0, ph = 0, acc = 0, acc_ph = 0;
+      PROF_DECL
+      for (WorkIter w(p); w.next();) {
         const int kb0 = w.kb0, kb1 = w.kb1;
-        const uint32_t acc = u % num_acc, acc_ph = (u / num_acc) & 1;
-        mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+        PROF_WAIT(prof_w0, mbar_wait(tempty_bar(acc), acc_ph ^ 1));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_stride;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(full_bar(s), ph);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          PROF_WAIT(prof_w1, mbar_wait(full_bar(s), ph));
           tc_fence_after();
-          const uint32_t sa = smem0 + s * stage_bytes, sb = sa + p.a_bytes;
-          // only the 16-wide k-steps that hold data: TMA zero-fills the rest of a partial last block (K = 96 -> 64 + 32)
-          const int ksteps = min(TBK / 16, (p.K - kb * TBK + 15) / 16);
+          if (elect_one()) {
+            const uint32_t a_lo = a_lo0 + s * stage16, b_lo = b_lo0 + s * stage16;
+            const uint32_t first = kb > kb0 ? 1u : 0u;
+            if (kb + 1 < p.kb_total || last_ksteps == TBK / 16) {
 #pragma unroll
-          for (int k = 0; k < TBK / 16; ++k) {
-            if (k >= ksteps) break;
-            const uint64_t ad = A_MN ? umma_desc(sa + k * 2048, 8192, 1024, kSw128) : umma_desc(sa + k * 32, 16, 1024, kSw128);
-            const uint64_t bd = B_MN ? umma_desc(sb + k * 2048, 8192, 1024, kSw128) : umma_desc(sb + k * 32, 16, 1024, kSw128);
-            const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
-            if (CTAS == 1) umma_bf16(d_tmem, ad, bd, idesc, accum); else umma_bf16_pair(d_tmem, ad, bd, idesc, accum);
-            if (do_colsum) {    // sum_k A[m,k] * 1  -> 16 identical columns per CTA at [256,272) (pair: N = 32, 16 from each CTA's ones tile)
-              const uint64_t od = umma_desc(smem_u32(ones_tile) + k * 2048, 8192, 1024, kSw128);
-              if (CTAS == 1) umma_bf16(d_tmem + 256, ad, od, umma_idesc_bf16(16, A_MN, B_MN), accum);
-              else umma_bf16_pair(d_tmem + 256, ad, od, umma_idesc_bf16(32, A_MN, B_MN, TM), accum);
+              for (uint32_t k = 0; k < TBK / 16; ++k) {
+                mma(d_tmem, a_lo + k * kStepA, b_lo + k * kStepB, idesc, k ? 1u : first);
+                if (do_colsum) mma(d_tmem + 256, a_lo + k * kStepA, ones_lo + k * (2048u >> 4), idesc_ones, k ? 1u : first);
+              }
+            } else {        // partial last k-block: only the k-steps that hold data (TMA zero-fills the rest; K = 96 -> 64 + 32)
+              for (uint32_t k = 0; k < last_ksteps; ++k) {
+                mma(d_tmem, a_lo + k * kStepA, b_lo + k * kStepB, idesc, k ? 1u : first);
+                if (do_colsum) mma(d_tmem + 256, a_lo + k * kStepA, ones_lo + k * (2048u >> 4), idesc_ones, k ? 1u : first);
+              }
             }
+            if (CTAS == 1) umma_commit(empty_bar(s)); else umma_commit_pair(empty_bar(s));          // smem slot reusable once these MMAs retire
+            if (kb + 1 == kb1) { if (CTAS == 1) umma_commit(tfull_bar(acc)); else umma_commit_pair(tfull_bar(acc)); }   // accumulator complete
           }
-          if (CTAS == 1) umma_commit(empty_bar(s)); else umma_commit_pair(empty_bar(s));          // smem slot reusable once these MMAs retire
+          __syncwarp();
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
         }
-        if (CTAS == 1) umma_commit(tfull_bar(acc)); else umma_commit_pair(tfull_bar(acc));        // accumulator complete
+        if (++acc == num_acc) { acc = 0; acc_ph ^= 1; }
       }
+      if (lane == 0) PROF_FLUSH(3, 4, 5);         // [3] MMA blocked on accumulator-empty, [4] on operand-full, [5] MMA warp total
     }
     __syncwarp();
   } else {
@@ -289,6 +328,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
     float4* stage = reinterpret_cast<float4*>(smem_raw + (smem0 - smem_u32(smem_raw)) + (uint32_t)p.stages * stage_bytes + (uint32_t)ew * p.epi_bytes_per_warp);
     uint32_t u = 0;
     uint32_t aux_n = 0;                       // class 2: aux tiles requested so far by this warp (buffer = n & 1)
+    PROF_DECL
     for (WorkIter w(p); w.next(); ++u) {
       const int tile = w.tile;
       const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
@@ -330,7 +370,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
         uint32_t cur = aux_n;
         int issued = 0;
         for (; issued < nch && issued < (int)nbuf - 1; ++issued) issue_aux(issued);
-        mbar_wait(tfull_bar(acc), acc_ph);
+        PROF_WAIT(prof_w0, mbar_wait(tfull_bar(acc), acc_ph));
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
         uint32_t v[32];
@@ -395,7 +435,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
       if (EPI_CLASS == 1) {
         // ---- STORE / GELU with bf16 outputs: math in the TMEM row layout, bf16 tile staged in the TMA 64B-swizzle
         //      layout, one TMA store per 32x32 chunk (no per-lane global stores, no address arithmetic)
-        mbar_wait(tfull_bar(acc), acc_ph);
+        PROF_WAIT(prof_w0, mbar_wait(tfull_bar(acc), acc_ph));
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
         const bool gelu = p.epi.epilogue == SWIN_EPI_GELU;
@@ -458,7 +498,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
         epi_rowscale[ew][lane] = scale;
       }
       __syncwarp();
-      mbar_wait(tfull_bar(acc), acc_ph);
+      PROF_WAIT(prof_w0, mbar_wait(tfull_bar(acc), acc_ph));
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
       const int piece = lane & 7, rsub = lane >> 3;
@@ -495,6 +535,9 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
       __syncwarp();
       if (lane == 0) { if (CTAS == 1) mbar_arrive(tempty_bar(acc)); else mbar_arrive_cluster(mapa_u32(tempty_bar(acc), 0)); }
     }
+#ifdef SWIN_GEMM_PROF
+    if (ew == 0 && lane == 0) PROF_FLUSH(6 + 8 * cta_rank, 7 + 8 * cta_rank, 15);      // [6] epilogue warp 0 blocked on accumulator-full
+#endif
   }
   if (EPI_CLASS != 0 && warp >= 2 && lane == 0) tma_store_wait_all<0>();
   tc_fence_before();
@@ -560,8 +603,12 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   p.ctas = 1;
   {
     const int mt = ceil_div(a->M, TBM), pbn = pick_pair_block_n(a->N, b_mn), mode = pair_mode();
-    // policy: an odd tile count wastes half a pair tile, acceptable from 8 tiles up
-    if (mode > 0 && pbn > 0 && mt >= 2 && (mode >= 2 || mt % 2 == 0 || mt >= 8)) { p.ctas = 2; p.block_n = pbn; }
+    // policy (measured, tools/pair_ab.sh): pair tiles win or tie everywhere except under the DGELU epilogue (its aux-tile ring
+    // couples the two CTAs' epilogues) and are neutral for the split-K weight gradient, which keeps its proven 1-CTA split;
+    // an odd tile count wastes half a pair tile, acceptable from 8 tiles up
+    const bool shape_ok = mt % 2 == 0 || mt >= 8;
+    const bool epi_ok = a->epilogue != SWIN_EPI_DGELU && a->epilogue != SWIN_EPI_ATOMIC_ADD;
+    if (mode > 0 && pbn > 0 && mt >= 2 && (mode >= 2 || (shape_ok && epi_ok))) { p.ctas = 2; p.block_n = pbn; }
   }
   p.m_tiles = ceil_div(a->M, TBM * p.ctas);
   p.n_tiles = a->N / p.block_n;
@@ -668,4 +715,14 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   return 0;
 }
 
+#ifdef SWIN_GEMM_PROF
+}  // namespace swin
+extern "C" int swin_debug_gemm_prof(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, swin::g_gemm_prof, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(swin::g_gemm_prof, z, sizeof(z)); }
+  return 0;
+}
+namespace swin {
+#endif
 }  // namespace swin
