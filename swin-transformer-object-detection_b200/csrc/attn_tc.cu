@@ -161,19 +161,29 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
 #pragma unroll
     for (int w = 0; w < 2; ++w) tma_load_2d(aV + w * 4096, &tmQKV, bar_v, 2 * p.C + h * AHD, (2 * pair + w) * AN);
   };
-  if (tid == 0 && g < p.npairs) { issue_qk(g); issue_v(g); }
+  // Single-thread work (TMA / MMA issue) sits on the item's serial chain: warp 0 enters converged and ONE elected lane issues
+  // (no per-active-lane retry loops in the SASS), with descriptors built as constant-hi : incremented-lo words.
+  constexpr uint32_t kHi64 = umma_desc_hi(512, (uint32_t)kSw64), kHi128 = umma_desc_hi(1024, (uint32_t)kSw128);
+  const uint32_t q_lo = umma_desc_lo(aQ, 16), k_lo = umma_desc_lo(aK, 16), p_lo = umma_desc_lo(aP, 16), v_lo = umma_desc_lo(aV, 4096);
+  if (warp == 0) {
+    if (elect_one() && g < p.npairs) { issue_qk(g); issue_v(g); }
+    __syncwarp();
+  }
 
   uint32_t it = 0;
   for (int pair = g; pair < p.npairs; pair += stride, ++it) {
     const uint32_t ph = it & 1;
     const bool has_next = pair + stride < p.npairs;
-    if (tid == 0) {                              // S = Q K^T as soon as Q, K have landed
-      mbar_wait(bar_qk, ph);
-      tc_fence_after();
+    if (warp == 0) {                             // S = Q K^T as soon as Q, K have landed
+      if (elect_one()) {
+        mbar_wait(bar_qk, ph);
+        tc_fence_after();
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
-        umma_bf16(tS, umma_desc(aQ + k * 32, 16, 512, kSw64), umma_desc(aK + k * 32, 16, 512, kSw64), idesc_s, k);
-      umma_commit(bar_s);
+        for (uint32_t k = 0; k < 2; ++k)
+          umma_bf16(tS, umma_desc_join(kHi64, q_lo + 2 * k), umma_desc_join(kHi64, k_lo + 2 * k), idesc_s, k);
+        umma_commit(bar_s);
+      }
+      __syncwarp();
     }
     const int win = 2 * pair + wloc;
     const bool valid = (i < AN) && (win < p.B_);
@@ -186,7 +196,10 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
     }
     mbar_wait(bar_s, ph);
     tc_fence_after();
-    if (tid == 0 && has_next) issue_qk(pair + stride);      // the Q, K tiles are free again
+    if (warp == 0) {                             // the Q, K tiles are free again
+      if (elect_one() && has_next) issue_qk(pair + stride);
+      __syncwarp();
+    }
     // Rows >= 49 of a window (and a whole missing window) run the same math on harmless finite values: their P rows only
     // feed O rows that are never stored.  Columns 49..51 carry kNegBig from the bias tile, so they become exact zeros.
     uint32_t v[52];
@@ -241,17 +254,23 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {                              // O = P [V0 | V1]
-      mbar_wait(bar_v, ph);
-      tc_fence_after();
+    if (warp == 0) {                             // O = P [V0 | V1]
+      if (elect_one()) {
+        mbar_wait(bar_v, ph);
+        tc_fence_after();
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        umma_bf16(tO, umma_desc(aP + kk * 32, 16, 1024, kSw128), umma_desc(aV + kk * 1024, 4096, 512, kSw64), idesc_o, kk);
-      umma_commit(bar_o);
+        for (uint32_t kk = 0; kk < 4; ++kk)
+          umma_bf16(tO, umma_desc_join(kHi128, p_lo + 2 * kk), umma_desc_join(kHi64, v_lo + 64 * kk), idesc_o, kk);
+        umma_commit(bar_o);
+      }
+      __syncwarp();
     }
     mbar_wait(bar_o, ph);
     tc_fence_after();
-    if (tid == 0 && has_next) issue_v(pair + stride);       // the V tile is free again
+    if (warp == 0) {                             // the V tile is free again
+      if (elect_one() && has_next) issue_v(pair + stride);
+      __syncwarp();
+    }
     uint32_t o[32];
     tmem_ld32(tO + lane_off + wloc * 32, o);
     tmem_ld_wait();
@@ -272,17 +291,23 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
+      if (elect_one()) {
 #pragma unroll
-      for (int w = 0; w < 2; ++w)
-        if (2 * pair + w < p.B_) tma_store_2d(&tmOut, aP + w * 4096, h * AHD, (2 * pair + w) * AN);
-      tma_store_commit();
-      // sP is rewritten with the next item's P only after every thread has passed bar_s of the next item, which this
-      // thread commits after this wait: the staged O tile has been read out by then
-      tma_store_wait_read<0>();
+        for (int w = 0; w < 2; ++w)
+          if (2 * pair + w < p.B_) tma_store_2d(&tmOut, aP + w * 4096, h * AHD, (2 * pair + w) * AN);
+        tma_store_commit();
+        // sP is rewritten with the next item's P only after every thread has passed bar_s of the next item, which this
+        // thread commits after this wait: the staged O tile has been read out by then
+        tma_store_wait_read<0>();
+      }
+      __syncwarp();
     }
   }
-  if (tid == 0) tma_store_wait_all<0>();
+  if (warp == 0) {
+    if (elect_one()) tma_store_wait_all<0>();
+    __syncwarp();
+  }
   __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_slot, 128); }
 }
@@ -345,7 +370,14 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
       tma_load_2d(base + 3 * kTileBytes + w * 4096, &tmDO, bar, h * AHD, row0);
     }
   };
-  if (tid == 0 && g < p.npairs) issue_loads(g, 0);
+  constexpr uint32_t kHi64 = umma_desc_hi(512, (uint32_t)kSw64), kHi128 = umma_desc_hi(1024, (uint32_t)kSw128);
+  const uint32_t p_lo_k = umma_desc_lo(aP, 16), ds_lo_k = umma_desc_lo(adS, 16);              // K-major views of P / dS
+  const uint32_t p_lo_mn = umma_desc_lo(aP, 8192), ds_lo_mn = umma_desc_lo(adS, 8192);          // MN-major (transposed) views
+  (void)p_lo_k;
+  if (warp == 0) {
+    if (elect_one() && g < p.npairs) issue_loads(g, 0);
+    __syncwarp();
+  }
 
   float db[32];
 #pragma unroll
@@ -357,17 +389,23 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
     const uint32_t ph = it & 1, buf = it & 1, lph = (it >> 1) & 1;
     const uint32_t aQ = aT + buf * kBwdTiles, aK = aQ + kTileBytes, aV = aK + kTileBytes, adO = aV + kTileBytes;
     TITEM
-    if (tid == 0) {
-      mbar_wait(bar_load0 + 8 * buf, lph);
-      tc_fence_after();
+    // operand tiles of this buffer as descriptor low words (K-major views: LBO 16; MN-major views of Q, K, dO: LBO 4096)
+    const uint32_t q_lo = umma_desc_lo(aQ, 16), k_lo = umma_desc_lo(aK, 16), v_lo = umma_desc_lo(aV, 16), do_lo = umma_desc_lo(adO, 16);
+    const uint32_t q_lo_mn = umma_desc_lo(aQ, 4096), k_lo_mn = umma_desc_lo(aK, 4096), do_lo_mn = umma_desc_lo(adO, 4096);
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_wait(bar_load0 + 8 * buf, lph);
+        tc_fence_after();
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
-        umma_bf16(tS, umma_desc(aQ + k * 32, 16, 512, kSw64), umma_desc(aK + k * 32, 16, 512, kSw64), idesc_s, k);
+        for (uint32_t k = 0; k < 2; ++k)
+          umma_bf16(tS, umma_desc_join(kHi64, q_lo + 2 * k), umma_desc_join(kHi64, k_lo + 2 * k), idesc_s, k);
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
-        umma_bf16(tdP, umma_desc(adO + k * 32, 16, 512, kSw64), umma_desc(aV + k * 32, 16, 512, kSw64), idesc_s, k);
-      umma_commit(bar_s);
-      if (pair + p.ctas_per_head < p.npairs) issue_loads(pair + p.ctas_per_head, buf ^ 1);   // after the MMAs are in flight
+        for (uint32_t k = 0; k < 2; ++k)
+          umma_bf16(tdP, umma_desc_join(kHi64, do_lo + 2 * k), umma_desc_join(kHi64, v_lo + 2 * k), idesc_s, k);
+        umma_commit(bar_s);
+        if (pair + p.ctas_per_head < p.npairs) issue_loads(pair + p.ctas_per_head, buf ^ 1);   // after the MMAs are in flight
+      }
+      __syncwarp();
     }
     const int win = 2 * pair + wloc;
     const bool valid = (i < AN) && (win < p.B_);
@@ -422,7 +460,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
     }
     sRed[hf][r] = delta;
     TMARK(2);
-    if (tid == 0) tma_store_wait_read<0>();      // previous item's dQ/dK/dV tiles (staged in sP/sdS) drained
+    if (warp == 0) {                             // previous item's dQ/dK/dV tiles (staged in sP/sdS) drained
+      if (elect_one()) tma_store_wait_read<0>();
+      __syncwarp();
+    }
     __syncthreads();
     TMARK(3);
     delta = sRed[0][r] + sRed[1][r];
@@ -443,18 +484,21 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
     tc_fence_before();
     __syncthreads();
     TMARK(5);
-    if (tid == 0) {
-      tc_fence_after();
+    if (warp == 0) {
+      if (elect_one()) {
+        tc_fence_after();
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)   // dV[(w,j), (w',d)] = sum_i P_w[i][j] dO_w'[i][d]
-        umma_bf16(tdV, umma_desc(aP + kk * 2048, 8192, 1024, kSw128), umma_desc(adO + kk * 1024, 4096, 512, kSw64), idesc_tt, kk);
+        for (uint32_t kk = 0; kk < 4; ++kk)   // dV[(w,j), (w',d)] = sum_i P_w[i][j] dO_w'[i][d]
+          umma_bf16(tdV, umma_desc_join(kHi128, p_lo_mn + 128 * kk), umma_desc_join(kHi64, do_lo_mn + 64 * kk), idesc_tt, kk);
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)   // dK = (scale dS)^T Q
-        umma_bf16(tdK, umma_desc(adS + kk * 2048, 8192, 1024, kSw128), umma_desc(aQ + kk * 1024, 4096, 512, kSw64), idesc_tt, kk);
+        for (uint32_t kk = 0; kk < 4; ++kk)   // dK = (scale dS)^T Q
+          umma_bf16(tdK, umma_desc_join(kHi128, ds_lo_mn + 128 * kk), umma_desc_join(kHi64, q_lo_mn + 64 * kk), idesc_tt, kk);
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)   // dQ = (scale dS) K
-        umma_bf16(tdQ, umma_desc(adS + kk * 32, 16, 1024, kSw128), umma_desc(aK + kk * 1024, 4096, 512, kSw64), idesc_nt, kk);
-      umma_commit(bar_o);
+        for (uint32_t kk = 0; kk < 4; ++kk)   // dQ = (scale dS) K
+          umma_bf16(tdQ, umma_desc_join(kHi128, ds_lo_k + 2 * kk), umma_desc_join(kHi64, k_lo_mn + 64 * kk), idesc_nt, kk);
+        umma_commit(bar_o);
+      }
+      __syncwarp();
     }
     mbar_wait(bar_o, ph);
     tc_fence_after();
@@ -478,19 +522,25 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
     tc_fence_before();
     __syncthreads();
     TMARK(8);
-    if (tid == 0) {
+    if (warp == 0) {
+      if (elect_one()) {
 #pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        if (2 * pair + w >= p.B_) continue;
+        for (int w = 0; w < 2; ++w) {
+          if (2 * pair + w >= p.B_) continue;
 #pragma unroll
-        for (int part = 0; part < 3; ++part)
-          tma_store_2d(&tmDQKV, aP + part * 8192 + w * 4096, part * p.C + h * AHD, (2 * pair + w) * AN);
+          for (int part = 0; part < 3; ++part)
+            tma_store_2d(&tmDQKV, aP + part * 8192 + w * 4096, part * p.C + h * AHD, (2 * pair + w) * AN);
+        }
+        tma_store_commit();
       }
-      tma_store_commit();
+      __syncwarp();
     }
   }
   TPRINT("attn_bwd");
-  if (tid == 0) tma_store_wait_all<0>();
+  if (warp == 0) {
+    if (elect_one()) tma_store_wait_all<0>();
+    __syncwarp();
+  }
   if (i < AN) {
     float* dst = p.dbias + ((size_t)h * AN + i) * AN + jbase;
 #pragma unroll

@@ -207,8 +207,11 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
+    // whole warp in the loop, one elected lane issues (no per-active-lane retry loops around the TMA instructions)
+    {
       uint32_t it = 0, s = 0, ph = 0;
+      const uint32_t lbar0 = CTAS == 2 ? mapa_u32(full_bar(0), 0) : full_bar(0);       // (leader's) full barrier of slot 0
+      const uint32_t b_chunks = p.b_bytes / 8192u;                                     // MN-major B: 64-column chunks per CTA
       PROF_DECL
       for (WorkIter w(p); w.next();) {
         const int tile = w.tile, kb0 = w.kb0, kb1 = w.kb1;
@@ -218,35 +221,40 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           if (it != 0 && ++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
           PROF_WAIT(prof_w0, mbar_wait(empty_bar(s), ph ^ 1));
-          const uint32_t sa = smem0 + s * stage_bytes, sb = sa + p.a_bytes;
-          if (CTAS == 1) {
-            mbar_expect_tx(full_bar(s), tx_bytes);
-            if (!A_MN) {
-              tma_load_2d(sa, &tmA, full_bar(s), kb * TBK, m0);
+          if (elect_one()) {
+            const uint32_t sa = smem0 + s * stage_bytes, sb = sa + p.a_bytes;
+            const int k0 = kb * TBK;
+            if (CTAS == 1) {
+              const uint32_t fb = lbar0 + 8 * s;
+              mbar_expect_tx(fb, tx_bytes);
+              if (!A_MN) {
+                tma_load_2d(sa, &tmA, fb, k0, m0);
+              } else {
+                tma_load_2d(sa, &tmA, fb, m0, k0);
+                tma_load_2d(sa + 8192, &tmA, fb, m0 + 64, k0);
+              }
+              if (!B_MN) {
+                tma_load_2d(sb, &tmB, fb, k0, n0);
+              } else {
+                for (uint32_t b = 0; b < b_chunks; ++b) tma_load_2d(sb + b * 8192, &tmB, fb, n0 + 64 * (int)b, k0);
+              }
             } else {
-              tma_load_2d(sa, &tmA, full_bar(s), m0, kb * TBK);
-              tma_load_2d(sa + 8192, &tmA, full_bar(s), m0 + 64, kb * TBK);
-            }
-            if (!B_MN) {
-              tma_load_2d(sb, &tmB, full_bar(s), kb * TBK, n0);
-            } else {
-              for (uint32_t b = 0; b * 8192 < p.b_bytes; ++b) tma_load_2d(sb + b * 8192, &tmB, full_bar(s), n0 + 64 * b, kb * TBK);
-            }
-          } else {
-            if (cta_rank == 0) mbar_expect_tx(full_bar(s), tx_bytes);      // one arrival per phase: the leader's, expecting both CTAs' bytes
-            const uint32_t lbar = mapa_u32(full_bar(s), 0);                // the leader's full barrier
-            if (!A_MN) {
-              tma_load_2d_pair(sa, &tmA, lbar, kb * TBK, m0);
-            } else {
-              tma_load_2d_pair(sa, &tmA, lbar, m0, kb * TBK);
-              tma_load_2d_pair(sa + 8192, &tmA, lbar, m0 + 64, kb * TBK);
-            }
-            if (!B_MN) {
-              tma_load_2d_pair(sb, &tmB, lbar, kb * TBK, n0);
-            } else {
-              for (uint32_t b = 0; b * 8192 < p.b_bytes; ++b) tma_load_2d_pair(sb + b * 8192, &tmB, lbar, n0 + 64 * b, kb * TBK);
+              if (cta_rank == 0) mbar_expect_tx(full_bar(s), tx_bytes);      // one arrival per phase: the leader's, expecting both CTAs' bytes
+              const uint32_t lbar = lbar0 + 8 * s;                           // the leader's full barrier
+              if (!A_MN) {
+                tma_load_2d_pair(sa, &tmA, lbar, k0, m0);
+              } else {
+                tma_load_2d_pair(sa, &tmA, lbar, m0, k0);
+                tma_load_2d_pair(sa + 8192, &tmA, lbar, m0 + 64, k0);
+              }
+              if (!B_MN) {
+                tma_load_2d_pair(sb, &tmB, lbar, k0, n0);
+              } else {
+                for (uint32_t b = 0; b < b_chunks; ++b) tma_load_2d_pair(sb + b * 8192, &tmB, lbar, n0 + 64 * (int)b, k0);
+              }
             }
           }
+          __syncwarp();
         }
       }
       if (CTAS == 2) {
@@ -255,7 +263,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
         const uint32_t n_last = it < (uint32_t)p.stages ? it : (uint32_t)p.stages;
         for (uint32_t j = it - n_last; j < it; ++j) mbar_wait(empty_bar(j % p.stages), (j / p.stages) & 1);
       }
-      PROF_FLUSH(0 + 8 * cta_rank, 1 + 8 * cta_rank, 2 + 8 * cta_rank);       // [0] producer blocked on empty, [2] producer total
+      if (lane == 0) PROF_FLUSH(0 + 8 * cta_rank, 1 + 8 * cta_rank, 2 + 8 * cta_rank);       // [0] producer blocked on empty, [2] producer total
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -285,6 +293,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
       PROF_DECL
       for (WorkIter w(p); w.next();) {
         const int kb0 = w.kb0, kb1 = w.kb1;
+        const bool colsum_unit = do_colsum && (w.tile % p.n_tiles) == 0;      // the epilogue takes the row sums from the n_blk == 0 units
         PROF_WAIT(prof_w0, mbar_wait(tempty_bar(acc), acc_ph ^ 1));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_stride;
@@ -298,12 +307,12 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
 #pragma unroll
               for (uint32_t k = 0; k < TBK / 16; ++k) {
                 mma(d_tmem, a_lo + k * kStepA, b_lo + k * kStepB, idesc, k ? 1u : first);
-                if (do_colsum) mma(d_tmem + 256, a_lo + k * kStepA, ones_lo + k * (2048u >> 4), idesc_ones, k ? 1u : first);
+                if (colsum_unit) mma(d_tmem + 256, a_lo + k * kStepA, ones_lo + k * (2048u >> 4), idesc_ones, k ? 1u : first);
               }
             } else {        // partial last k-block: only the k-steps that hold data (TMA zero-fills the rest; K = 96 -> 64 + 32)
               for (uint32_t k = 0; k < last_ksteps; ++k) {
                 mma(d_tmem, a_lo + k * kStepA, b_lo + k * kStepB, idesc, k ? 1u : first);
-                if (do_colsum) mma(d_tmem + 256, a_lo + k * kStepA, ones_lo + k * (2048u >> 4), idesc_ones, k ? 1u : first);
+                if (colsum_unit) mma(d_tmem + 256, a_lo + k * kStepA, ones_lo + k * (2048u >> 4), idesc_ones, k ? 1u : first);
               }
             }
             if (CTAS == 1) umma_commit(empty_bar(s)); else umma_commit_pair(empty_bar(s));          // smem slot reusable once these MMAs retire
@@ -603,11 +612,14 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   p.ctas = 1;
   {
     const int mt = ceil_div(a->M, TBM), pbn = pick_pair_block_n(a->N, b_mn), mode = pair_mode();
-    // policy (measured, tools/pair_ab.sh): pair tiles win or tie everywhere except under the DGELU epilogue (its aux-tile ring
-    // couples the two CTAs' epilogues) and are neutral for the split-K weight gradient, which keeps its proven 1-CTA split;
-    // an odd tile count wastes half a pair tile, acceptable from 8 tiles up
-    const bool shape_ok = mt % 2 == 0 || mt >= 8;
-    const bool epi_ok = a->epilogue != SWIN_EPI_DGELU && a->epilogue != SWIN_EPI_ATOMIC_ADD;
+    // policy (measured per shape, tools/pair_ab.sh -> profiles/r01/gemm_pair_ab.txt): pair tiles win or tie under every epilogue
+    // except DGELU (its aux-tile ring couples the two CTAs' epilogues).  An MN-major B needs half-tiles of whole 64-column
+    // atoms, so N = 384 would drop from 192- to 128-wide tiles: a wash for dX, kept on 1-CTA tiles.  The split-K weight
+    // gradient pairs up only for an even tile count (a half-empty pair is pure loss when every unit runs the whole K range).
+    // Elsewhere an odd tile count wastes half a pair tile once, acceptable from 8 tiles up.
+    const bool dw = a->epilogue == SWIN_EPI_ATOMIC_ADD;
+    const bool shape_ok = dw ? (mt % 2 == 0) : (mt % 2 == 0 || mt >= 8);
+    const bool epi_ok = a->epilogue != SWIN_EPI_DGELU && (dw || !b_mn || pbn >= p.block_n);
     if (mode > 0 && pbn > 0 && mt >= 2 && (mode >= 2 || (shape_ok && epi_ok))) { p.ctas = 2; p.block_n = pbn; }
   }
   p.m_tiles = ceil_div(a->M, TBM * p.ctas);

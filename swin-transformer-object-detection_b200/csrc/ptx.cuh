@@ -111,6 +111,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (swz << 61);
 }
+// The same descriptor as hi:lo words: hi is a compile-time constant per operand kind, lo = (addr >> 4) | LBO << 16 advances by
+// a constant per k-step, so an MMA issue loop costs one add per operand (see gemm_tc.cu: the issuing thread is the critical path).
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t swz) { return (sbo_bytes >> 4) | (1u << 14) | (swz << 29); }
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFF) >> 4) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint64_t umma_desc_join(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
 // Instruction descriptor for kind::f16, BF16 x BF16 -> F32, M=128.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n, bool a_mn, bool b_mn, int m = 128) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |

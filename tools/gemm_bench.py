@@ -58,6 +58,10 @@ run("fc1_store_s2", T2, 1536, 384)
 run("fc2_resid_s2", T2, 384, 1536, L.EPI_RESIDUAL)
 run("dgelu_s2", T2, 1536, 384, L.EPI_DGELU, b_trans=True)
 run("dW_fc2_s2", 384, 1536, T2, L.EPI_ATOMIC_ADD, a_trans=True, b_trans=True)
+run("dW_qkv_s2", 1152, 384, Tp2, L.EPI_ATOMIC_ADD, a_trans=True, b_trans=True)
+run("dx_fc1_s2", T2, 384, 1536, b_trans=True)
+run("dx_qkv_s2", Tp2, 384, 1152, b_trans=True)
+run("dx_proj_s2", Tp2, 384, 384, b_trans=True)
 run("square_8k", 8192, 8192, 8192)
 run("square_4k_f32out", 4096, 4096, 4096, out_f32=True)
 run("sq4k_tt", 4096, 4096, 4096, a_trans=True, b_trans=True)

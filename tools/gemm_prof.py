@@ -36,6 +36,8 @@ def run(name, M, N, K, epi=L.EPI_STORE, a_trans=False, b_trans=False):
         lib.swin_debug_gemm_prof(C.byref(buf), 1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        if epi == L.EPI_ATOMIC_ADD and a_trans and b_trans:
+            kw["colsum_a"] = torch.zeros(M, device=dev)
         ops.gemm(A, B, M, N, K, a_trans=a_trans, b_trans=b_trans, epilogue=epi, out=out, **kw)
         e1.record()
         torch.cuda.synchronize()
@@ -59,4 +61,8 @@ run("fc1_gelu_s2", T2, 1536, 384, L.EPI_GELU)
 run("fc2_resid_s2", T2, 384, 1536, L.EPI_RESIDUAL)
 run("dgelu_s2", T2, 1536, 384, L.EPI_DGELU, b_trans=True)
 run("dW_fc1_s2", 1536, 384, T2, L.EPI_ATOMIC_ADD, a_trans=True, b_trans=True)
+run("dW_fc2_s2", 384, 1536, T2, L.EPI_ATOMIC_ADD, a_trans=True, b_trans=True)
+run("dW_qkv_s2", 1152, 384, Tp2, L.EPI_ATOMIC_ADD, a_trans=True, b_trans=True)
+run("dx_fc1_s2", T2, 384, 1536, b_trans=True)
+run("dx_qkv_s2", Tp2, 384, 1152, b_trans=True)
 run("square_8k", 8192, 8192, 8192)
