@@ -244,3 +244,36 @@ class OutNormFn(torch.autograd.Function):
         x, nw, mean, rstd = ctx.saved_tensors
         dx, dg, db = ops.ln_nchw_bwd(_f32c(dout), x, nw.detach(), mean, rstd)
         return dx, dg, db, None, None, None
+
+
+class OutNormMergeFn(torch.autograd.Function):
+    """The two consumers of a stage output -- norm{i} + NCHW (REF:618-623) and the stage's PatchMerging (REF:258-298) -- as ONE
+    autograd node.  Separately they hand autograd two full-size dx tensors that it sums with an ATen add (3 passes over
+    (B, H*W, C) fp32); here the out-norm backward runs first and the PatchMerging LayerNorm backward takes its dx as the
+    residual gradient (``dres``) it already knows how to add, so x's gradient is written once."""
+
+    @staticmethod
+    def forward(ctx, x, onw, onb, mnw, mnb, redw, H, W, dt, eps_out, eps_merge):
+        B, Lx, Cc = x.shape
+        x = _f32c(x)
+        out, omean, orstd = ops.ln_nchw_fwd(x, onw.detach(), onb.detach(), H, W, eps_out)
+        g, mean, rstd = ops.ln_fwd(2, x, mnw.detach(), mnb.detach(), B, H, W, Cc, 1, 0, eps_merge, dt)
+        T2 = g.shape[0] * g.shape[1]
+        y = ops.gemm(g.view(T2, 4 * Cc), _w(redw, dt), T2, 2 * Cc, 4 * Cc, out_dtype=L.F32)
+        ctx.save_for_backward(x, onw, omean, orstd, mnw, redw, g, mean, rstd)
+        ctx.cfg = (B, H, W, Cc, dt, T2)
+        return out, y.view(B, g.shape[1], 2 * Cc)
+
+    @staticmethod
+    def backward(ctx, dout, dy):
+        x, onw, omean, orstd, mnw, redw, g, mean, rstd = ctx.saved_tensors
+        B, H, W, Cc, dt, T2 = ctx.cfg
+        dx_out, dog, dob = ops.ln_nchw_bwd(_f32c(dout), x, onw.detach(), omean, orstd)
+        dyf = _f32c(dy).view(T2, 2 * Cc)
+        dy1 = dyf if dt == L.F32 else ops.scale_cast(dyf, None, 0, 1, T2, 1, 2 * Cc, 1, 0, dt)
+        dredw = torch.zeros_like(redw, dtype=torch.float32)
+        ops.gemm(dy1, g.view(T2, 4 * Cc), 2 * Cc, 4 * Cc, T2, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dredw)
+        dg = ops.gemm(dy1, _w(redw, dt), T2, 4 * Cc, 2 * Cc, b_trans=True)
+        dx, dnw, dnb = ops.ln_bwd(2, dg, x, mnw.detach(), mean, rstd, dx_out, B, H, W, Cc, 1, 0)
+        return dx, dog, dob, dnw, dnb, dredw, None, None, None, None, None
+

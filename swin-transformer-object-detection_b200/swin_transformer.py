@@ -21,7 +21,7 @@ import torch.utils.checkpoint as cp
 
 from . import _lib as L
 from . import ops
-from .functional import OutNormFn, PatchEmbedFn, PatchMergingFn, SwinBlockFn, WindowAttentionFn
+from .functional import OutNormFn, OutNormMergeFn, PatchEmbedFn, PatchMergingFn, SwinBlockFn, WindowAttentionFn
 from .registry import register_backbone
 
 
@@ -287,15 +287,25 @@ class BasicLayer(nn.Module):
             self._mask_cache[key] = m
         return m
 
-    def forward(self, x, H, W):
+    def forward(self, x, H, W, out_norm=None):
+        """Reference signature ``forward(x, H, W) -> (x, H, W, x_down, Wh, Ww)`` (REF:362, :397-402).  With ``out_norm`` (the
+        backbone's norm{i} module; SwinTransformer.forward passes it) the first element is already norm{i}(x) in NCHW:
+        the output norm and the downsample then form one autograd node (functional.OutNormMergeFn)."""
         _need_cuda(x, "BasicLayer")
         mask = self.attn_mask(H, W, x.device)
         for blk in self.blocks:
             blk.H, blk.W = H, W
             x = cp.checkpoint(blk, x, mask, use_reentrant=False) if self.use_checkpoint else blk(x, mask)
         if self.downsample is not None:
+            if out_norm is not None:
+                ds = self.downsample
+                out, x_down = OutNormMergeFn.apply(x, out_norm.weight, out_norm.bias, ds.norm.weight, ds.norm.bias,
+                                                   ds.reduction.weight, H, W, ds._dt, float(out_norm.eps), float(ds.norm.eps))
+                return out, H, W, x_down, (H + 1) // 2, (W + 1) // 2
             x_down = self.downsample(x, H, W)
             return x, H, W, x_down, (H + 1) // 2, (W + 1) // 2
+        if out_norm is not None:
+            return OutNormFn.apply(x, out_norm.weight, out_norm.bias, H, W, float(out_norm.eps)), H, W, x, H, W
         return x, H, W, x, H, W
 
 
@@ -419,9 +429,11 @@ class SwinTransformer(nn.Module):
         for i, m in enumerate(mods):
             m._pending = [scales[2 * i], scales[2 * i + 1]]
 
-    def forward_tokens(self, x):
+    def forward_tokens(self, x, apply_out_norm=False):
         """The block stack without the output norms: [(stage index, tokens (B, H*W, C) fp32, H, W)] for ``out_indices``
-        (REF:600-617).  ``forward`` applies norm{i} + NCHW on top; ``swin_b200.fpn`` feeds FPN laterals from it directly."""
+        (REF:600-617); ``swin_b200.fpn`` feeds FPN laterals from it directly.  ``forward`` calls it with
+        ``apply_out_norm=True``: each stage then applies norm{i} + NCHW itself (fused with its downsample's backward) and
+        the second tuple element is the finished (B, C, H, W) output."""
         _need_cuda(x, "SwinTransformer")
         if self.training and not any(layer.use_checkpoint for layer in self.layers):
             # (activation checkpointing re-runs the blocks under the saved RNG state, which only per-call draws reproduce)
@@ -433,17 +445,14 @@ class SwinTransformer(nn.Module):
         x = self.pos_drop(x)
         outs = []
         for i, layer in enumerate(self.layers):
-            x_out, H, W, x, Wh, Ww = layer(x, Wh, Ww)
+            n = getattr(self, f"norm{i}") if (apply_out_norm and i in self.out_indices) else None
+            x_out, H, W, x, Wh, Ww = layer(x, Wh, Ww) if n is None else layer(x, Wh, Ww, out_norm=n)
             if i in self.out_indices:
                 outs.append((i, x_out, H, W))
         return outs
 
     def forward(self, x):
-        outs = []
-        for i, x_out, H, W in self.forward_tokens(x):
-            n = getattr(self, f"norm{i}")
-            outs.append(OutNormFn.apply(x_out, n.weight, n.bias, H, W, float(n.eps)))
-        return tuple(outs)
+        return tuple(o for _, o, _, _ in self.forward_tokens(x, apply_out_norm=True))
 
     def train(self, mode=True):
         super().train(mode)
