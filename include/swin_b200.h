@@ -141,6 +141,11 @@ typedef struct swin_gemm_args {
                            extra N=16 MMA per k-step against a constant all-ones smem tile (no extra pass over dY).     */
 } swin_gemm_args;
 int swin_gemm(const swin_gemm_args* a, void* stream);
+/* Tile mode of the bf16 GEMM: 0 = 1-CTA tiles (128 x N) only, 1 = per-shape policy (default), 2 = CTA-pair tiles
+ * (cta_group::2, 256 x N) wherever they are legal.  Results are identical in every mode; the knob exists so that tests
+ * and the A/B tools can run both kernel families on the same shapes.  mode < 0 only queries.  Returns the previous mode.
+ * (Initial value: environment variable SWIN_GEMM_PAIR, else 1.) */
+int swin_gemm_pair_mode(int mode);
 
 /* colsum[n] += sum_m X[m,n]  (bias gradients); X (M,N) ld, dtype; colsum fp32, caller zero-fills. */
 int swin_colsum(const void* X, int M, int N, int64_t ld, int dtype, float* colsum, void* stream);

@@ -147,6 +147,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // internal entry points implemented per translation unit
 int gemm_simt(const swin_gemm_args* a, cudaStream_t st);
 int gemm_tc(const swin_gemm_args* a, cudaStream_t st);
+int set_pair_mode(int mode);
 int attn_simt_fwd(const swin_attn_args* a, cudaStream_t st);
 int attn_simt_bwd(const swin_attn_args* a, cudaStream_t st);
 int attn_tc_fwd(const swin_attn_args* a, cudaStream_t st);

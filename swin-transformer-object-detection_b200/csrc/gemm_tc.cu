@@ -564,12 +564,14 @@ static int pick_block_n(int N) {
   return 0;
 }
 
-// CTA-pair mode (cta_group::2, 256-row tiles).  SWIN_GEMM_PAIR=0 disables it, 1 (default) applies the shape policy below,
-// 2 uses it wherever it is legal (tests).  The B half-tile of a CTA must be whole swizzle atoms: any multiple of 8 rows when
+// CTA-pair mode (cta_group::2, 256-row tiles).  swin_gemm_pair_mode() / SWIN_GEMM_PAIR: 0 disables it, 1 (default) applies the shape policy
+// below, 2 uses it wherever it is legal (tests, A/B tools).  The B half-tile of a CTA must be whole swizzle atoms: any multiple of 8 rows when
 // B is K-major, a multiple of 64 columns when it is MN-major.
-static int pair_mode() {
-  static const int v = [] { const char* e = getenv("SWIN_GEMM_PAIR"); return e ? atoi(e) : 1; }();
-  return v;
+static int g_pair_mode = [] { const char* e = getenv("SWIN_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+static int pair_mode() { return __atomic_load_n(&g_pair_mode, __ATOMIC_RELAXED); }
+int set_pair_mode(int mode) {
+  if (mode < 0) return pair_mode();
+  return __atomic_exchange_n(&g_pair_mode, mode > 2 ? 2 : mode, __ATOMIC_RELAXED);
 }
 static int pick_pair_block_n(int N, bool b_mn) {
   if (!b_mn) { const int bn = pick_block_n(N); return (bn > 0 && bn % 16 == 0) ? bn : 0; }

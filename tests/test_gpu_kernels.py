@@ -309,6 +309,94 @@ def test_gemm_bf16_matches_fp32_kernel_on_device():
     assert rel(b16, dY.double().sum(0)) < 1e-5 and rel(b32, dY.double().sum(0)) < 1e-5
 
 
+# Both tile families of the tcgen05 GEMM on the same shapes: 1-CTA tiles (mode 0) and CTA-pair tiles forced wherever they
+# are legal (mode 2; cta_group::2, each CTA stages half of B).  Shapes cover one pair tile, ragged / odd tile counts, half-tiles of
+# 8..128 rows, MN-major operands, every fused epilogue, split-K with the tensor-core bias gradient, and multi-wave grids.
+PAIR_CASES = [
+    # name, M, N, K, epilogue, a_trans, b_trans, f32 output
+    ("one unit", 256, 256, 64, "store", False, False, True),
+    ("N=96 half 48", 256, 96, 192, "store", False, False, True),
+    ("N=16 half 8", 256, 16, 128, "store", False, False, True),
+    ("ragged M", 1000, 512, 320, "store", False, False, True),
+    ("odd tiles, partial k-block", 1100, 192, 96, "store", False, False, True),
+    ("bf16 TMA store N=192", 1024, 384, 384, "store", False, False, False),
+    ("B MN-major", 1024, 512, 512, "store", False, True, True),
+    ("B MN-major N=384", 1024, 384, 512, "store", False, True, False),
+    ("A MN-major", 1024, 256, 512, "store", True, False, True),
+    ("gelu", 1024, 512, 128, "gelu", False, False, False),
+    ("dgelu", 1024, 512, 128, "dgelu", False, True, False),
+    ("residual N=384", 2048, 384, 1536, "residual", False, False, True),
+    ("split-K dW + colsum", 512, 256, 20000, "atomic", True, True, True),
+    ("split-K dW N=384", 1536, 384, 16800, "atomic", True, True, True),
+    ("many waves", 40000, 1152, 384, "store", False, False, False),
+]
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
+def test_gemm_tile_modes(case, mode):
+    ops, L = _ops()
+    _, M, N, K, epi, a_trans, b_trans, out_f32 = case
+    prev = L.lib().swin_gemm_pair_mode(mode)
+    try:
+        g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+        A = (torch.randn((K, M) if a_trans else (M, K), generator=g) * 0.5).bfloat16().to(DEV)
+        Bm = (torch.randn((K, N) if b_trans else (N, K), generator=g) * 0.5).bfloat16().to(DEV)
+        acc = _gemm_ref(A.cpu(), Bm.cpu(), a_trans, b_trans)
+        bias = torch.randn(N, generator=g).to(DEV)
+        bd = bias.double().cpu()
+        kw, want2 = {}, None
+        if epi == "store":
+            out = torch.empty(M, N, device=DEV, dtype=torch.float32 if out_f32 else torch.bfloat16)
+            code, want = L.EPI_STORE, acc + bd
+        elif epi == "gelu":
+            out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+            kw["out2"] = torch.empty_like(out)
+            u = (acc + bd).requires_grad_(True)
+            hr = so.gelu_erf(u)
+            hr.sum().backward()
+            code, want, want2 = L.EPI_GELU, hr.detach(), u.grad
+        elif epi == "dgelu":
+            out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+            kw["aux"] = torch.randn(M, N, generator=g).bfloat16().to(DEV)
+            code, want = L.EPI_DGELU, (acc + bd) * kw["aux"].double().cpu()
+        elif epi == "residual":
+            out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+            kw["aux"] = torch.randn(M, N, generator=g).to(DEV)
+            code, want = L.EPI_RESIDUAL, kw["aux"].double().cpu() + acc + bd
+        else:
+            out = torch.zeros(M, N, device=DEV, dtype=torch.float32)
+            kw["colsum_a"] = torch.zeros(M, device=DEV)
+            code, want, bias = L.EPI_ATOMIC_ADD, acc, None
+        ops.gemm(A, Bm, M, N, K, a_trans=a_trans, b_trans=b_trans, epilogue=code, bias=bias, out=out, **kw)
+        tol = 1e-5 if out.dtype == torch.float32 else 6e-3       # fp32 accumulate of bf16 products / one bf16 output rounding
+        assert rel(out, want) < tol, case[0]
+        if want2 is not None:
+            assert rel(kw["out2"], want2) < tol
+        if "colsum_a" in kw:
+            A2 = A.double().cpu().t() if a_trans else A.double().cpu()
+            assert rel(kw["colsum_a"], A2.sum(1)) < 1e-5
+    finally:
+        L.lib().swin_gemm_pair_mode(prev)
+
+
+def test_gemm_tile_modes_agree_bitwise_on_fp32_store():
+    """The two tile families accumulate each output element over k in the same order (fp32, in TMEM): identical bits."""
+    ops, L = _ops()
+    M, N, K = 3000, 384, 768
+    A = torch.randn(M, K, device=DEV).bfloat16()
+    Bm = torch.randn(N, K, device=DEV).bfloat16()
+    outs = []
+    prev = L.lib().swin_gemm_pair_mode(-1)
+    try:
+        for mode in (0, 2):
+            L.lib().swin_gemm_pair_mode(mode)
+            outs.append(ops.gemm(A, Bm, M, N, K, out_dtype=L.F32).clone())
+    finally:
+        L.lib().swin_gemm_pair_mode(prev)
+    assert torch.equal(outs[0], outs[1])
+
+
 # ---------------------------------------------------------------- window attention core
 def _attn_ref(qkv, bias, mask, nH, scale, cot):
     B_, N, C3 = qkv.shape

@@ -13,8 +13,9 @@ for g in "$@"; do
   case $g in
     index) run index 300 tests/test_gpu_kernels.py -m gpu -k "index or roundtrip or rel_bias" ;;
     ln) run ln 300 tests/test_gpu_kernels.py -m gpu -k "layernorm or scale_cast or ln_nchw or patch_unfold" ;;
-    gemm32) run gemm32 300 tests/test_gpu_kernels.py -m gpu -k "gemm and f32 and not bf16_matches" ;;
-    gemm16) run gemm16 300 tests/test_gpu_kernels.py -m gpu -k "gemm and bf16" ;;
+    gemm32) run gemm32 300 tests/test_gpu_kernels.py -m gpu -k "gemm and f32 and not bf16_matches and not tile_modes" ;;
+    gemm16) run gemm16 300 tests/test_gpu_kernels.py -m gpu -k "gemm and bf16 and not tile_modes" ;;
+    tiles) run tiles 300 tests/test_gpu_kernels.py -m gpu -k "tile_modes" ;;
     attn32) run attn32 300 tests/test_gpu_kernels.py -m gpu -k "window_attention_core and f32" ;;
     attn16) run attn16 300 tests/test_gpu_kernels.py -m gpu -k "window_attention_core and bf16" ;;
     attnfull) run attnfull 300 tests/test_gpu_kernels.py -m gpu -k "full_size_tcgen05" ;;

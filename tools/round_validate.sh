@@ -3,7 +3,7 @@
 # the ncu captures of the GEMM / attention kernels.  usage: round_validate.sh [tag]
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 R=${1:-r01}
-bash tools/gpu_check.sh index ln gemm32 gemm16 attn32 attn16 attnfull optim model
+bash tools/gpu_check.sh index ln gemm32 gemm16 tiles attn32 attn16 attnfull optim model
 python bench.py --breakdown gpurun_out/${R}_step_breakdown.txt > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err; echo "bench exit=$?"
 cat gpurun_out/${R}_bench.json
 bash tools/profile_step.sh $R
