@@ -301,6 +301,9 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
           PROF_WAIT(prof_w1, mbar_wait(full_bar(s), ph));
           tc_fence_after();
           if (elect_one()) {
+#ifdef SWIN_GEMM_PROF
+            const long long tm0 = clock64();
+#endif
             const uint32_t a_lo = a_lo0 + s * stage16, b_lo = b_lo0 + s * stage16;
             const uint32_t first = kb > kb0 ? 1u : 0u;
             if (kb + 1 < p.kb_total || last_ksteps == TBK / 16) {
@@ -315,8 +318,17 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
                 if (colsum_unit) mma(d_tmem + 256, a_lo + k * kStepA, ones_lo + k * (2048u >> 4), idesc_ones, k ? 1u : first);
               }
             }
+#ifdef SWIN_GEMM_PROF
+            const long long tm1 = clock64();
+#endif
             if (CTAS == 1) umma_commit(empty_bar(s)); else umma_commit_pair(empty_bar(s));          // smem slot reusable once these MMAs retire
             if (kb + 1 == kb1) { if (CTAS == 1) umma_commit(tfull_bar(acc)); else umma_commit_pair(tfull_bar(acc)); }   // accumulator complete
+#ifdef SWIN_GEMM_PROF
+            if (blockIdx.x == 0) {        // [11] clocks issuing MMAs, [12] clocks issuing commits, [13] k-blocks
+              atomicAdd(&g_gemm_prof[11], (unsigned long long)(tm1 - tm0)); atomicAdd(&g_gemm_prof[12], (unsigned long long)(clock64() - tm1));
+              atomicAdd(&g_gemm_prof[13], 1ull);
+            }
+#endif
           }
           __syncwarp();
           if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }

@@ -47,7 +47,8 @@ def run(name, M, N, K, epi=L.EPI_STORE, a_trans=False, b_trans=False):
     pt, mt, et = max(v[2], 1), max(v[5], 1), max(v[15], 1)
     print(f"{name:14s} {us:8.1f} us {2*M*N*K/us/1e6:7.1f} TF/s | producer0 empty-wait {100*v[0]/pt:5.1f}%  producer1 {100*v[8]/max(v[10],1):5.1f}% | "
           f"MMA acc-empty {100*v[3]/mt:5.1f}% operand-full {100*v[4]/mt:5.1f}% issue {100*(mt-v[3]-v[4])/mt:5.1f}% | "
-          f"epi0 acc-full rank0 {100*v[6]/max(mt,1):5.1f}% rank1 {100*v[14]/max(mt,1):5.1f}%  (MMA thread {mt/1e3:.0f} kclk)", flush=True)
+          f"epi0 acc-full rank0 {100*v[6]/max(mt,1):5.1f}% rank1 {100*v[14]/max(mt,1):5.1f}%  (MMA thread {mt/1e3:.0f} kclk; per k-block: "
+          f"{mt/max(v[13],1):.0f} clk total, {v[11]/max(v[13],1):.0f} issuing MMAs, {v[12]/max(v[13],1):.0f} issuing commits, k-blocks {v[13]})", flush=True)
 
 
 print("SWIN_GEMM_PAIR =", os.environ.get("SWIN_GEMM_PAIR", "(default)"))
