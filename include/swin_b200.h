@@ -84,8 +84,9 @@ typedef struct swin_ln_args {
   float* dx;           /* bwd out fp32, same layout as x                                           */
   float* dgamma;       /* bwd out, ACCUMULATED (+=) with atomics: caller zero-fills               */
   float* dbeta;
-  /* bwd, mode 0, optional (NULL = off): dy2[slot(token)] = dy2_scale[b] * dx[token] in y_dtype, laid out as window
-   * slots (B*nW, N, C) for (ws2, shift2) — the drop-path-scaled, partitioned dY of the proj Linear (REF:252 backward),
+  /* bwd, modes 0 and 1, optional (NULL = off): dy2[slot(token)] = dy2_scale[b] * dx[token] in y_dtype, laid out as window
+   * slots (B*nW, N, C) for (ws2, shift2) — mode 0: the drop-path-scaled, partitioned dY of the proj Linear (REF:252 backward);
+   * mode 1 with ws2 = 1 (slot == token): the drop-path-scaled dY of the PREVIOUS block's fc2 Linear (REF:253 backward) —
    * emitted while dx is in registers.  Pad slots are written as zeros by the kernel (dy2 needs no initialisation).  dy2_colsum (C) += column sums. */
   void* dy2;
   const float* dy2_scale;

@@ -151,7 +151,7 @@ struct LnGeom {
   FastDiv dper2, dW2, dvps;   // dividers: H2*W2, W2, C/4
   int rows;        // iteration rows (see kernels); < 2^30, and rows * row width < 2^31 float4 (checked in ln_geom)
   float eps;
-  // backward, mode 0 only: optional second output  y2[slot(token)] = y2_scale[b] * dx[token]  (window-slot layout,
+  // backward, modes 0 and 1 (iteration rows = tokens): optional second output  y2[slot(token)] = y2_scale[b] * dx[token]  (window-slot layout,
   // dtype of dy) + its column sums: the dY of the proj Linear, produced while dx is still in registers
   WinGeom g2;
   void* y2;
@@ -642,7 +642,7 @@ static int ln_geom(const swin_ln_args* a, bool bwd, LnGeom* out) {
   SWIN_REQUIRE(a->y_dtype == SWIN_F32 || (a->y_dtype == SWIN_BF16), "ln: bad y dtype");
   lg.g2 = lg.g; lg.y2 = nullptr; lg.y2_scale = nullptr; lg.y2_colsum = nullptr;
   if (bwd && a->dy2 != nullptr) {
-    SWIN_REQUIRE(a->mode == 0, "ln_bwd: the window-slot second output (dy2) is only available in mode 0");
+    SWIN_REQUIRE(a->mode == 0 || a->mode == 1, "ln_bwd: the second output (dy2) is available in modes 0 and 1 (rows = tokens)");
     SWIN_REQUIRE(a->ws2 > 0 && a->shift2 >= 0 && a->shift2 < a->ws2 && aligned16(a->dy2), "ln_bwd: bad dy2 geometry/alignment");
     lg.g2 = make_geom(a->B, a->H, a->W, a->C, a->ws2, a->shift2);
     lg.y2 = a->dy2; lg.y2_scale = a->dy2_scale; lg.y2_colsum = a->dy2_colsum;

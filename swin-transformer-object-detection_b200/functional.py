@@ -58,10 +58,33 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
+class BlockLink:
+    """Hand-over between two consecutive blocks of a stage in backward.  Block b+1's last backward kernel (LN1 backward, which
+    writes dx = the gradient of block b's output) can emit, from registers, what block b's backward would otherwise produce
+    with a separate pass over that gradient: the drop-path-scaled, compute-dtype copy (dY of fc2) and its column sums
+    (d fc2.bias).  ``s2`` is set by block b in forward; ``dy2 / colsum / key`` are deposited by block b+1 in backward and
+    consumed (then cleared) by block b only if its incoming gradient is that very tensor, unmodified."""
+    __slots__ = ("s2", "dy2", "colsum", "key")
+
+    def __init__(self):
+        self.s2 = None
+        self.dy2 = self.colsum = self.key = None
+
+    def deposit(self, dx, dy2, colsum):
+        self.dy2, self.colsum, self.key = dy2, colsum, (dx.data_ptr(), tuple(dx.shape), dx._version)
+
+    def take(self, dx2):
+        dy2, colsum, key = self.dy2, self.colsum, self.key
+        self.dy2 = self.colsum = self.key = None
+        if dy2 is not None and key == (dx2.data_ptr(), tuple(dx2.shape), dx2._version):
+            return dy2, colsum
+        return None
+
+
 class SwinBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, n1w, n1b, table, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b, mask, mask_nz, s1, s2,
-                H, W, ws, shift, nH, scale, dt, eps, canon=(0, 0)):
+                H, W, ws, shift, nH, scale, dt, eps, canon=(0, 0), recv=None, send=None):
         B, Lx, Cc = x.shape
         x = _f32c(x)
         geom = (H, W, ws, shift)
@@ -86,6 +109,10 @@ class SwinBlockFn(torch.autograd.Function):
         ctx.save_for_backward(x, n1w, table, qkvw, projw, n2w, fc1w, fc2w, mask, mask_nz, s1, s2,
                               xw, mean1, rstd1, qkv, bias, o, lse, x1, xn, mean2, rstd2, u, h)
         ctx.cfg = (B, H, W, Cc, ws, shift, nH, scale, dt, hid, qkvb is not None, canon)
+        # recv: link to the NEXT block (it deposits this block's fc2 dY); send: link to the PREVIOUS block (this block deposits)
+        ctx.recv, ctx.send = recv, send
+        if recv is not None:
+            recv.s2 = s2
         return x2
 
     @staticmethod
@@ -103,7 +130,11 @@ class SwinBlockFn(torch.autograd.Function):
         dfc2w, dfc1w, dprojw, dqkvw, dfc1b, dqkvb_buf, dfc2b_buf, dgb2, dgb1, dbias_buf, dtable_buf = _zeros_flat(
             dx2.device, tuple(fc2w.shape), tuple(fc1w.shape), tuple(projw.shape), tuple(qkvw.shape), (hid,), (3 * Cc,),
             (Cc,), (3, Cc), (3, Cc), (nH, N, N), tuple(table.shape))
-        dy2, dfc2b = ops.scale_cast(dx2, s2, 0, B, H, W, Cc, 1, 0, dt, want_colsum=True, colsum_out=dfc2b_buf)  # (T, C) + bias grad
+        got = ctx.recv.take(dx2) if ctx.recv is not None else None
+        if got is not None:
+            dy2, dfc2b = got                         # emitted by the next block's LN1 backward (BlockLink)
+        else:
+            dy2, dfc2b = ops.scale_cast(dx2, s2, 0, B, H, W, Cc, 1, 0, dt, want_colsum=True, colsum_out=dfc2b_buf)  # (T, C) + bias grad
         ops.gemm(dy2, h, Cc, hid, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc2w)
         du = ops.gemm(dy2, _w(fc2w, dt), T, hid, Cc, b_trans=True, epilogue=L.EPI_DGELU, aux=u)
         ops.gemm(du, xn, hid, Cc, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc1w, colsum_a=dfc1b)
@@ -121,9 +152,15 @@ class SwinBlockFn(torch.autograd.Function):
         dqkvb = dqkvb_buf if has_qkvb else None
         ops.gemm(dqkv, xw, 3 * Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dqkvw, colsum_a=dqkvb)
         dxw = ops.gemm(dqkv.view(Tp, 3 * Cc), _w(qkvw, dt), Tp, Cc, 3 * Cc, b_trans=True)
-        dx, dn1w, dn1b = ops.ln_bwd(1, dxw, x, n1w.detach(), mean1, rstd1, dx1, B, H, W, Cc, ws, shift, dgb=dgb1)
+        if ctx.send is not None:
+            # also emit the previous block's fc2 dY (its drop-path scale, compute dtype, token order: "windows" of one token)
+            dx, dn1w, dn1b, dyp, csp = ops.ln_bwd(1, dxw, x, n1w.detach(), mean1, rstd1, dx1, B, H, W, Cc, ws, shift,
+                                                  emit_windows=(1, 0, ctx.send.s2), dgb=dgb1)
+            ctx.send.deposit(dx, dyp, csp)
+        else:
+            dx, dn1w, dn1b = ops.ln_bwd(1, dxw, x, n1w.detach(), mean1, rstd1, dx1, B, H, W, Cc, ws, shift, dgb=dgb1)
         return (dx, dn1w, dn1b, dtable, dqkvw, dqkvb, dprojw, dprojb, dn2w, dn2b, dfc1w, dfc1b, dfc2w, dfc2b,
-                None, None, None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 class WindowAttentionFn(torch.autograd.Function):

@@ -193,7 +193,7 @@ def ln_fwd(mode: int, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, 
 def ln_bwd(mode: int, dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor,
            dres: Optional[torch.Tensor], B: int, H: int, W: int, Cc: int, ws: int, shift: int, emit_windows=None,
            dgb: Optional[torch.Tensor] = None):
-    """Returns (dx fp32 like x, dgamma, dbeta).  With ``emit_windows=(ws2, shift2, row_scale)`` (mode 0 only) it also
+    """Returns (dx fp32 like x, dgamma, dbeta).  With ``emit_windows=(ws2, shift2, row_scale)`` (modes 0 and 1) it also
     returns (dy2, colsum2): row_scale[b]*dx cast to dy's dtype and gathered into window slots, plus its column sums."""
     _chk(dy, x, gamma, mean, rstd, dres)
     dx = torch.empty_like(x)

@@ -21,7 +21,7 @@ import torch.utils.checkpoint as cp
 
 from . import _lib as L
 from . import ops
-from .functional import OutNormFn, OutNormMergeFn, PatchEmbedFn, PatchMergingFn, SwinBlockFn, WindowAttentionFn
+from .functional import BlockLink, OutNormFn, OutNormMergeFn, PatchEmbedFn, PatchMergingFn, SwinBlockFn, WindowAttentionFn
 from .registry import register_backbone
 
 
@@ -204,7 +204,9 @@ class SwinTransformerBlock(nn.Module):
         self._drop = drop
         self._dt = _dt_code(compute_dtype)
 
-    def forward(self, x, mask_matrix):
+    def forward(self, x, mask_matrix, recv=None, send=None):
+        """Reference signature ``forward(x, mask_matrix)`` (REF:198).  ``recv`` / ``send`` are the backward hand-over links to
+        the next / previous block of the stage (functional.BlockLink), passed by BasicLayer.forward only."""
         _need_cuda(x, "SwinTransformerBlock")
         B, Lx, C = x.shape
         H, W = self.H, self.W
@@ -232,7 +234,7 @@ class SwinTransformerBlock(nn.Module):
                                  a.qkv.bias, a.proj.weight, a.proj.bias, self.norm2.weight, self.norm2.bias,
                                  m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, mask, mask_nz, s1, s2,
                                  H, W, self.window_size, self.shift_size, self.num_heads, float(a.scale), self._dt,
-                                 float(self.norm1.eps), canon)
+                                 float(self.norm1.eps), canon, recv, send)
 
 
 class PatchMerging(nn.Module):
@@ -293,9 +295,18 @@ class BasicLayer(nn.Module):
         the output norm and the downsample then form one autograd node (functional.OutNormMergeFn)."""
         _need_cuda(x, "BasicLayer")
         mask = self.attn_mask(H, W, x.device)
-        for blk in self.blocks:
+        # backward hand-over between consecutive blocks (functional.BlockLink); not under activation checkpointing, whose
+        # recomputation would run the blocks' forwards out of order
+        link = torch.is_grad_enabled() and not self.use_checkpoint
+        send = None
+        for bi, blk in enumerate(self.blocks):
             blk.H, blk.W = H, W
-            x = cp.checkpoint(blk, x, mask, use_reentrant=False) if self.use_checkpoint else blk(x, mask)
+            if self.use_checkpoint:
+                x = cp.checkpoint(blk, x, mask, use_reentrant=False)
+            else:
+                recv = BlockLink() if (link and bi + 1 < len(self.blocks)) else None
+                x = blk(x, mask, recv, send)
+                send = recv
         if self.downsample is not None:
             if out_norm is not None:
                 ds = self.downsample
