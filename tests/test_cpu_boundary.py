@@ -144,3 +144,36 @@ def test_drop_path_scale_semantics():
     r = 0.75 + torch.rand((1000, 1, 1))
     torch.manual_seed(0)
     assert torch.equal(dp.sample_scale(torch.zeros(1000, 4, 8)), (r.floor() / 0.75).reshape(-1))
+
+
+def test_gemm_pair_mode_knob_is_a_plain_setter(lib):
+    """swin_gemm_pair_mode: returns the previous mode, a negative argument only queries, values above 2 clamp."""
+    prev = lib.swin_gemm_pair_mode(-1)
+    try:
+        assert lib.swin_gemm_pair_mode(0) == prev
+        assert lib.swin_gemm_pair_mode(-1) == 0
+        assert lib.swin_gemm_pair_mode(7) == 0
+        assert lib.swin_gemm_pair_mode(-1) == 2
+    finally:
+        lib.swin_gemm_pair_mode(prev)
+    assert lib.swin_gemm_pair_mode(-1) == prev
+
+
+def test_block_link_hands_over_only_the_unmodified_gradient():
+    """functional.BlockLink: the next block's emitted dY is taken only for the very tensor it was derived from."""
+    from swin_b200.functional import BlockLink
+    dx = torch.zeros(2, 6, 8)
+    dy2, cs = torch.ones(12, 8), torch.ones(8)
+    link = BlockLink()
+    assert link.take(dx) is None                               # nothing deposited
+    link.deposit(dx, dy2, cs)
+    got = link.take(dx.detach())                               # autograd hands over a detached alias: same storage, same version
+    assert got is not None and got[0] is dy2 and got[1] is cs
+    assert link.take(dx) is None                               # consumed: a second backward falls back to scale_cast
+    link.deposit(dx, dy2, cs)
+    assert link.take(dx.clone()) is None                       # another tensor (accumulated / hooked gradient)
+    link.deposit(dx, dy2, cs)
+    dx.add_(1.0)                                               # modified in place after the emission
+    assert link.take(dx) is None
+    link.deposit(dx, dy2, cs)
+    assert link.take(dx.view(12, 8)) is None                   # same storage, different shape
