@@ -127,8 +127,22 @@ def _oracle_run(params, img, cfg, cots, drop_scales=None, autocast=False):
 SWIN_T = dict(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7)
 
 
+# BASELINE config 4's widths (Swin-B: embed 128, heads 4-8-16-32, i.e. C = 128 / 256 / 512 / 1024, hidden up to 4096) on a
+# shallow stack: every GEMM N / K the deep model has (incl. N = 384 = 3 x 128 with an MN-major B), two blocks per stage
+SWIN_B_WIDTHS = dict(embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=7)
+
+
+@pytest.mark.parametrize("mode,B,HW", [("fp32", 1, (224, 224)), ("bf16", 2, (224, 300))])
+def test_swin_b_widths_vs_oracle(mode, B, HW):
+    _backbone_vs_oracle(SWIN_B_WIDTHS, mode, B, HW)
+
+
 @pytest.mark.parametrize("mode,B,HW", [("fp32", 1, (224, 224)), ("bf16", 2, (224, 224)), ("bf16", 1, (800, 1333))])
 def test_swin_t_vs_oracle(mode, B, HW):
+    _backbone_vs_oracle(SWIN_T, mode, B, HW)
+
+
+def _backbone_vs_oracle(SWIN_T, mode, B, HW):
     """BASELINE configs 1 and 2 (at B=1-2): Swin-T on seeded weights, outputs + input grad + all 173 param grads.
 
     fp32 mode: every tensor <= 1e-4.  bf16 mode: outputs, input gradient and parameter gradients <= 2e-2, EXCEPT that a
