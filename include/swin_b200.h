@@ -147,6 +147,10 @@ int swin_gemm(const swin_gemm_args* a, void* stream);
  * and the A/B tools can run both kernel families on the same shapes.  mode < 0 only queries.  Returns the previous mode.
  * (Initial value: environment variable SWIN_GEMM_PAIR, else 1.) */
 int swin_gemm_pair_mode(int mode);
+/* The tile plan swin_gemm would use for this bf16 problem (only dtype, M, N, K, a_trans, b_trans and epilogue are read; no
+ * CUDA call, works without a GPU): out6 = { CTAs per tile (1 | 2), tile width N, tiles along M (of 128 x CTAs rows),
+ * tiles along N, split-K factor, 64-wide k-blocks per split }. */
+int swin_gemm_plan(const swin_gemm_args* a, int* out6);
 
 /* colsum[n] += sum_m X[m,n]  (bias gradients); X (M,N) ld, dtype; colsum fp32, caller zero-fills. */
 int swin_colsum(const void* X, int M, int N, int64_t ld, int dtype, float* colsum, void* stream);

@@ -68,6 +68,7 @@ SYMBOLS = {
     "swin_scale_cast": (c_int, [vp, vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp]),
     "swin_cast_bf16": (c_int, [vp, vp, c_i64, vp]),
     "swin_gemm_pair_mode": (c_int, [c_int]),
+    "swin_gemm_plan": (c_int, [vp, vp]),
     "swin_grad_gather": (c_int, [vp, vp, vp, c_int, vp, vp]),
     "swin_adamw_step": (c_int, [vp, vp, vp, vp, vp, vp, vp, c_int, C.c_double, C.c_double, C.c_double, C.c_double, c_int, C.c_double, vp]),
     "swin_window_attn_fwd": (c_int, [C.POINTER(AttnArgs), vp]),

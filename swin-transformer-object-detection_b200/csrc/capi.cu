@@ -35,6 +35,7 @@ extern "C" int swin_gemm(const swin_gemm_args* a, void* stream) {
   return -EINVAL;
 }
 extern "C" int swin_gemm_pair_mode(int mode) { return set_pair_mode(mode); }
+extern "C" int swin_gemm_plan(const swin_gemm_args* a, int* out6) { return gemm_tc_plan(a, out6); }
 extern "C" int swin_window_attn_fwd(const swin_attn_args* a, void* stream) {
   if (!a) { set_error("attn: null args"); return -EINVAL; }
   if (a->dtype == SWIN_F32) return attn_simt_fwd(a, (cudaStream_t)stream);

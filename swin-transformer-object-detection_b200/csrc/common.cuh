@@ -148,6 +148,7 @@ __device__ __forceinline__ float warp_max(float v) {
 int gemm_simt(const swin_gemm_args* a, cudaStream_t st);
 int gemm_tc(const swin_gemm_args* a, cudaStream_t st);
 int set_pair_mode(int mode);
+int gemm_tc_plan(const swin_gemm_args* a, int* out6);
 int attn_simt_fwd(const swin_attn_args* a, cudaStream_t st);
 int attn_simt_bwd(const swin_attn_args* a, cudaStream_t st);
 int attn_tc_fwd(const swin_attn_args* a, cudaStream_t st);

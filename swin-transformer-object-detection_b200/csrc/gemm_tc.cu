@@ -610,17 +610,11 @@ static int pick_splits(int tiles, int kb_total, int slots) {
   return best;
 }
 
-int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
-  EpiParams ep;
-  int rc = make_epi_params(a, &ep);
-  if (rc) return rc;
-  SWIN_REQUIRE(a->A && a->B, "gemm: null operand");
-  SWIN_REQUIRE(a->N % 16 == 0, "gemm(bf16): N must be a multiple of 16 (got %d)", a->N);
-  SWIN_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "gemm(bf16): lda/ldb must be multiples of 8");
-  if (a->M == 0) return 0;
-  const bool a_mn = a->a_trans != 0, b_mn = a->b_trans != 0;
-  GemmTcParams p;
-  p.epi = ep;
+// Tile family, tile width, tile grid and split-K factor of one problem: pure host logic (no CUDA call), also reachable
+// through swin_gemm_plan() so that the policy is testable without a GPU.
+static int choose_tiles(const swin_gemm_args* a, GemmTcParams* pp) {
+  GemmTcParams& p = *pp;
+  const bool b_mn = a->b_trans != 0;
   p.block_n = pick_block_n(a->N);
   SWIN_REQUIRE(p.block_n > 0, "gemm(bf16): unsupported N %d", a->N);
   p.ctas = 1;
@@ -641,13 +635,40 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   p.kb_total = ceil_div(a->K, TBK);
   p.K = a->K;
   p.splits = a->epilogue == SWIN_EPI_ATOMIC_ADD ? pick_splits(p.m_tiles * p.n_tiles, p.kb_total, kNumSMs / p.ctas) : 1;
+  p.kb_per_split = ceil_div(p.kb_total, p.splits);
+  p.splits = ceil_div(p.kb_total, p.kb_per_split);
+  return 0;
+}
+
+int gemm_tc_plan(const swin_gemm_args* a, int* out6) {
+  SWIN_REQUIRE(a && out6, "gemm_plan: null pointer");
+  SWIN_REQUIRE(a->dtype == SWIN_BF16, "gemm_plan: only the bf16 (tcgen05) GEMM has a tile plan");
+  SWIN_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->N % 16 == 0, "gemm_plan: bad shape (N must be a multiple of 16)");
+  GemmTcParams p;
+  const int rc = choose_tiles(a, &p);
+  if (rc) return rc;
+  out6[0] = p.ctas; out6[1] = p.block_n; out6[2] = p.m_tiles; out6[3] = p.n_tiles; out6[4] = p.splits; out6[5] = p.kb_per_split;
+  return 0;
+}
+
+int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
+  EpiParams ep;
+  int rc = make_epi_params(a, &ep);
+  if (rc) return rc;
+  SWIN_REQUIRE(a->A && a->B, "gemm: null operand");
+  SWIN_REQUIRE(a->N % 16 == 0, "gemm(bf16): N must be a multiple of 16 (got %d)", a->N);
+  SWIN_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "gemm(bf16): lda/ldb must be multiples of 8");
+  if (a->M == 0) return 0;
+  const bool a_mn = a->a_trans != 0, b_mn = a->b_trans != 0;
+  GemmTcParams p;
+  p.epi = ep;
+  rc = choose_tiles(a, &p);
+  if (rc) return rc;
   p.colsum_a = nullptr;
   if (a->colsum_a != nullptr) {
     SWIN_REQUIRE(a->epilogue == SWIN_EPI_ATOMIC_ADD && a_mn && b_mn, "gemm: colsum_a needs ATOMIC_ADD with a_trans = b_trans = 1");
     p.colsum_a = a->colsum_a;
   }
-  p.kb_per_split = ceil_div(p.kb_total, p.splits);
-  p.splits = ceil_div(p.kb_total, p.kb_per_split);
   p.a_bytes = TBM * TBK * 2;
   const int bn_cta = p.block_n / p.ctas;                       // B rows (columns of D) staged by one CTA
   const int bn_rows = b_mn ? ceil_div(bn_cta, 64) * 64 : bn_cta;

@@ -177,3 +177,49 @@ def test_block_link_hands_over_only_the_unmodified_gradient():
     assert link.take(dx) is None
     link.deposit(dx, dy2, cs)
     assert link.take(dx.view(12, 8)) is None                   # same storage, different shape
+
+
+def _plan(lib, M, N, K, epi=0, a_trans=0, b_trans=0):
+    from swin_b200 import _lib as L
+    a = L.GemmArgs(dtype=L.BF16, M=M, N=N, K=K, a_trans=a_trans, b_trans=b_trans, epilogue=epi)
+    out = (ctypes.c_int * 6)()
+    rc = lib.swin_gemm_plan(ctypes.byref(a), ctypes.cast(out, ctypes.c_void_p))
+    assert rc == 0, lib.swin_last_error()
+    return tuple(out)          # CTAs per tile, tile width, tiles along M, tiles along N, split-K factor, k-blocks per split
+
+
+def test_gemm_tile_policy_on_the_benchmark_shapes(lib):
+    """Host logic of the tcgen05 GEMM (no GPU needed): which tile family / width / split-K factor each GEMM of the
+    benchmark step (Swin-T, B=16, 800x1333) gets.  The expected values are the ones the measurements in
+    profiles/r01/gemm_pair_ab.txt were taken with."""
+    from swin_b200 import _lib as L
+    T0, Tp0, T2, Tp2 = 1068800, 1091328, 67200, 75264
+    prev = lib.swin_gemm_pair_mode(1)
+    try:
+        # forward, K-major B: CTA pairs, each CTA stages half of the tile width
+        assert _plan(lib, Tp2, 1152, 384) == (2, 192, 294, 6, 1, 6)                        # qkv, stage 2
+        assert _plan(lib, T2, 1536, 384, L.EPI_GELU) == (2, 256, 263, 6, 1, 6)             # fc1 + GELU (odd tile count, >= 8 tiles)
+        assert _plan(lib, T2, 384, 1536, L.EPI_RESIDUAL) == (2, 192, 263, 2, 1, 24)        # fc2 + residual
+        assert _plan(lib, Tp2, 384, 384, L.EPI_SCATTER_RESIDUAL) == (2, 192, 294, 2, 1, 6) # proj + window reverse + residual
+        assert _plan(lib, Tp0, 288, 96) == (2, 96, 4263, 3, 1, 2)                          # qkv, stage 0 (K = 96: 64 + 32)
+        assert _plan(lib, T0, 96, 48) == (2, 96, 4175, 1, 1, 1)                            # PatchEmbed conv as a GEMM
+        # backward: DGELU stays on 1-CTA tiles; MN-major B with N = 384 would need 128-wide pair tiles -> 1-CTA 192-wide
+        assert _plan(lib, T2, 1536, 384, L.EPI_DGELU, b_trans=1) == (1, 256, 525, 6, 1, 6)
+        assert _plan(lib, T2, 384, 1536, b_trans=1) == (1, 192, 525, 2, 1, 24)             # dX of fc1
+        assert _plan(lib, 16800, 768, 3072, b_trans=1) == (2, 256, 66, 3, 1, 48)           # dX of fc1, stage 3 (N % 256 == 0)
+        # split-K weight gradients: pairs only for an even tile count; the split fills the SMs (or SM pairs) in whole rounds
+        assert _plan(lib, 1536, 384, T2, L.EPI_ATOMIC_ADD, 1, 1) == (2, 128, 6, 3, 4, 263)     # 18 tiles x 4 = 72 of 74 pairs
+        assert _plan(lib, 1152, 384, Tp2, L.EPI_ATOMIC_ADD, 1, 1) == (1, 192, 9, 2, 8, 147)    # 9 tiles along M: odd -> 1-CTA, 144 of 148 SMs
+        assert _plan(lib, 384, 1536, T2, L.EPI_ATOMIC_ADD, 1, 1) == (1, 256, 3, 6, 8, 132)
+        # a single 128-row tile never pairs
+        assert _plan(lib, 96, 384, T0, L.EPI_ATOMIC_ADD, 1, 1)[0] == 1
+        lib.swin_gemm_pair_mode(0)
+        assert _plan(lib, Tp2, 1152, 384) == (1, 192, 588, 6, 1, 6)
+        lib.swin_gemm_pair_mode(2)                                                          # forced wherever legal (tests, A/B tools)
+        assert _plan(lib, T2, 1536, 384, L.EPI_DGELU, b_trans=1) == (2, 256, 263, 6, 1, 6)
+        assert _plan(lib, T2, 384, 1536, b_trans=1) == (2, 128, 263, 3, 1, 24)
+        assert _plan(lib, T0, 96, 384, b_trans=1)[0] == 1                                  # N = 96, MN-major: no legal half-tile
+    finally:
+        lib.swin_gemm_pair_mode(prev)
+    a = L.GemmArgs(dtype=L.F32, M=128, N=128, K=64)
+    assert lib.swin_gemm_plan(ctypes.byref(a), ctypes.cast((ctypes.c_int * 6)(), ctypes.c_void_p)) == -22
