@@ -1,10 +1,12 @@
 // bf16 GEMM on the 5th-generation tensor cores: persistent, warp-specialised
-//   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring)
-//   warp 1      MMA issuer     (one thread, tcgen05.mma kind::f16, fp32 accumulators in TMEM)
-//   warps 2..9  epilogue       (tcgen05.ld -> fused epilogue -> global), overlapped with the next
-//                               tile's main loop through two TMEM accumulator stages.
-// Operands may be K-major or MN-major ("transposed") so forward (X W^T), dX (dY W) and the
-// split-K weight gradient (dY^T X) all run on the same kernel.
+//   warp 0        TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring; whole warp in the loop, one elected lane issues)
+//   warp 1        MMA issuer     (one elected lane, tcgen05.mma kind::f16, fp32 accumulators in TMEM; the critical path: kept
+//                                 to constant-hi / incremented-lo descriptors and incremental ring indices)
+//   warps 2..9/13 epilogue       (tcgen05.ld -> fused epilogue -> global / TMA store), overlapped with the next tiles' main
+//                                 loops through 2 or 4 TMEM accumulator stages
+// Operands may be K-major or MN-major ("transposed") so forward (X W^T), dX (dY W) and the split-K weight gradient
+// (dY^T X) all run on the same kernel.  CTAS = 2 instantiations pair the two CTAs of a cluster on 256-row tiles
+// (cta_group::2): see the comment above gemm_tc_kernel and choose_tiles() for where they are used.
 #include <stdlib.h>
 #include "epilogue.cuh"
 #include "ptx.cuh"
