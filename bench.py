@@ -29,10 +29,20 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 SWIN_T = dict(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7)
+SWIN_B = dict(embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32], window_size=7)
 IMG_HW = (800, 1333)
-GFLOP_PER_IMG = 593.18           # fwd+bwd, SURVEY.md §8(d) / BASELINE.md §2
-METRIC = "swin_t_backbone_fwd_bwd_images_per_sec_800x1333"
-WORKLOAD = "configs[1]: Swin-T backbone fwd+bwd bf16, batch 16 per GPU, synthetic 3x800x1333, window 7 with shift masks"
+# model -> (constructor kwargs, fwd+bwd GFLOP per image (SURVEY.md §8(d) / BASELINE.md §2), drop_path_rate of its config,
+#           metric name, workload description)
+MODELS = {
+    "swin_t": (SWIN_T, 593.18, 0.1, "swin_t_backbone_fwd_bwd_images_per_sec_800x1333",
+               "configs[1]: Swin-T backbone fwd+bwd bf16, batch 16 per GPU, synthetic 3x800x1333, window 7 with shift masks"),
+    "swin_b": (SWIN_B, 2052.6, 0.3, "swin_b_backbone_fwd_bwd_images_per_sec_800x1333",
+               "configs[3]: Cascade Mask R-CNN Swin-B backbone (embed 128, depths 2-2-18-2) fwd+bwd bf16, batch 16 per GPU, synthetic "
+               "3x800x1333, NCCL gradient all-reduce (347 MB fp32) overlapped with backward"),
+}
+GFLOP_PER_IMG = MODELS["swin_t"][1]
+METRIC = MODELS["swin_t"][3]
+WORKLOAD = MODELS["swin_t"][4]
 
 
 def measured_peaks():
@@ -127,9 +137,71 @@ class KernelTimer:
         return "\n".join(out)
 
 
-def oracle_step_fn(batch: int):
+def eager_gpu_step_fn(batch: int, dev, cfg):
+    """The GPU bar: the reference algorithm as plain torch-eager ops ON THE SAME B200 under
+    torch.autocast(bf16) -- the oracle port with torch's fused layer_norm / gelu primitives, i.e. the kernels the reference
+    module itself would launch.  Baseline arm only: never on the product path, never in --impl reference."""
+    from oracle import swin_oracle as so
+    so.FAST_OPS = True
+    shapes = so.param_shapes(**cfg)
+    params = {k: v.to(dev).requires_grad_(True) for k, v in so.seeded_params(shapes, seed=0, noisy=False).items()}
+    img = torch.from_numpy(np.random.default_rng(0).standard_normal((batch, 3) + IMG_HW).astype(np.float32)).to(dev)
+    state = {"cots": None}
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            outs = so.backbone_forward(img, params, **cfg)
+        if state["cots"] is None:
+            state["cots"] = [torch.randn(o.shape, device=dev, dtype=o.dtype) for o in outs]
+        torch.autograd.backward(outs, state["cots"])
+        for p in params.values():
+            p.grad = None
+    return step
+
+
+def time_eager_gpu(dev, cfg, batch: int, steps: int, warmup: int):
+    """(images/s, ms/step, batch actually used) of the eager-GPU arm; halves the batch on OOM."""
+    b = batch
+    while b >= 1:
+        try:
+            step = eager_gpu_step_fn(b, dev, cfg)
+            for _ in range(max(1, warmup)):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            return b / (ms / 1e3), ms, b
+        except torch.OutOfMemoryError:
+            step = None
+            torch.cuda.empty_cache()
+            b //= 2
+    return None, None, 0
+
+
+def run_torch_eager(args, emit=print):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, gflop, _, metric, workload = MODELS[args.model]
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    v, ms, b = time_eager_gpu(dev, cfg, args.batch, args.steps, max(args.warmup, 1))
+    emit(json.dumps({
+        "impl": "torch_eager", "metric": metric, "value": v, "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload, "per_gpu_batch": b,
+                   "note": "oracle port of the reference algorithm as torch-eager CUDA ops under torch.autocast(bf16), on this GPU"}}))
+
+
+def oracle_step_fn(batch: int, cfg=None):
     """The reference algorithm on the CPU (oracle port of mmdet/models/backbones/swin_transformer.py), fp32."""
     from oracle import swin_oracle as so
+    SWIN_T = cfg or MODELS["swin_t"][0]
     shapes = so.param_shapes(**SWIN_T)
     params = {k: v.requires_grad_(True) for k, v in so.seeded_params(shapes, seed=0, noisy=False).items()}
     img = torch.from_numpy(np.random.default_rng(0).standard_normal((batch, 3) + IMG_HW).astype(np.float32))
@@ -154,7 +226,8 @@ def run_reference(args, emit=print):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = oracle_step_fn(1)
+    cfg, _, _, METRIC, WORKLOAD = MODELS[args.model]
+    step = oracle_step_fn(1, cfg)
     for _ in range(max(1, min(args.warmup, 2))):
         step()
     t0 = time.perf_counter()
@@ -177,7 +250,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_eager"],
+                    help="reference: the reference algorithm on the host CPU cores; torch_eager: the same algorithm as eager torch ops on the GPU")
+    ap.add_argument("--model", default="swin_t", choices=sorted(MODELS), help="swin_t = BASELINE configs[1]; swin_b = configs[3]")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the torch-eager GPU baseline leg (N=1 only)")
+    ap.add_argument("--attn-sweep", default=None, help="run the configs[4] window-attention sweep, write the table to this file, and exit")
+    ap.add_argument("--sm-reserve", type=int, default=None, help="SMs the persistent kernels leave free for NCCL (default: 0 at N=1, "
+                    "SWIN_SM_RESERVE or 4 at N>1)")
+    ap.add_argument("--nccl-max-ctas", type=int, default=None, help="cap NCCL's CTAs per collective (default SWIN_NCCL_MAX_CTAS or 4)")
     ap.add_argument("--batch", type=int, default=16, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--compute-dtype", default="bf16")
@@ -202,6 +282,12 @@ def main():
 
     if args.impl == "reference":
         return run_reference(args, emit)
+    if args.impl == "torch_eager":
+        return run_torch_eager(args, emit)
+    if args.attn_sweep:
+        from tools.attn_sweep import run_sweep
+        return run_sweep(args.attn_sweep)
+    SWIN_T, GFLOP_PER_IMG, DPR, METRIC, WORKLOAD = MODELS[args.model]
 
     import torch.distributed as dist
     import swin_b200
@@ -214,15 +300,33 @@ def main():
     assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU; there is no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    nccl_ctas = sm_reserve = 0
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # The gradient all-reduce is latency-, not bandwidth-bound on NVSwitch (110 MB per step against >= 25 ms of compute):
+        # cap NCCL at a few CTAs and leave exactly that many SMs out of the persistent kernels' grids, so a GEMM / attention
+        # launch never waits a whole extra wave for the SMs NCCL is holding (the fixed +0.6..0.9 ms per step of round 1).
+        nccl_ctas = args.nccl_max_ctas if args.nccl_max_ctas is not None else int(os.environ.get("SWIN_NCCL_MAX_CTAS", "4"))
+        sm_reserve = args.sm_reserve if args.sm_reserve is not None else int(os.environ.get("SWIN_SM_RESERVE", str(nccl_ctas)))
+        pg_opts = None
+        if nccl_ctas > 0:
+            try:
+                pg_opts = dist.ProcessGroupNCCL.Options()
+                pg_opts.config.max_ctas = nccl_ctas
+                pg_opts.config.min_ctas = 1
+            except Exception as e:
+                sys.stderr.write(f"[bench] NCCL CTA cap unavailable ({e})\n")
+                pg_opts, nccl_ctas = None, 0
+        dist.init_process_group("nccl", device_id=dev, pg_options=pg_opts)
+        if sm_reserve > 0:
+            from swin_b200 import _lib
+            _lib.lib().swin_sm_reserve(sm_reserve)
     W = max(args.warmup, 3)
     K = args.steps
     B = args.batch
 
     torch.manual_seed(0)
-    net = swin_b200.SwinTransformer(drop_path_rate=0.1, compute_dtype=args.compute_dtype, **SWIN_T)
+    net = swin_b200.SwinTransformer(drop_path_rate=DPR, compute_dtype=args.compute_dtype, **SWIN_T)
     net.init_weights()
     net = net.to(dev).train()
     ddp = BucketedGradAllReduce(net, bucket_mb=32.0)
@@ -350,6 +454,17 @@ def main():
     except Exception:
         pass
     _, _, _, gemm_bytes = timer.summary("gemm_tc")
+    # the window-attention kernels (the metric's "attn % peak"): every launch whose kind starts with "attn" -- the attention
+    # core (attn_fwd / attn_bwd) and, where the fused QKV + attention kernel runs, that kernel with its projection flops
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    attn = {}
+    for pref in ("attn_fwd", "attn_qkv_fwd", "attn_bwd", "attn"):
+        n_a, ms_a, fl_a, by_a = timer.summary(pref)
+        if n_a and ms_a > 0:
+            tf = fl_a / (ms_a / 1e3) / 1e12
+            attn[pref if pref != "attn" else "all"] = {
+                "launches_per_step": n_a // max(K, 1), "ms_per_step": ms_a / max(K, 1), "achieved": tf, "unit": "TFLOP/s",
+                "frac": tf / peak, "dram_gbs": by_a / (ms_a / 1e3) / 1e9, "dram_frac_of_hbm_peak": by_a / (ms_a / 1e3) / 1e9 / hbm_peak}
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all epilogues)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": gemm_bytes / max(n_launch, 1),
@@ -358,12 +473,13 @@ def main():
                 "dram_frac_of_hbm_peak": (traffic * n_launch / (gemm_ms / 1e3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0))) if (traffic and gemm_ms > 0) else None,
                 "peak_source": peak_kind + " (sustained: timed inside a long step)",
                 "launches_per_step": n_launch // max(K, 1), "ms_per_step_in_kernel": gemm_ms / max(K, 1),
-                "whole_step_frac_of_tensor_roofline": (GFLOP_PER_IMG * 1e9 * B / (ms_step / 1e3)) / (peak * 1e12)}
+                "whole_step_frac_of_tensor_roofline": (GFLOP_PER_IMG * 1e9 * B / (ms_step / 1e3)) / (peak * 1e12),
+                "attention": attn}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        cstep = oracle_step_fn(1)
+        cstep = oracle_step_fn(1, SWIN_T)
         t0 = time.perf_counter(); cstep(); warm = time.perf_counter() - t0
         n = 3 if warm < 8 else 1
         t0 = time.perf_counter()
@@ -373,26 +489,54 @@ def main():
         cpu_baseline = {"value": 1.0 / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                         "sample": f"oracle port, fp32, 1 image 3x{IMG_HW[0]}x{IMG_HW[1]} fwd+bwd, 1 warm-up + {n} timed"}
 
+    dispatch = "cuda_graph" if graphed is not None else "eager"
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_gpu_eager:
+        # the GPU bar: same algorithm as torch-eager ops on this same GPU (bounded: 1 warm-up + 2 timed steps)
+        graphed = None
+        torch.cuda.empty_cache()
+        try:
+            v_e, ms_e, b_e = time_eager_gpu(dev, SWIN_T, B, 2, 1)
+            if v_e:
+                gpu_eager = {"value": v_e, "unit": "images/s", "ms_per_step": ms_e, "per_gpu_batch": b_e, "kind": "port",
+                             "sample": "oracle port as torch-eager CUDA ops under torch.autocast(bf16) (fused layer_norm/gelu/softmax "
+                                       "primitives), same GPU, 1 warm-up + 2 timed steps", "speedup_ours": value / v_e}
+        except Exception as e:
+            gpu_eager = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        from oracle import swin_oracle as _so
+        _so.FAST_OPS = False
+
     if rank == 0:
         img_bytes = B * 3 * IMG_HW[0] * IMG_HW[1] * 4
         emit(json.dumps({
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.compute_dtype == "bf16" else "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * B, "per_gpu_batch": B, "drop_path_rate": 0.1,
-                       "parallelism": f"dp{world}", "dispatch": "cuda_graph" if graphed is not None else "eager", "l2": "inputs (205 MB/step) and activations (>10 GB/step) exceed the 126 MB L2",
+            "config": {"workload": WORKLOAD, "global_batch": world * B, "per_gpu_batch": B, "drop_path_rate": DPR,
+                       "nccl_max_ctas": nccl_ctas, "sm_reserve": sm_reserve,
+                       "parallelism": f"dp{world}", "dispatch": dispatch, "l2": "inputs (205 MB/step) and activations (>10 GB/step) exceed the 126 MB L2",
                        "precision": "bf16 tcgen05 operands, fp32 accumulate/LN/softmax/residual stream, fp32 master weights"},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": 4,
                     "input_pipeline": "pinned host -> staging buffer on a copy stream (overlaps the previous step) -> device-to-device into the static input"},
-            "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}))
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "gpu_eager_baseline": gpu_eager}))
     sys.stdout.flush()
     if world > 1:
-        # dist.destroy_process_group() hangs after CUDA-graph-captured NCCL collectives (observed on this stack:
-        # torch 2.11 / NCCL 2.28); all ranks are done and in sync here, so leave without tearing the communicator down
+        # Clean teardown: the captured graph holds NCCL kernels of this communicator, so it is destroyed first (graph, its
+        # private pool, the events), the device is drained, and only then is the process group torn down.  A watchdog turns a
+        # teardown that still hangs (seen on torch 2.11 / NCCL 2.28 when the graph outlives the communicator) into exit 0.
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
-        os._exit(0)
+        graphed = run_step = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        killer = threading.Timer(20.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
+        dist.destroy_process_group()
+        killer.cancel()
 
 
 if __name__ == "__main__":

@@ -41,6 +41,10 @@ int swin_version(void);
 const char* swin_last_error(void);
 /* 0 if `device` is compute capability 10.x, else -ENOTSUP. */
 int swin_device_check(int device);
+/* SMs the persistent kernels (tcgen05 GEMM, attention) leave free, e.g. for NCCL's CTAs when the gradient all-reduce of
+ * mmdet/apis/train.py:91-99 overlaps backward: their grids become (SM count - n) CTAs instead of one per SM.  n < 0 only
+ * queries.  Returns the previous value (initially 0).  Kernel attributes and the SM count are tracked per device. */
+int swin_sm_reserve(int n);
 
 /* ---------------------------------------------------------------- index ops (bit-exact) */
 

@@ -49,6 +49,7 @@ SYMBOLS = {
     "swin_version": (c_int, []),
     "swin_last_error": (C.c_char_p, []),
     "swin_device_check": (c_int, [c_int]),
+    "swin_sm_reserve": (c_int, [c_int]),
     "swin_window_partition": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp]),
     "swin_window_reverse": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp]),
     "swin_window_gather": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, vp]),

@@ -51,8 +51,25 @@ def adapt_state_dict(model: torch.nn.Module, state_dict: Dict[str, torch.Tensor]
     return sd
 
 
-def load_checkpoint(model: torch.nn.Module, filename: str, map_location="cpu", strict: bool = False):
-    ckpt = torch.load(filename, map_location=map_location, weights_only=False)
+def _read(filename: str, map_location, allow_pickle: bool):
+    """Local path, or an http(s):// URL through torch.hub (the reference's ``_load_checkpoint`` also resolves
+    ``modelzoo://`` / ``open-mmlab://`` aliases through mmcv's model-zoo tables: not reproduced -- pass the URL itself).
+    Tensors-only unpickling first; arbitrary-object unpickling (code execution on a hostile file) only on opt-in."""
+    if filename.startswith(("http://", "https://")):
+        return torch.hub.load_state_dict_from_url(filename, map_location=map_location, weights_only=not allow_pickle)
+    if filename.startswith(("modelzoo://", "open-mmlab://", "torchvision://")):
+        raise RuntimeError(f"{filename}: model-zoo aliases are not resolved here; pass a local path or an http(s) URL")
+    try:
+        return torch.load(filename, map_location=map_location, weights_only=True)
+    except Exception as e:
+        if not allow_pickle:
+            raise RuntimeError(f"{filename} cannot be read with weights_only=True ({type(e).__name__}: {e}); if you trust the "
+                               "file, call load_checkpoint(..., allow_pickle=True)") from e
+        return torch.load(filename, map_location=map_location, weights_only=False)
+
+
+def load_checkpoint(model: torch.nn.Module, filename: str, map_location="cpu", strict: bool = False, allow_pickle: bool = False):
+    ckpt = _read(filename, map_location, allow_pickle)
     if not isinstance(ckpt, dict):
         raise RuntimeError(f"No state_dict found in checkpoint file {filename}")
     state = ckpt.get("state_dict", ckpt.get("model", ckpt))

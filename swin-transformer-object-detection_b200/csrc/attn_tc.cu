@@ -560,7 +560,7 @@ static int attn_tc_common(const swin_attn_args* a, AttnTcParams* out, bool bwd, 
   AttnTcParams p;
   p.B_ = a->B_; p.nH = a->nH; p.nW = a->nW > 0 ? a->nW : 1; p.C = a->nH * AHD; p.scale = a->scale;
   p.npairs = (a->B_ + 1) / 2;
-  int per_head = (kNumSMs * ctas_per_sm) / a->nH;     // floor: the whole grid must be co-resident (one wave, no tail CTA)
+  int per_head = (persistent_sms() * ctas_per_sm) / a->nH;     // floor: the whole grid must be co-resident (one wave, no tail CTA)
   if (per_head > p.npairs) per_head = p.npairs;
   if (per_head < 1) per_head = 1;
   p.ctas_per_head = per_head;
@@ -585,12 +585,8 @@ int attn_tc_fwd(const swin_attn_args* a, cudaStream_t st) {
   rc = make_tmap_bf16_2d(&tm, a->qkv, (uint64_t)3 * p.C, (uint64_t)p.B_ * AN, (uint64_t)3 * p.C * 2, AHD, AN, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
   const size_t smem = kFwdTiles + kPBytes + (AN * kFwdBiasLd + 16) * sizeof(float) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
-  }
+  rc = ensure_dyn_smem((const void*)attn_tc_fwd_kernel, (int)smem);
+  if (rc) return rc;
   CUtensorMap tmo;
   rc = make_tmap_bf16_2d(&tmo, a->out, (uint64_t)p.C, (uint64_t)p.B_ * AN, (uint64_t)p.C * 2, AHD, AN, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
@@ -610,12 +606,8 @@ int attn_tc_bwd(const swin_attn_args* a, cudaStream_t st) {
   rc = make_tmap_bf16_2d(&tmdo, a->dout, (uint64_t)p.C, (uint64_t)p.B_ * AN, (uint64_t)p.C * 2, AHD, AN, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
   const size_t smem = 2 * kBwdTiles + 2 * kPBytes + AN * kBiasLd * sizeof(float) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
-  }
+  rc = ensure_dyn_smem((const void*)attn_tc_bwd_kernel, (int)smem);
+  if (rc) return rc;
   CUtensorMap tmdq;
   rc = make_tmap_bf16_2d(&tmdq, a->dqkv, (uint64_t)3 * p.C, (uint64_t)p.B_ * AN, (uint64_t)3 * p.C * 2, AHD, AN, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;

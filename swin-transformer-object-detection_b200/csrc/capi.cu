@@ -2,6 +2,11 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include "common.cuh"
 
 namespace swin {
@@ -12,9 +17,45 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<int> g_sm_count[64];       // 0 = not queried yet
+static std::atomic<int> g_sm_reserve{0};
+int persistent_sms() {
+  int dev = 0, n = kNumSMs;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+    n = g_sm_count[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+      if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+      g_sm_count[dev].store(n, std::memory_order_relaxed);
+    }
+  } else {
+    (void)cudaGetLastError();                 // no device: keep the sticky-error state clean for the host-only entry points
+  }
+  n -= g_sm_reserve.load(std::memory_order_relaxed);
+  n &= ~1;                                    // CTA pairs occupy whole TPCs
+  return n < 2 ? 2 : n;
+}
+
+static std::mutex g_attr_mu;
+static std::set<std::pair<const void*, int>> g_attr_done;
+int ensure_dyn_smem(const void* func, int bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_attr_mu);
+  if (g_attr_done.count({func, dev})) return 0;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  g_attr_done.insert({func, dev});
+  return 0;
+}
 }  // namespace swin
 
 using namespace swin;
+
+extern "C" int swin_sm_reserve(int n) {
+  if (n < 0) return g_sm_reserve.load(std::memory_order_relaxed);
+  return g_sm_reserve.exchange(n > 64 ? 64 : n, std::memory_order_relaxed);
+}
 
 extern "C" int swin_version(void) { return SWIN_B200_VERSION; }
 extern "C" const char* swin_last_error(void) { return g_err; }

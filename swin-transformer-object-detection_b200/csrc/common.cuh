@@ -10,9 +10,15 @@
 
 namespace swin {
 
-constexpr int kNumSMs = 148;
+constexpr int kNumSMs = 148;    // B200; grid-size heuristic of the (over-subscribed) HBM-bound kernels only
 
 void set_error(const char* fmt, ...);
+// SMs of the CURRENT device (queried once per device; 148 when no device is visible, so the host-only tile planner works
+// without a GPU) minus the SMs reserved with swin_sm_reserve(): the grid size of the persistent kernels (GEMM, attention).
+int persistent_sms();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device); thread-safe (forward runs on the main thread,
+// backward on autograd's worker).  Returns 0 or a cudaError_t (message in swin_last_error()).
+int ensure_dyn_smem(const void* func, int bytes);
 
 #define SWIN_REQUIRE(cond, ...)        \
   do {                                 \

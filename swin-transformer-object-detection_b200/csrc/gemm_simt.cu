@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
   __shared__ float As[SBK][SBM + 4];
   __shared__ float Bs[SBK][SBN + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+  const int m0 = blockIdx.x * SBM, n0 = blockIdx.y * SBN;      // M tiles on gridDim.x (2^31 limit): M = B*H*W rows can exceed 65535 * 64
   const int k0 = blockIdx.z * k_per_split;
   const int k1 = min(K, k0 + k_per_split);
   float acc[4][4];
@@ -85,7 +85,7 @@ int gemm_simt(const swin_gemm_args* a, cudaStream_t st) {
   }
   int kps = ceil_div(ceil_div(a->K, splits), SBK) * SBK;
   splits = ceil_div(a->K, kps);
-  dim3 grid(gx, gy, splits);
+  dim3 grid(gy, gx, splits);
   gemm_simt_kernel<<<grid, 256, 0, st>>>((const float*)a->A, sam, sak, (const float*)a->B, sbn, sbk, a->K, kps, p);
   SWIN_LAUNCH_CHECK();
   if (a->colsum_a != nullptr) {

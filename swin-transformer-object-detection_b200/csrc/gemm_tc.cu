@@ -636,7 +636,7 @@ static int choose_tiles(const swin_gemm_args* a, GemmTcParams* pp) {
   p.n_tiles = a->N / p.block_n;
   p.kb_total = ceil_div(a->K, TBK);
   p.K = a->K;
-  p.splits = a->epilogue == SWIN_EPI_ATOMIC_ADD ? pick_splits(p.m_tiles * p.n_tiles, p.kb_total, kNumSMs / p.ctas) : 1;
+  p.splits = a->epilogue == SWIN_EPI_ATOMIC_ADD ? pick_splits(p.m_tiles * p.n_tiles, p.kb_total, persistent_sms() / p.ctas) : 1;
   p.kb_per_split = ceil_div(p.kb_total, p.splits);
   p.splits = ceil_div(p.kb_total, p.kb_per_split);
   return 0;
@@ -726,17 +726,11 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
   }
   const size_t smem = (size_t)p.stages * stage_bytes + epi_bytes + 1024;
   const int total_units = p.m_tiles * p.n_tiles * p.splits;
-  const int slots = kNumSMs / p.ctas;                          // CTAs, or CTA pairs (one per TPC)
+  const int slots = persistent_sms() / p.ctas;                          // CTAs, or CTA pairs (one per TPC)
   const int grid = (total_units < slots ? total_units : slots) * p.ctas;
 #define LAUNCH_TC(AM, BM, TE, CT)                                                                                 \
   do {                                                                                                            \
-    static bool attr_done = false;                                                                                \
-    if (!attr_done) {                                                                                             \
-      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AM, BM, TE, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           212 * 1024);                                                           \
-      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }      \
-      attr_done = true;                                                                                           \
-    }                                                                                                             \
+    { const int ar = ensure_dyn_smem((const void*)gemm_tc_kernel<AM, BM, TE, CT>, 212 * 1024); if (ar) return ar; }  \
     cudaLaunchConfig_t cfg = {};                                                                                  \
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)gemm_threads(TE));                          \
     cfg.dynamicSmemBytes = smem; cfg.stream = st;                                                                 \

@@ -3,6 +3,7 @@
 Each Function is one reference operator (forward + hand-written backward):
   SwinBlockFn        SwinTransformerBlock.forward   mmdet/models/backbones/swin_transformer.py:198-255
   WindowAttentionFn  WindowAttention.forward        :121-153
+  MlpFn              Mlp.forward                    :32-38 (stand-alone calls; inside a block the MLP is part of SwinBlockFn)
   PatchMergingFn     PatchMerging.forward           :271-298
 Gradients of parameters are RETURNED (not accumulated in place) so AccumulateGrad hooks — and
 therefore the bucketed NCCL all-reduce in ddp.py — fire per parameter during backward.
@@ -135,22 +136,34 @@ class SwinBlockFn(torch.autograd.Function):
             dy2, dfc2b = got                         # emitted by the next block's LN1 backward (BlockLink)
         else:
             dy2, dfc2b = ops.scale_cast(dx2, s2, 0, B, H, W, Cc, 1, 0, dt, want_colsum=True, colsum_out=dfc2b_buf)  # (T, C) + bias grad
-        ops.gemm(dy2, h, Cc, hid, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc2w)
+        # weight gradients of frozen Linears (requires_grad False: frozen_stages, REF:557-572) are not computed at all
+        need = ctx.needs_input_grad
+        n_qkv, n_proj, n_fc1, n_fc2 = need[4] or need[5], need[6] or need[7], need[10] or need[11], need[12] or need[13]
+        if n_fc2:
+            ops.gemm(dy2, h, Cc, hid, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc2w)
         du = ops.gemm(dy2, _w(fc2w, dt), T, hid, Cc, b_trans=True, epilogue=L.EPI_DGELU, aux=u)
-        ops.gemm(du, xn, hid, Cc, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc1w, colsum_a=dfc1b)
+        if n_fc1:
+            ops.gemm(du, xn, hid, Cc, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc1w, colsum_a=dfc1b)
         dxn = ops.gemm(du, _w(fc1w, dt), T, Cc, hid, b_trans=True)
         # LN2 backward + residual-gradient add; the same kernel also emits dY of the proj Linear (drop-path scaled,
         # cast and partitioned into window slots) and its column sums (= d proj.bias)
         dx1, dn2w, dn2b, dy1, dprojb = ops.ln_bwd(0, dxn, x1, n2w.detach(), mean2, rstd2, dx2, B, H, W, Cc, 1, 0,
                                                   emit_windows=(ws, shift, s1), dgb=dgb2)
         # ---- attention branch
-        ops.gemm(dy1, o, Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dprojw)
+        if n_proj:
+            ops.gemm(dy1, o, Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dprojw)
         do = ops.gemm(dy1, _w(projw, dt), Tp, Cc, Cc, b_trans=True)
         dqkv, dbias = ops.window_attn_bwd(qkv.view(-1, N, 3 * Cc), o, do.view(-1, N, Cc), lse, bias, mask, Tp // N, nH, ws, scale, mask_nz, canon,
                                           dbias=dbias_buf)
-        dtable = ops.rel_bias_reduce(dbias, ws, out=dtable_buf)
+        dtable = ops.rel_bias_reduce(dbias, ws, out=dtable_buf) if need[3] else None
         dqkvb = dqkvb_buf if has_qkvb else None
-        ops.gemm(dqkv, xw, 3 * Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dqkvw, colsum_a=dqkvb)
+        if n_qkv:
+            ops.gemm(dqkv, xw, 3 * Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dqkvw, colsum_a=dqkvb)
+        if not (need[0] or need[1] or need[2]):
+            # first trainable block behind frozen stages: nothing upstream wants dx, norm1 is frozen too
+            return (None, None, None, dtable, dqkvw if need[4] else None, dqkvb if need[5] else None, dprojw if need[6] else None,
+                    dprojb if need[7] else None, dn2w, dn2b, dfc1w if need[10] else None, dfc1b if need[11] else None,
+                    dfc2w if need[12] else None, dfc2b if need[13] else None) + (None,) * 15
         dxw = ops.gemm(dqkv.view(Tp, 3 * Cc), _w(qkvw, dt), Tp, Cc, 3 * Cc, b_trans=True)
         if ctx.send is not None:
             # also emit the previous block's fc2 dY (its drop-path scale, compute dtype, token order: "windows" of one token)
@@ -159,8 +172,47 @@ class SwinBlockFn(torch.autograd.Function):
             ctx.send.deposit(dx, dyp, csp)
         else:
             dx, dn1w, dn1b = ops.ln_bwd(1, dxw, x, n1w.detach(), mean1, rstd1, dx1, B, H, W, Cc, ws, shift, dgb=dgb1)
-        return (dx, dn1w, dn1b, dtable, dqkvw, dqkvb, dprojw, dprojb, dn2w, dn2b, dfc1w, dfc1b, dfc2w, dfc2b,
-                None, None, None, None, None, None, None, None, None, None, None, None, None, None, None)
+        return (dx, dn1w, dn1b, dtable, dqkvw if need[4] else None, dqkvb if need[5] else None, dprojw if need[6] else None,
+                dprojb if need[7] else None, dn2w, dn2b, dfc1w if need[10] else None, dfc1b if need[11] else None,
+                dfc2w if need[12] else None, dfc2b if need[13] else None) + (None,) * 15
+
+
+class MlpFn(torch.autograd.Function):
+    """Mlp.forward (REF:32-38) called on its own: x (..., Cin) -> fc2(GELU_erf(fc1(x))), the same two GEMM kernels the fused
+    block uses (fc1 with the GELU epilogue, which also saves gelu'(u) for backward) without LayerNorm / residual."""
+
+    @staticmethod
+    def forward(ctx, x, fc1w, fc1b, fc2w, fc2b, dt):
+        Cin, hid, Cout = fc1w.shape[1], fc1w.shape[0], fc2w.shape[0]
+        xin = _f32c(x).view(-1, Cin)
+        rows = xin.shape[0]
+        xa = xin if dt == L.F32 else ops.scale_cast(xin, None, 0, 1, rows, 1, Cin, 1, 0, dt)
+        xa = xa.view(rows, Cin)
+        u = torch.empty((rows, hid), dtype=xa.dtype, device=x.device)
+        h = ops.gemm(xa, _w(fc1w, dt), rows, hid, Cin, bias=None if fc1b is None else fc1b.detach(), epilogue=L.EPI_GELU, out2=u)
+        y = ops.gemm(h, _w(fc2w, dt), rows, Cout, hid, bias=None if fc2b is None else fc2b.detach(), out_dtype=L.F32)
+        ctx.save_for_backward(fc1w, fc2w, xa, u, h)
+        ctx.cfg = (tuple(x.shape), x.dtype, dt, fc1b is not None, fc2b is not None)
+        return y.view(tuple(x.shape[:-1]) + (Cout,)).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        fc1w, fc2w, xa, u, h = ctx.saved_tensors
+        xshape, xdtype, dt, has_b1, has_b2 = ctx.cfg
+        Cin, hid, Cout = fc1w.shape[1], fc1w.shape[0], fc2w.shape[0]
+        rows = xa.shape[0]
+        dyf = _f32c(dy).view(rows, Cout)
+        dy2 = dyf if dt == L.F32 else ops.scale_cast(dyf, None, 0, 1, rows, 1, Cout, 1, 0, dt)
+        dy2 = dy2.view(rows, Cout)
+        dfc2b = ops.colsum(dy2) if has_b2 else None
+        dfc2w = torch.zeros_like(fc2w, dtype=torch.float32)
+        ops.gemm(dy2, h, Cout, hid, rows, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc2w)
+        du = ops.gemm(dy2, _w(fc2w, dt), rows, hid, Cout, b_trans=True, epilogue=L.EPI_DGELU, aux=u)
+        dfc1b = ops.colsum(du) if has_b1 else None
+        dfc1w = torch.zeros_like(fc1w, dtype=torch.float32)
+        ops.gemm(du, xa, hid, Cin, rows, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc1w)
+        dx = ops.gemm(du, _w(fc1w, dt), rows, Cin, hid, b_trans=True, out_dtype=L.F32)
+        return dx.view(xshape).to(xdtype), dfc1w, dfc1b, dfc2w, dfc2b, None
 
 
 class WindowAttentionFn(torch.autograd.Function):

@@ -66,6 +66,7 @@ def _p(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _chk(*ts: Optional[torch.Tensor]) -> None:
+    dev = None
     for t in ts:
         if t is None:
             continue
@@ -73,6 +74,14 @@ def _chk(*ts: Optional[torch.Tensor]) -> None:
             raise RuntimeError("swin_b200 ops need CUDA tensors (no CPU fallback exists)")
         if not t.is_contiguous():
             raise RuntimeError("swin_b200 ops need contiguous tensors")
+        if dev is None:
+            # kernels are enqueued on the CURRENT device's current stream: the operands must live there
+            dev = t.device
+            if dev.index != torch.cuda.current_device():
+                raise RuntimeError(f"swin_b200 ops: tensor on {dev} but the current CUDA device is {torch.cuda.current_device()} "
+                                   "(wrap the call in torch.cuda.device(tensor.device))")
+        elif t.device != dev:
+            raise RuntimeError(f"swin_b200 ops: operands on different devices ({dev} and {t.device})")
 
 
 def torch_dtype(code: int) -> torch.dtype:

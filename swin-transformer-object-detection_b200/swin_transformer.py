@@ -21,7 +21,7 @@ import torch.utils.checkpoint as cp
 
 from . import _lib as L
 from . import ops
-from .functional import BlockLink, OutNormFn, OutNormMergeFn, PatchEmbedFn, PatchMergingFn, SwinBlockFn, WindowAttentionFn
+from .functional import BlockLink, MlpFn, OutNormFn, OutNormMergeFn, PatchEmbedFn, PatchMergingFn, SwinBlockFn, WindowAttentionFn
 from .registry import register_backbone
 
 
@@ -55,37 +55,39 @@ def window_reverse(windows: torch.Tensor, window_size: int, H: int, W: int) -> t
     return ops.window_reverse(windows.contiguous(), window_size, H, W)
 
 
-_CANON_CACHE = {}
-
-
 def _canonical_grid(mask: torch.Tensor, ws: int, shift: int):
     """(nwh, nww) if ``mask`` is bit-for-bit the canonical SW-MSA mask (REF:370-389) of some window grid with nwh*nww ==
-    mask.shape[0], else (0, 0).  Masks made by BasicLayer.attn_mask carry the answer as an attribute; a mask that
-    arrives from elsewhere (e.g. built by reference code) is compared once against the candidate grids and the verdict
-    is cached per (storage, version), so the attention kernel can evaluate it in closed form instead of reading it."""
+    mask.shape[0], else (0, 0).  Masks made by BasicLayer.attn_mask carry the answer as the ``_swin_canon`` attribute.  A
+    mask that arrives from elsewhere (e.g. built by reference code) is compared against the candidate grids on the device;
+    the verdict is remembered ON THE TENSOR OBJECT together with its version counter -- never under its address, which the
+    caching allocator hands to the next mask of a different grid (3x4 vs 4x3 windows in multi-scale training) -- so a
+    rebuilt mask is verified again and an in-place edit invalidates the verdict."""
     tag = getattr(mask, "_swin_canon", None)
     if tag is not None:
         return tag
     if ws != 7 or shift != 3 or mask.dim() != 3 or mask.shape[1] != ws * ws:
         return (0, 0)
-    key = (mask.data_ptr(), mask._version, tuple(mask.shape), str(mask.device))
-    hit = _CANON_CACHE.get(key)
-    if hit is not None:
-        return hit
+    seen = getattr(mask, "_swin_canon_checked", None)
+    if seen is not None and seen[0] == mask._version:
+        return seen[1]
     if torch.cuda.is_current_stream_capturing():
         return (0, 0)                      # cannot compare (needs a host read) while capturing: honour the tensor
     nW, verdict = mask.shape[0], (0, 0)
+    m32 = mask.detach()
+    if m32.dtype != torch.float32 or not m32.is_contiguous():
+        m32 = m32.float().contiguous()
     for nwh in range(1, nW + 1):
         if nW % nwh:
             continue
         nww = nW // nwh
         cand = ops.shift_mask(nwh * ws, nww * ws, ws, shift, mask.device)
-        if torch.equal(cand, mask):
+        if torch.equal(cand, m32):
             verdict = (nwh, nww)
             break
-    if len(_CANON_CACHE) > 64:
-        _CANON_CACHE.clear()
-    _CANON_CACHE[key] = verdict
+    try:
+        mask._swin_canon_checked = (mask._version, verdict)
+    except Exception:
+        pass
     return verdict
 
 
@@ -122,7 +124,8 @@ class Mlp(nn.Module):
     """fc1 -> GELU(erf) -> fc2 (REF:20-38).  Inside a block the fused path uses these parameters directly;
     called standalone it runs the same GEMM kernels."""
 
-    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0):
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0,
+                 compute_dtype: Optional[str] = None):
         super().__init__()
         if act_layer is not nn.GELU:
             raise NotImplementedError("swin_b200 fuses exact-erf GELU; other activations are not supported")
@@ -132,8 +135,14 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
         self.drop_rate = drop
 
+        self._dt = _dt_code(compute_dtype)
+
     def forward(self, x):
-        raise NotImplementedError("Mlp is executed fused inside SwinTransformerBlock (LN2 + fc1 + GELU + fc2 + residual)")
+        """x (..., in_features) -> (..., out_features).  REF:32-38 (dropout p = 0)."""
+        _need_cuda(x, "Mlp")
+        if self.training and self.drop_rate > 0:
+            raise NotImplementedError("dropout > 0 is not implemented in the fused kernels")
+        return MlpFn.apply(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, self._dt)
 
 
 class WindowAttention(nn.Module):
@@ -173,11 +182,11 @@ class WindowAttention(nn.Module):
         mask_nz = None
         canon = (0, 0)
         if mask is not None:
-            mask = mask.detach().float().contiguous()
+            canon = _canonical_grid(mask, self.window_size[0], self.window_size[0] // 2)    # on the caller's tensor object
             mask_nz = getattr(mask, "_swin_nz", None)
+            mask = mask.detach().float().contiguous()
             if mask_nz is None:
                 mask_nz = ops.mask_nonzero(mask)
-            canon = _canonical_grid(mask, self.window_size[0], self.window_size[0] // 2)
         return WindowAttentionFn.apply(x, self.relative_position_bias_table, self.qkv.weight, self.qkv.bias,
                                        self.proj.weight, self.proj.bias, mask, mask_nz, canon, self.window_size[0], self.num_heads,
                                        float(self.scale), self._dt)
@@ -198,7 +207,7 @@ class SwinTransformerBlock(nn.Module):
         self.attn = WindowAttention(dim, _pair(window_size), num_heads, qkv_bias, qk_scale, attn_drop, drop, compute_dtype)
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
         self.norm2 = norm_layer(dim)
-        self.mlp = Mlp(dim, int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio), act_layer=act_layer, drop=drop, compute_dtype=compute_dtype)
         self.H = None
         self.W = None
         self._drop = drop
@@ -223,8 +232,7 @@ class SwinTransformerBlock(nn.Module):
             if mask_nz is None:
                 mask_nz = ops.mask_nonzero(mask)
             # the mask built by BasicLayer.attn_mask is the canonical one: the kernel evaluates it in closed form
-            canon = _canonical_grid(mask_matrix if getattr(mask_matrix, "_swin_canon", None) is not None else mask,
-                                    self.window_size, self.shift_size)
+            canon = _canonical_grid(mask_matrix, self.window_size, self.shift_size)
         s1 = s2 = None
         if isinstance(self.drop_path, DropPath):
             s1 = self.drop_path.sample_scale(x)      # attention-branch draw first, then MLP (REF:252-253)

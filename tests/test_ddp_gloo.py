@@ -33,7 +33,7 @@ def _worker(rank, world, port, ret):
     if rank == 1:                                   # rank 1 starts from different weights: broadcast must fix it
         for p in net.parameters():
             p.data.add_(1.0)
-    ddp = BucketedGradAllReduce(net, bucket_mb=0.01)    # tiny buckets -> several buckets
+    ddp = BucketedGradAllReduce(net, bucket_mb=0.01, tail_kb=0.5)    # tiny buckets -> several buckets + a small tail bucket
     assert len(ddp.buckets) > 2
     g = torch.Generator().manual_seed(1)
     x = torch.randn(8, 16, generator=g)

@@ -115,6 +115,32 @@ def test_backbone_tiny_vs_reference_fixture(mode):
     check_grads(net, lambda k: torch.from_numpy(d["g_" + k]), TOL[mode])
 
 
+def _exception_ceilings():
+    import json
+    path = os.path.join(GOLDEN, "bf16_exceptions.json")
+    if not os.path.isfile(path):
+        return {}
+    with open(path) as f:
+        return json.load(f)
+
+
+def _record_exceptions(tag, over):
+    """Every parameter gradient whose bf16 error exceeds the north-star's 2e-2, with the error and the oracle's own
+    autocast-bf16 floor for the same tensor, printed and written to gpurun_out/parity_exceptions_<tag>.json."""
+    import json
+    rows = [{"tensor": k, "rel_l2": e, "oracle_autocast_floor": fl} for k, e, fl in sorted(over, key=lambda r: -r[1])]
+    print(f"[parity] {tag}: {len(rows)} parameter gradients above 2e-2 (bounded by 1.25 x the oracle's bf16 floor)")
+    for r in rows:
+        print(f"[parity]   {r['tensor']:60s} err {r['rel_l2']:.4f}  floor {r['oracle_autocast_floor']:.4f}")
+    out = os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, f"parity_exceptions_{tag}.json"), "w") as f:
+            json.dump(rows, f, indent=1)
+    except OSError:
+        pass
+
+
 def _oracle_run(params, img, cfg, cots, drop_scales=None, autocast=False):
     p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     im = img.clone().requires_grad_(True)
@@ -171,14 +197,23 @@ def _backbone_vs_oracle(SWIN_T, mode, B, HW):
         check_grads(net, lambda k: grads_r[k], TOL[mode])
     else:
         _, _, grads_ac = _oracle_run(params, img, SWIN_T, cots, autocast=True)
-        bad, worst = [], 0.0
+        bad, over = [], []
         for k, v in net.named_parameters():
             e = so.rel_l2(v.grad, grads_r[k])
             floor = so.rel_l2(grads_ac[k], grads_r[k])
-            worst = max(worst, e)
+            if not e < TOL[mode]:
+                over.append((k, e, floor))                 # takes the noise-floor exception: recorded and printed
             if not e < max(TOL[mode], 1.25 * floor if floor > 1e-2 else 0.0):
                 bad.append((k, e, floor))
+        tag = f"C{SWIN_T['embed_dim']}_d{'-'.join(map(str, SWIN_T['depths']))}_B{B}_{HW[0]}x{HW[1]}"
+        _record_exceptions(tag, over)
         assert not bad, bad
+        # committed ceiling (tests/golden/bf16_exceptions.json): WHICH tensors may exceed 2e-2 and by how much is pinned, so a
+        # regression inside the exception class cannot hide behind the oracle's own bf16 noise floor
+        ceil = _exception_ceilings().get(tag)
+        if ceil is not None:
+            loose = [(k, e, ceil.get(k)) for k, e, _ in over if e > ceil.get(k, 0.0)]
+            assert not loose, f"gradients above 2e-2 AND above their committed ceiling: {loose}"
 
 
 def test_drop_path_train_mode_matches_oracle_with_same_draws():
@@ -255,6 +290,40 @@ def test_untagged_canonical_mask_is_detected_and_matches():
     odd[0, 0, 1] = -100.0
     assert _canonical_grid(odd, ws, 3) == (0, 0)
     assert not torch.equal(blk(x, odd), y_tag)
+    # an in-place edit of a verified mask invalidates the verdict (version counter), it is not served from a cache
+    plain[0, 0, 1] = -100.0
+    assert _canonical_grid(plain, ws, 3) == (0, 0)
+    assert torch.equal(blk(x, plain), blk(x, odd))
+
+
+def test_rebuilt_masks_of_swapped_grids_are_not_confused():
+    """masks rebuilt every forward (as the reference's BasicLayer does) are freed and re-allocated at the same
+    address.  Two grids with the same nW (3x4 vs 4x3 windows) must each be evaluated as what they are."""
+    import swin_b200
+    C, nH, ws = 32, 1, 7
+    attn = swin_b200.WindowAttention(C, (ws, ws), nH, compute_dtype="bf16").to(DEV)
+    with torch.no_grad():
+        attn.relative_position_bias_table.normal_(0, 0.5)
+    x = torch.randn(12, ws * ws, C, device=DEV)
+    outs, ptrs = {}, []
+    for rep in range(3):
+        for (H, W) in ((3 * ws, 4 * ws), (4 * ws, 3 * ws)):
+            m = torch.from_numpy(so.shift_mask_np(H, W, ws, 3)).to(DEV)       # fresh, untagged tensor every time
+            ptrs.append(m.data_ptr())
+            y = attn(x, m)
+            outs.setdefault((H, W), []).append(y)
+            del m
+    a, b = outs[(3 * ws, 4 * ws)], outs[(4 * ws, 3 * ws)]
+    assert all(torch.equal(a[0], t) for t in a) and all(torch.equal(b[0], t) for t in b)
+    assert not torch.equal(a[0], b[0])
+    # cross-check each against the fp32 reference arithmetic on the same mask
+    for (H, W), ys in outs.items():
+        m = torch.from_numpy(so.shift_mask_np(H, W, ws, 3))
+        p = {"qkv.weight": attn.qkv.weight.detach().cpu(), "qkv.bias": attn.qkv.bias.detach().cpu(),
+             "proj.weight": attn.proj.weight.detach().cpu(), "proj.bias": attn.proj.bias.detach().cpu(),
+             "relative_position_bias_table": attn.relative_position_bias_table.detach().cpu()}
+        want = so.window_attention(x.cpu(), p, "", nH, ws, m)
+        assert so.rel_l2(ys[0], want) < 2e-2
 
 
 @pytest.mark.gpu
