@@ -352,7 +352,7 @@ def seeded_params(shapes: Dict[str, Tuple[int, ...]], seed: int = 0, std: float 
         else:
             fan_in = shape[-1]
             a = rng.standard_normal(shape) * (1.0 / math.sqrt(fan_in) if noisy else std)
-        out[name] = torch.from_numpy(np.asarray(a, dtype=np.float64)).to(dtype)
+        out[name] = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), shape))).to(dtype)
     return out
 
 

@@ -212,7 +212,7 @@ def _backbone_vs_oracle(SWIN_T, mode, B, HW):
         # regression inside the exception class cannot hide behind the oracle's own bf16 noise floor
         ceil = _exception_ceilings().get(tag)
         if ceil is not None:
-            loose = [(k, e, ceil.get(k)) for k, e, _ in over if e > ceil.get(k, 0.0)]
+            loose = [(k, e, ceil.get(k)) for k, e, _ in over if e > float(ceil.get(k, 0.0))]
             assert not loose, f"gradients above 2e-2 AND above their committed ceiling: {loose}"
 
 
