@@ -210,6 +210,34 @@ typedef struct swin_attn_args {
 int swin_window_attn_fwd(const swin_attn_args* a, void* stream);
 int swin_window_attn_bwd(const swin_attn_args* a, void* stream);
 
+/* ---------------------------------------------------------------- fused QKV projection + window attention, REF:128-150
+ * One kernel for  qkv = x Wqkv^T + bqkv ; out = softmax(scale q k^T + bias + mask) v :  the window rows x are read once and
+ * Q / K / V never touch HBM (unless qkv_out is given).  bf16 operands, window 7, head_dim 32; the weight must fit in shared
+ * memory next to the pipeline (swin_window_attn_qkv_supported: C <= 96 today, i.e. stage 0 of Swin-T / Swin-S).
+ *   x     (B_*N, C)   bf16  LayerNorm'd, shifted, partitioned window rows (swin_ln_fwd mode 1)
+ *   wqkv  (3C, C)     bf16  qkv.weight, rows [q|k|v] x [head] x [32] (REF:129);  bqkv (3C) fp32 or NULL
+ *   bias  (nH,N,N)    fp32  (swin_rel_bias_expand);  mask / mask_nz / canon_* as in swin_attn_args
+ *   out   (B_, N, C)  bf16 ; lse (B_, nH, N) fp32 or NULL (inference)
+ *   qkv_out (B_, N, 3C) bf16 or NULL: also write q, k, v (what swin_window_attn_bwd reads)
+ */
+typedef struct swin_attn_qkv_args {
+  int B_, nH, ws, nW;
+  float scale;
+  const void* x;
+  const void* wqkv;
+  const float* bqkv;
+  const float* bias;
+  const float* mask;
+  const int32_t* mask_nz;
+  int canon_nwh, canon_nww;
+  void* out;
+  float* lse;
+  void* qkv_out;
+} swin_attn_qkv_args;
+int swin_window_attn_qkv_fwd(const swin_attn_qkv_args* a, void* stream);
+/* 1 if the fused kernel can run this shape (no CUDA call), else 0. */
+int swin_window_attn_qkv_supported(int C, int nH, int ws);
+
 #ifdef __cplusplus
 }
 #endif

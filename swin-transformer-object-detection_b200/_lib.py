@@ -44,6 +44,12 @@ class AttnArgs(C.Structure):
                 ("dout", vp), ("dqkv", vp), ("dbias", vp)]
 
 
+class AttnQkvArgs(C.Structure):
+    _fields_ = [("B_", c_int), ("nH", c_int), ("ws", c_int), ("nW", c_int), ("scale", c_f32), ("x", vp), ("wqkv", vp), ("bqkv", vp),
+                ("bias", vp), ("mask", vp), ("mask_nz", vp), ("canon_nwh", c_int), ("canon_nww", c_int), ("out", vp), ("lse", vp),
+                ("qkv_out", vp)]
+
+
 # name -> (restype, argtypes): every symbol include/swin_b200.h declares
 SYMBOLS = {
     "swin_version": (c_int, []),
@@ -74,6 +80,8 @@ SYMBOLS = {
     "swin_adamw_step": (c_int, [vp, vp, vp, vp, vp, vp, vp, c_int, C.c_double, C.c_double, C.c_double, C.c_double, c_int, C.c_double, vp]),
     "swin_window_attn_fwd": (c_int, [C.POINTER(AttnArgs), vp]),
     "swin_window_attn_bwd": (c_int, [C.POINTER(AttnArgs), vp]),
+    "swin_window_attn_qkv_fwd": (c_int, [C.POINTER(AttnQkvArgs), vp]),
+    "swin_window_attn_qkv_supported": (c_int, [c_int, c_int, c_int]),
 }
 
 _lib = None

@@ -91,3 +91,8 @@ extern "C" int swin_window_attn_bwd(const swin_attn_args* a, void* stream) {
   set_error("attn: bad dtype %d", a->dtype);
   return -EINVAL;
 }
+extern "C" int swin_window_attn_qkv_fwd(const swin_attn_qkv_args* a, void* stream) {
+  if (!a) { set_error("attn_qkv: null args"); return -EINVAL; }
+  return attn_qkv_fwd(a, (cudaStream_t)stream);
+}
+extern "C" int swin_window_attn_qkv_supported(int C, int nH, int ws) { return attn_qkv_supported(C, nH, ws); }

@@ -406,3 +406,27 @@ def window_attn_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, ls
     with _timed(f"attn_bwd nH={nH}", 768320.0 * B_ * nH if ws == 7 else 0.0, _nb(qkv, dout, dqkv)):
         L.check(L.lib().swin_window_attn_bwd(C.byref(a), _stream()), "window_attn_bwd")
     return dqkv, dbias
+
+
+def window_attn_qkv_supported(Cc: int, nH: int, ws: int) -> bool:
+    return bool(L.lib().swin_window_attn_qkv_supported(Cc, nH, ws))
+
+
+def window_attn_qkv_fwd(xw: torch.Tensor, wqkv: torch.Tensor, bqkv: Optional[torch.Tensor], bias: torch.Tensor,
+                        mask: Optional[torch.Tensor], B_: int, nH: int, ws: int, scale: float,
+                        mask_nz: Optional[torch.Tensor] = None, canon=(0, 0), want_qkv: bool = True, want_lse: bool = True):
+    """Fused qkv Linear + window attention (REF:128-150): xw (B_*N, C) bf16 -> (out (B_, N, C), lse, qkv or None)."""
+    _chk(xw, wqkv, bqkv, bias, mask, mask_nz)
+    assert xw.dtype == torch.bfloat16 and wqkv.dtype == torch.bfloat16
+    N, Cc = ws * ws, nH * 32
+    out = torch.empty((B_, N, Cc), dtype=xw.dtype, device=xw.device)
+    lse = torch.empty((B_, nH, N), dtype=torch.float32, device=xw.device) if want_lse else None
+    qkv = torch.empty((B_, N, 3 * Cc), dtype=xw.dtype, device=xw.device) if want_qkv else None
+    a = L.AttnQkvArgs(B_=B_, nH=nH, ws=ws, nW=0 if mask is None else mask.shape[0], scale=scale, x=_p(xw), wqkv=_p(wqkv), bqkv=_p(bqkv),
+                      bias=_p(bias), mask=_p(mask), mask_nz=_p(mask_nz), canon_nwh=canon[0], canon_nww=canon[1], out=_p(out), lse=_p(lse),
+                      qkv_out=_p(qkv))
+    _count()
+    flops = 2.0 * B_ * N * Cc * 3 * Cc + 307328.0 * B_ * nH
+    with _timed(f"attn_qkv_fwd nH={nH}", flops, _nb(xw, out, qkv)):
+        L.check(L.lib().swin_window_attn_qkv_fwd(C.byref(a), _stream()), "window_attn_qkv_fwd")
+    return out, lse, qkv

@@ -173,3 +173,51 @@ def test_two_gpu_nccl_sharded_gradients_equal_full_batch():
     sys.stderr.write(r.stderr[-3000:])
     assert r.returncode == 0
     assert "DDP_NCCL_OK" in r.stdout
+
+
+@pytest.mark.parametrize("nH,B_,mask_kind", [(3, 22, "none"), (3, 24, "canon"), (3, 24, "tensor"), (2, 7, "none"), (1, 12, "canon"),
+                                             (3, 1, "none"), (3, 4000, "canon")])
+def test_fused_qkv_attention_matches_separate_kernels(nH, B_, mask_kind):
+    """swin_window_attn_qkv_fwd (qkv projection inside the attention kernel, REF:128-150) against the qkv GEMM + the
+    stand-alone attention kernel on the same bf16 inputs, and both against the fp32 arithmetic of the oracle."""
+    from swin_b200 import ops
+    from swin_b200 import _lib as L
+    ws, N, C = 7, 49, 32 * nH
+    if not ops.window_attn_qkv_supported(C, nH, ws):
+        pytest.skip("shape not supported by the fused kernel")
+    g = torch.Generator(device=DEV).manual_seed(nH * 1000 + B_)
+    xw = (torch.randn(B_ * N, C, device=DEV, generator=g)).bfloat16()
+    w = (torch.randn(3 * C, C, device=DEV, generator=g) / C ** 0.5).bfloat16()
+    b = torch.randn(3 * C, device=DEV, generator=g) * 0.3
+    table = torch.randn((2 * ws - 1) ** 2, nH, device=DEV, generator=g) * 0.5
+    bias = ops.rel_bias_expand(table, ws)
+    mask = mnz = None
+    canon = (0, 0)
+    if mask_kind != "none":
+        grid = {24: (2, 2), 12: (2, 2), 4000: (4, 5)}[B_]
+        mask = torch.from_numpy(so.shift_mask_np(grid[0] * ws, grid[1] * ws, ws, 3)).to(DEV)
+        mnz = ops.mask_nonzero(mask)
+        if mask_kind == "canon":
+            canon = grid
+        else:
+            mask = mask * (torch.rand(mask.shape, device=DEV, generator=g) > 0.3).float()      # an arbitrary additive mask
+            mnz = ops.mask_nonzero(mask)
+    scale = 32 ** -0.5
+    qkv_ref = ops.gemm(xw, w, B_ * N, 3 * C, C, bias=b)
+    o_ref, lse_ref = ops.window_attn_fwd(qkv_ref.view(B_, N, 3 * C), bias, mask, B_, nH, ws, scale, mnz, canon)
+    o, lse, qkv = ops.window_attn_qkv_fwd(xw, w, b, bias, mask, B_, nH, ws, scale, mnz, canon, want_qkv=True)
+    torch.cuda.synchronize()
+    assert so.rel_l2(qkv.view(-1, 3 * C), qkv_ref) < 1e-3
+    assert so.rel_l2(o, o_ref) < 4e-3, so.rel_l2(o, o_ref)
+    assert torch.allclose(lse, lse_ref, rtol=1e-3, atol=2e-3)
+    # inference variant: no qkv, no lse
+    o2, lse2, qkv2 = ops.window_attn_qkv_fwd(xw, w, b, bias, mask, B_, nH, ws, scale, mnz, canon, want_qkv=False, want_lse=False)
+    assert qkv2 is None and lse2 is None and torch.equal(o2, o)
+    # fp32 arithmetic
+    xf, wf = xw.float().cpu(), w.float().cpu()
+    qkvf = (xf @ wf.t() + b.cpu()).view(B_, N, 3, nH, 32).permute(2, 0, 3, 1, 4)
+    s = (qkvf[0] * scale) @ qkvf[1].transpose(-1, -2) + bias.cpu()[None]
+    if mask is not None:
+        s = s + mask.cpu()[torch.arange(B_) % mask.shape[0]][:, None]
+    want = (torch.softmax(s, -1) @ qkvf[2]).transpose(1, 2).reshape(B_, N, C)
+    assert so.rel_l2(o, want) < 1.5e-2, so.rel_l2(o, want)
