@@ -29,6 +29,7 @@ constexpr int QN = 49;             // tokens per window (ws = 7)
 constexpr int kQThreads = 320;
 constexpr int kRelLd = 52;         // rel-bias row pitch (floats): 49 columns + 3 x kNegBigQ
 constexpr float kNegBigQ = -1.0e30f;
+constexpr size_t kMaxDynSmem = 227 * 1024 - 4096;     // opt-in limit minus head-room for the kernel's static shared memory
 constexpr uint32_t kQkvTileBytes = 3 * 8192;    // Q, K, V operand tiles of one group: 128 rows x 32 bf16 each (SW64), window 1 at +4096
 constexpr uint32_t kPTileBytes = 16384;         // compact P: 128 rows x 64 bf16 (SW128); later the O staging tile
 constexpr uint32_t kXFull = 16384, kXTail = 8192;      // X k-blocks: 128 rows x 64 (SW128) / x 32 (SW64) bf16
@@ -387,7 +388,7 @@ static size_t attn_qkv_smem(int C, int nH, uint32_t* x_slot, uint32_t* w_head) {
 int attn_qkv_supported(int C, int nH, int ws) {
   if (ws != 7) return 0;
   const size_t s = attn_qkv_smem(C, nH, nullptr, nullptr);
-  return s != 0 && s <= 227 * 1024;
+  return s != 0 && s <= kMaxDynSmem;
 }
 
 int attn_qkv_fwd(const swin_attn_qkv_args* a, cudaStream_t st) {
@@ -398,7 +399,7 @@ int attn_qkv_fwd(const swin_attn_qkv_args* a, cudaStream_t st) {
   const int C = a->nH * QHD;
   AttnQkvParams p;
   const size_t smem = attn_qkv_smem(C, a->nH, &p.x_slot_bytes, &p.w_head_bytes);
-  SWIN_REQUIRE(smem != 0 && smem <= 227 * 1024, "attn_qkv: C = %d does not fit the resident-weight kernel (needs %zu bytes of shared memory)", C, smem);
+  SWIN_REQUIRE(smem != 0 && smem <= kMaxDynSmem, "attn_qkv: C = %d does not fit the resident-weight kernel (needs %zu bytes of shared memory)", C, smem);
   if (a->B_ == 0) return 0;
   p.B_ = a->B_; p.nH = a->nH; p.nW = a->nW > 0 ? a->nW : 1; p.C = C; p.ntiles = (a->B_ + 1) / 2;
   p.nfull = C / 64; p.tail = (C % 64) ? 1 : 0;
@@ -426,7 +427,7 @@ int attn_qkv_fwd(const swin_attn_qkv_args* a, cudaStream_t st) {
   tmQKV = tmOut;
   if (p.write_qkv)
     if ((rc = make_tmap_bf16_2d(&tmQKV, a->qkv_out, (uint64_t)3 * C, rows, (uint64_t)3 * C * 2, QHD, QN, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  rc = ensure_dyn_smem((const void*)attn_qkv_fwd_kernel, 227 * 1024);
+  rc = ensure_dyn_smem((const void*)attn_qkv_fwd_kernel, 0);       // the opt-in maximum minus the kernel's static shared memory
   if (rc) return rc;
   const int sms = persistent_sms();
   const int grid = p.ntiles < sms ? p.ntiles : sms;

@@ -43,6 +43,14 @@ int ensure_dyn_smem(const void* func, int bytes) {
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lk(g_attr_mu);
   if (g_attr_done.count({func, dev})) return 0;
+  if (bytes <= 0) {                             // "as much as this kernel can have": opt-in limit minus its static shared memory
+    cudaFuncAttributes fa;
+    int optin = 0;
+    cudaError_t e0 = cudaFuncGetAttributes(&fa, func);
+    if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e0 != cudaSuccess) { set_error("cudaFuncGetAttributes: %s", cudaGetErrorString(e0)); return (int)e0; }
+    bytes = optin - (int)fa.sharedSizeBytes;
+  }
   cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
   g_attr_done.insert({func, dev});
