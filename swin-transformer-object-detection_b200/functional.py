@@ -23,6 +23,8 @@ from . import _lib as L
 from . import ops
 
 _W16 = {}     # id(param) -> (weakref(param), version, bf16 copy)
+# qkv Linear + window attention as ONE kernel where the weight fits in shared memory (SWIN_FUSE_QKV=0: the two-kernel path, for A/B runs)
+FUSE_QKV_ATTENTION = __import__("os").environ.get("SWIN_FUSE_QKV", "1") != "0"
 
 
 def _w(param: torch.Tensor, dt: int) -> torch.Tensor:
@@ -94,9 +96,15 @@ class SwinBlockFn(torch.autograd.Function):
         # attention branch: LN1 + pad/roll/partition -> qkv -> window attention -> proj + reverse/roll/crop + residual
         xw, mean1, rstd1 = ops.ln_fwd(1, x, n1w.detach(), n1b.detach(), B, H, W, Cc, ws, shift, eps, dt)
         Tp = xw.shape[0] * xw.shape[1]
-        qkv = ops.gemm(xw, _w(qkvw, dt), Tp, 3 * Cc, Cc, bias=None if qkvb is None else qkvb.detach())
         bias = ops.rel_bias_expand(table.detach().contiguous(), ws)
-        o, lse = ops.window_attn_fwd(qkv.view(-1, ws * ws, 3 * Cc), bias, mask, Tp // (ws * ws), nH, ws, scale, mask_nz, canon)
+        if dt == L.BF16 and FUSE_QKV_ATTENTION and ops.window_attn_qkv_supported(Cc, nH, ws):
+            # qkv projection inside the attention kernel (the window rows are read once; q, k, v are written only because
+            # the backward kernel reads them)
+            o, lse, qkv = ops.window_attn_qkv_fwd(xw.view(Tp, Cc), _w(qkvw, dt), None if qkvb is None else qkvb.detach(), bias, mask,
+                                                  Tp // (ws * ws), nH, ws, scale, mask_nz, canon, want_qkv=True)
+        else:
+            qkv = ops.gemm(xw, _w(qkvw, dt), Tp, 3 * Cc, Cc, bias=None if qkvb is None else qkvb.detach())
+            o, lse = ops.window_attn_fwd(qkv.view(-1, ws * ws, 3 * Cc), bias, mask, Tp // (ws * ws), nH, ws, scale, mask_nz, canon)
         x1 = torch.empty_like(x)
         ops.gemm(o, _w(projw, dt), Tp, Cc, Cc, bias=projb.detach(), epilogue=L.EPI_SCATTER_RESIDUAL, out=x1, aux=x,
                  row_scale=s1, geom=geom)
