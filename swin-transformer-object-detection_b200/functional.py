@@ -23,7 +23,7 @@ from . import _lib as L
 from . import ops
 
 _W16 = {}     # id(param) -> (weakref(param), version, bf16 copy)
-# qkv Linear + window attention as ONE kernel where the weight fits in shared memory (SWIN_FUSE_QKV=0: the two-kernel path, for A/B runs)
+# inference: qkv Linear + window attention as ONE kernel where the weight fits in shared memory (SWIN_FUSE_QKV=0: the two-kernel path, for A/B runs)
 FUSE_QKV_ATTENTION = __import__("os").environ.get("SWIN_FUSE_QKV", "1") != "0"
 
 
@@ -97,11 +97,12 @@ class SwinBlockFn(torch.autograd.Function):
         xw, mean1, rstd1 = ops.ln_fwd(1, x, n1w.detach(), n1b.detach(), B, H, W, Cc, ws, shift, eps, dt)
         Tp = xw.shape[0] * xw.shape[1]
         bias = ops.rel_bias_expand(table.detach().contiguous(), ws)
-        if dt == L.BF16 and FUSE_QKV_ATTENTION and ops.window_attn_qkv_supported(Cc, nH, ws):
-            # qkv projection inside the attention kernel (the window rows are read once; q, k, v are written only because
-            # the backward kernel reads them)
+        if dt == L.BF16 and FUSE_QKV_ATTENTION and not any(ctx.needs_input_grad) and ops.window_attn_qkv_supported(Cc, nH, ws):
+            # inference (no backward will run): qkv projection inside the attention kernel -- the window rows are read once and
+            # q, k, v never reach HBM.  With a backward to feed, q / k / v must be written anyway and the two-kernel chain is
+            # as fast (measured, profiles/r02/attn_qkv.txt), so training keeps it.
             o, lse, qkv = ops.window_attn_qkv_fwd(xw.view(Tp, Cc), _w(qkvw, dt), None if qkvb is None else qkvb.detach(), bias, mask,
-                                                  Tp // (ws * ws), nH, ws, scale, mask_nz, canon, want_qkv=True)
+                                                  Tp // (ws * ws), nH, ws, scale, mask_nz, canon, want_qkv=False, want_lse=False)
         else:
             qkv = ops.gemm(xw, _w(qkvw, dt), Tp, 3 * Cc, Cc, bias=None if qkvb is None else qkvb.detach())
             o, lse = ops.window_attn_fwd(qkv.view(-1, ws * ws, 3 * Cc), bias, mask, Tp // (ws * ws), nH, ws, scale, mask_nz, canon)
@@ -233,9 +234,13 @@ class WindowAttentionFn(torch.autograd.Function):
         xin = _f32c(xwin)
         xw = xin if dt == L.F32 else ops.scale_cast(xin, None, 0, 1, rows, 1, Cc, 1, 0, dt)
         xw = xw.view(rows, Cc)
-        qkv = ops.gemm(xw, _w(qkvw, dt), rows, 3 * Cc, Cc, bias=None if qkvb is None else qkvb.detach())
         bias = ops.rel_bias_expand(table.detach().contiguous(), ws)
-        o, lse = ops.window_attn_fwd(qkv.view(B_, N, 3 * Cc), bias, mask, B_, nH, ws, scale, mask_nz, canon)
+        if dt == L.BF16 and FUSE_QKV_ATTENTION and not any(ctx.needs_input_grad) and ops.window_attn_qkv_supported(Cc, nH, ws):
+            o, lse, qkv = ops.window_attn_qkv_fwd(xw, _w(qkvw, dt), None if qkvb is None else qkvb.detach(), bias, mask, B_, nH, ws, scale,
+                                                  mask_nz, canon, want_qkv=False, want_lse=False)
+        else:
+            qkv = ops.gemm(xw, _w(qkvw, dt), rows, 3 * Cc, Cc, bias=None if qkvb is None else qkvb.detach())
+            o, lse = ops.window_attn_fwd(qkv.view(B_, N, 3 * Cc), bias, mask, B_, nH, ws, scale, mask_nz, canon)
         y = ops.gemm(o.view(rows, Cc), _w(projw, dt), rows, Cc, Cc, bias=projb.detach(), out_dtype=L.F32)
         ctx.save_for_backward(table, qkvw, projw, mask, mask_nz, xw, qkv, bias, o, lse)
         ctx.cfg = (B_, N, Cc, ws, nH, scale, dt, qkvb is not None, xwin.dtype, canon)

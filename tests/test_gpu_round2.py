@@ -221,3 +221,32 @@ def test_fused_qkv_attention_matches_separate_kernels(nH, B_, mask_kind):
         s = s + mask.cpu()[torch.arange(B_) % mask.shape[0]][:, None]
     want = (torch.softmax(s, -1) @ qkvf[2]).transpose(1, 2).reshape(B_, N, C)
     assert so.rel_l2(o, want) < 1.5e-2, so.rel_l2(o, want)
+
+
+def test_no_grad_forward_uses_fused_kernel_and_matches_training_forward():
+    """Inference (torch.no_grad) runs stage-0 blocks through the fused QKV + attention kernel; outputs agree with the
+    training-mode forward (two-kernel chain) on the same weights."""
+    import swin_b200
+    from swin_b200 import ops
+
+    class Rec:
+        def __init__(self): self.kinds = []
+        def begin(self, kind, flops=0.0, nbytes=0.0): self.kinds.append(kind)
+        def end(self): pass
+    torch.manual_seed(1)
+    net = swin_b200.SwinTransformer(embed_dim=96, depths=[2, 2], num_heads=[3, 6], out_indices=(0, 1), drop_path_rate=0.0).to(DEV).eval()
+    x = torch.randn(2, 3, 120, 200, device=DEV)
+    rec = Rec()
+    ops.set_kernel_timer(rec)
+    try:
+        with torch.no_grad():
+            outs_ng = net(x)
+        n_fused = sum(k.startswith("attn_qkv_fwd") for k in rec.kinds)
+        rec.kinds.clear()
+        outs_g = net(x.clone().requires_grad_(True))
+        n_fused_g = sum(k.startswith("attn_qkv_fwd") for k in rec.kinds)
+    finally:
+        ops.set_kernel_timer(None)
+    assert n_fused == 2 and n_fused_g == 0          # the two stage-0 blocks (C = 96); C = 192 keeps the two-kernel chain
+    for a, b in zip(outs_ng, outs_g):
+        assert so.rel_l2(a, b) < 5e-3
