@@ -87,7 +87,9 @@ class BlockLink:
 class SwinBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, n1w, n1b, table, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b, mask, mask_nz, s1, s2,
-                H, W, ws, shift, nH, scale, dt, eps, canon=(0, 0), recv=None, send=None):
+                H, W, ws, shift, nH, scale, dt, eps, canon=(0, 0), recv=None, send=None, infer=False):
+        """``infer``: the caller ran under torch.no_grad() (grad mode is always off INSIDE Function.forward, so the module passes
+        it in): nothing is needed for a backward, which lets the attention branch use the fused QKV + attention kernel."""
         B, Lx, Cc = x.shape
         x = _f32c(x)
         geom = (H, W, ws, shift)
@@ -97,7 +99,7 @@ class SwinBlockFn(torch.autograd.Function):
         xw, mean1, rstd1 = ops.ln_fwd(1, x, n1w.detach(), n1b.detach(), B, H, W, Cc, ws, shift, eps, dt)
         Tp = xw.shape[0] * xw.shape[1]
         bias = ops.rel_bias_expand(table.detach().contiguous(), ws)
-        if dt == L.BF16 and FUSE_QKV_ATTENTION and not any(ctx.needs_input_grad) and ops.window_attn_qkv_supported(Cc, nH, ws):
+        if dt == L.BF16 and FUSE_QKV_ATTENTION and infer and ops.window_attn_qkv_supported(Cc, nH, ws):
             # inference (no backward will run): qkv projection inside the attention kernel -- the window rows are read once and
             # q, k, v never reach HBM.  With a backward to feed, q / k / v must be written anyway and the two-kernel chain is
             # as fast (measured, profiles/r02/attn_qkv.txt), so training keeps it.
@@ -172,7 +174,7 @@ class SwinBlockFn(torch.autograd.Function):
             # first trainable block behind frozen stages: nothing upstream wants dx, norm1 is frozen too
             return (None, None, None, dtable, dqkvw if need[4] else None, dqkvb if need[5] else None, dprojw if need[6] else None,
                     dprojb if need[7] else None, dn2w, dn2b, dfc1w if need[10] else None, dfc1b if need[11] else None,
-                    dfc2w if need[12] else None, dfc2b if need[13] else None) + (None,) * 15
+                    dfc2w if need[12] else None, dfc2b if need[13] else None) + (None,) * 16
         dxw = ops.gemm(dqkv.view(Tp, 3 * Cc), _w(qkvw, dt), Tp, Cc, 3 * Cc, b_trans=True)
         if ctx.send is not None:
             # also emit the previous block's fc2 dY (its drop-path scale, compute dtype, token order: "windows" of one token)
@@ -183,7 +185,7 @@ class SwinBlockFn(torch.autograd.Function):
             dx, dn1w, dn1b = ops.ln_bwd(1, dxw, x, n1w.detach(), mean1, rstd1, dx1, B, H, W, Cc, ws, shift, dgb=dgb1)
         return (dx, dn1w, dn1b, dtable, dqkvw if need[4] else None, dqkvb if need[5] else None, dprojw if need[6] else None,
                 dprojb if need[7] else None, dn2w, dn2b, dfc1w if need[10] else None, dfc1b if need[11] else None,
-                dfc2w if need[12] else None, dfc2b if need[13] else None) + (None,) * 15
+                dfc2w if need[12] else None, dfc2b if need[13] else None) + (None,) * 16
 
 
 class MlpFn(torch.autograd.Function):
@@ -228,14 +230,14 @@ class WindowAttentionFn(torch.autograd.Function):
     """x_windows (B_, N, C) -> (B_, N, C): qkv Linear, attention core, proj Linear."""
 
     @staticmethod
-    def forward(ctx, xwin, table, qkvw, qkvb, projw, projb, mask, mask_nz, canon, ws, nH, scale, dt):
+    def forward(ctx, xwin, table, qkvw, qkvb, projw, projb, mask, mask_nz, canon, ws, nH, scale, dt, infer=False):
         B_, N, Cc = xwin.shape
         rows = B_ * N
         xin = _f32c(xwin)
         xw = xin if dt == L.F32 else ops.scale_cast(xin, None, 0, 1, rows, 1, Cc, 1, 0, dt)
         xw = xw.view(rows, Cc)
         bias = ops.rel_bias_expand(table.detach().contiguous(), ws)
-        if dt == L.BF16 and FUSE_QKV_ATTENTION and not any(ctx.needs_input_grad) and ops.window_attn_qkv_supported(Cc, nH, ws):
+        if dt == L.BF16 and FUSE_QKV_ATTENTION and infer and ops.window_attn_qkv_supported(Cc, nH, ws):
             o, lse, qkv = ops.window_attn_qkv_fwd(xw, _w(qkvw, dt), None if qkvb is None else qkvb.detach(), bias, mask, B_, nH, ws, scale,
                                                   mask_nz, canon, want_qkv=False, want_lse=False)
         else:
@@ -263,7 +265,7 @@ class WindowAttentionFn(torch.autograd.Function):
         dqkvw = torch.zeros_like(qkvw, dtype=torch.float32)
         ops.gemm(dqkv.view(rows, 3 * Cc), xw, 3 * Cc, Cc, rows, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dqkvw)
         dx = ops.gemm(dqkv.view(rows, 3 * Cc), _w(qkvw, dt), rows, Cc, 3 * Cc, b_trans=True, out_dtype=L.F32)
-        return dx.view(B_, N, Cc).to(in_dtype), dtable, dqkvw, dqkvb, dprojw, dprojb, None, None, None, None, None, None, None
+        return dx.view(B_, N, Cc).to(in_dtype), dtable, dqkvw, dqkvb, dprojw, dprojb, None, None, None, None, None, None, None, None
 
 
 class PatchMergingFn(torch.autograd.Function):

@@ -189,7 +189,7 @@ class WindowAttention(nn.Module):
                 mask_nz = ops.mask_nonzero(mask)
         return WindowAttentionFn.apply(x, self.relative_position_bias_table, self.qkv.weight, self.qkv.bias,
                                        self.proj.weight, self.proj.bias, mask, mask_nz, canon, self.window_size[0], self.num_heads,
-                                       float(self.scale), self._dt)
+                                       float(self.scale), self._dt, not torch.is_grad_enabled())
 
 
 class SwinTransformerBlock(nn.Module):
@@ -242,7 +242,7 @@ class SwinTransformerBlock(nn.Module):
                                  a.qkv.bias, a.proj.weight, a.proj.bias, self.norm2.weight, self.norm2.bias,
                                  m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, mask, mask_nz, s1, s2,
                                  H, W, self.window_size, self.shift_size, self.num_heads, float(a.scale), self._dt,
-                                 float(self.norm1.eps), canon, recv, send)
+                                 float(self.norm1.eps), canon, recv, send, not torch.is_grad_enabled())
 
 
 class PatchMerging(nn.Module):
