@@ -213,12 +213,13 @@ int swin_window_attn_bwd(const swin_attn_args* a, void* stream);
 /* ---------------------------------------------------------------- fused QKV projection + window attention, REF:128-150
  * One kernel for  qkv = x Wqkv^T + bqkv ; out = softmax(scale q k^T + bias + mask) v :  the window rows x are read once and
  * Q / K / V never touch HBM (unless qkv_out is given).  bf16 operands, window 7, head_dim 32; the weight must fit in shared
- * memory next to the pipeline (swin_window_attn_qkv_supported: C <= 96 today, i.e. stage 0 of Swin-T / Swin-S).
+ * memory next to the pipeline, or -- streamed per head through a ring of k-blocks -- leave room for the 128 x C window-pair
+ * tile (swin_window_attn_qkv_supported: C <= 384, i.e. stages 0-2 of Swin-T / Swin-S, stages 0-1 of Swin-B).
  *   x     (B_*N, C)   bf16  LayerNorm'd, shifted, partitioned window rows (swin_ln_fwd mode 1)
  *   wqkv  (3C, C)     bf16  qkv.weight, rows [q|k|v] x [head] x [32] (REF:129);  bqkv (3C) fp32 or NULL
  *   bias  (nH,N,N)    fp32  (swin_rel_bias_expand);  mask / mask_nz / canon_* as in swin_attn_args
  *   out   (B_, N, C)  bf16 ; lse (B_, nH, N) fp32 or NULL (inference)
- *   qkv_out (B_, N, 3C) bf16 or NULL: also write q, k, v (what swin_window_attn_bwd reads)
+ *   qkv_out (B_, N, 3C) bf16 or NULL: also write q, k, v (what swin_window_attn_bwd reads), TMA-stored from the operand tiles
  */
 typedef struct swin_attn_qkv_args {
   int B_, nH, ws, nW;
@@ -233,8 +234,12 @@ typedef struct swin_attn_qkv_args {
   void* out;
   float* lse;
   void* qkv_out;
+  void* workspace;            /* device scratch of swin_window_attn_qkv_workspace(C, nH, ws) bytes, 16-byte aligned (NULL if 0) */
+  long long workspace_bytes;
 } swin_attn_qkv_args;
 int swin_window_attn_qkv_fwd(const swin_attn_qkv_args* a, void* stream);
+/* bytes of device scratch the fused kernel needs for this shape (the padded, pre-scaled bias table of the streamed-weight mode); 0 = none */
+long long swin_window_attn_qkv_workspace(int C, int nH, int ws);
 /* 1 if the fused kernel can run this shape (no CUDA call), else 0. */
 int swin_window_attn_qkv_supported(int C, int nH, int ws);
 

@@ -47,7 +47,7 @@ class AttnArgs(C.Structure):
 class AttnQkvArgs(C.Structure):
     _fields_ = [("B_", c_int), ("nH", c_int), ("ws", c_int), ("nW", c_int), ("scale", c_f32), ("x", vp), ("wqkv", vp), ("bqkv", vp),
                 ("bias", vp), ("mask", vp), ("mask_nz", vp), ("canon_nwh", c_int), ("canon_nww", c_int), ("out", vp), ("lse", vp),
-                ("qkv_out", vp)]
+                ("qkv_out", vp), ("workspace", vp), ("workspace_bytes", C.c_longlong)]
 
 
 # name -> (restype, argtypes): every symbol include/swin_b200.h declares
@@ -82,6 +82,7 @@ SYMBOLS = {
     "swin_window_attn_bwd": (c_int, [C.POINTER(AttnArgs), vp]),
     "swin_window_attn_qkv_fwd": (c_int, [C.POINTER(AttnQkvArgs), vp]),
     "swin_window_attn_qkv_supported": (c_int, [c_int, c_int, c_int]),
+    "swin_window_attn_qkv_workspace": (C.c_longlong, [c_int, c_int, c_int]),
 }
 
 _lib = None

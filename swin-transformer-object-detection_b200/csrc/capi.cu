@@ -104,3 +104,4 @@ extern "C" int swin_window_attn_qkv_fwd(const swin_attn_qkv_args* a, void* strea
   return attn_qkv_fwd(a, (cudaStream_t)stream);
 }
 extern "C" int swin_window_attn_qkv_supported(int C, int nH, int ws) { return attn_qkv_supported(C, nH, ws); }
+extern "C" long long swin_window_attn_qkv_workspace(int C, int nH, int ws) { return attn_qkv_workspace_bytes(C, nH, ws); }

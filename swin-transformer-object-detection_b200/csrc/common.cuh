@@ -161,5 +161,6 @@ int attn_tc_fwd(const swin_attn_args* a, cudaStream_t st);
 int attn_tc_bwd(const swin_attn_args* a, cudaStream_t st);
 int attn_qkv_fwd(const swin_attn_qkv_args* a, cudaStream_t st);
 int attn_qkv_supported(int C, int nH, int ws);
+long long attn_qkv_workspace_bytes(int C, int nH, int ws);
 
 }  // namespace swin

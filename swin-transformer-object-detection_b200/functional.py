@@ -23,8 +23,16 @@ from . import _lib as L
 from . import ops
 
 _W16 = {}     # id(param) -> (weakref(param), version, bf16 copy)
-# inference: qkv Linear + window attention as ONE kernel where the weight fits in shared memory (SWIN_FUSE_QKV=0: the two-kernel path, for A/B runs)
-FUSE_QKV_ATTENTION = __import__("os").environ.get("SWIN_FUSE_QKV", "1") != "0"
+# inference: qkv Linear + window attention as ONE kernel (SWIN_FUSE_QKV=0: the two-kernel path, for A/B runs).  The kernel runs
+# every C <= 384; it is the default only where it is measured faster than the GEMM + attention pair (resident weights, C <= 128:
+# profiles/r02/attn_qkv.txt) -- SWIN_FUSE_QKV=2 forces it wherever it is supported.
+_FUSE_ENV = __import__("os").environ.get("SWIN_FUSE_QKV", "1")
+FUSE_QKV_ATTENTION = _FUSE_ENV != "0"
+FUSE_QKV_MAX_C = 384 if _FUSE_ENV == "2" else 128
+
+
+def _fuse_qkv(Cc: int, nH: int, ws: int) -> bool:
+    return FUSE_QKV_ATTENTION and Cc <= FUSE_QKV_MAX_C and ops.window_attn_qkv_supported(Cc, nH, ws)
 
 
 def _w(param: torch.Tensor, dt: int) -> torch.Tensor:
@@ -99,7 +107,7 @@ class SwinBlockFn(torch.autograd.Function):
         xw, mean1, rstd1 = ops.ln_fwd(1, x, n1w.detach(), n1b.detach(), B, H, W, Cc, ws, shift, eps, dt)
         Tp = xw.shape[0] * xw.shape[1]
         bias = ops.rel_bias_expand(table.detach().contiguous(), ws)
-        if dt == L.BF16 and FUSE_QKV_ATTENTION and infer and ops.window_attn_qkv_supported(Cc, nH, ws):
+        if dt == L.BF16 and infer and _fuse_qkv(Cc, nH, ws):
             # inference (no backward will run): qkv projection inside the attention kernel -- the window rows are read once and
             # q, k, v never reach HBM.  With a backward to feed, q / k / v must be written anyway and the two-kernel chain is
             # as fast (measured, profiles/r02/attn_qkv.txt), so training keeps it.
@@ -237,7 +245,7 @@ class WindowAttentionFn(torch.autograd.Function):
         xw = xin if dt == L.F32 else ops.scale_cast(xin, None, 0, 1, rows, 1, Cc, 1, 0, dt)
         xw = xw.view(rows, Cc)
         bias = ops.rel_bias_expand(table.detach().contiguous(), ws)
-        if dt == L.BF16 and FUSE_QKV_ATTENTION and infer and ops.window_attn_qkv_supported(Cc, nH, ws):
+        if dt == L.BF16 and infer and _fuse_qkv(Cc, nH, ws):
             o, lse, qkv = ops.window_attn_qkv_fwd(xw, _w(qkvw, dt), None if qkvb is None else qkvb.detach(), bias, mask, B_, nH, ws, scale,
                                                   mask_nz, canon, want_qkv=False, want_lse=False)
         else:

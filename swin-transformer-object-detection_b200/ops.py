@@ -422,10 +422,12 @@ def window_attn_qkv_fwd(xw: torch.Tensor, wqkv: torch.Tensor, bqkv: Optional[tor
     out = torch.empty((B_, N, Cc), dtype=xw.dtype, device=xw.device)
     lse = torch.empty((B_, nH, N), dtype=torch.float32, device=xw.device) if want_lse else None
     qkv = torch.empty((B_, N, 3 * Cc), dtype=xw.dtype, device=xw.device) if want_qkv else None
+    wsb = int(L.lib().swin_window_attn_qkv_workspace(Cc, nH, ws))
+    wsp = torch.empty((wsb // 4,), dtype=torch.float32, device=xw.device) if wsb else None
     a = L.AttnQkvArgs(B_=B_, nH=nH, ws=ws, nW=0 if mask is None else mask.shape[0], scale=scale, x=_p(xw), wqkv=_p(wqkv), bqkv=_p(bqkv),
                       bias=_p(bias), mask=_p(mask), mask_nz=_p(mask_nz), canon_nwh=canon[0], canon_nww=canon[1], out=_p(out), lse=_p(lse),
-                      qkv_out=_p(qkv))
-    _count()
+                      qkv_out=_p(qkv), workspace=_p(wsp), workspace_bytes=wsb)
+    _count(2 if wsb else 1)
     flops = 2.0 * B_ * N * Cc * 3 * Cc + 307328.0 * B_ * nH
     with _timed(f"attn_qkv_fwd nH={nH}", flops, _nb(xw, out, qkv)):
         L.check(L.lib().swin_window_attn_qkv_fwd(C.byref(a), _stream()), "window_attn_qkv_fwd")

@@ -176,7 +176,10 @@ def test_two_gpu_nccl_sharded_gradients_equal_full_batch():
 
 
 @pytest.mark.parametrize("nH,B_,mask_kind", [(3, 22, "none"), (3, 24, "canon"), (3, 24, "tensor"), (2, 7, "none"), (1, 12, "canon"),
-                                             (3, 1, "none"), (3, 4000, "canon")])
+                                             (3, 1, "none"), (3, 4000, "canon"),
+                                             # streamed-weight mode: C = 128 / 192 (two X slots), 256 / 384 (one X slot)
+                                             (4, 24, "canon"), (4, 7, "none"), (6, 24, "tensor"), (6, 4000, "canon"), (8, 24, "canon"),
+                                             (12, 24, "canon"), (12, 1, "none"), (12, 4000, "canon"), (12, 777, "none")])
 def test_fused_qkv_attention_matches_separate_kernels(nH, B_, mask_kind):
     """swin_window_attn_qkv_fwd (qkv projection inside the attention kernel, REF:128-150) against the qkv GEMM + the
     stand-alone attention kernel on the same bf16 inputs, and both against the fp32 arithmetic of the oracle."""
@@ -247,6 +250,6 @@ def test_no_grad_forward_uses_fused_kernel_and_matches_training_forward():
         n_fused_g = sum(k.startswith("attn_qkv_fwd") for k in rec.kinds)
     finally:
         ops.set_kernel_timer(None)
-    assert n_fused == 2 and n_fused_g == 0          # the two stage-0 blocks (C = 96); C = 192 keeps the two-kernel chain
+    assert n_fused == 2 and n_fused_g == 0          # the two stage-0 blocks (C = 96, resident weights); C = 192 keeps the two-kernel chain
     for a, b in zip(outs_ng, outs_g):
         assert so.rel_l2(a, b) < 5e-3

@@ -8,7 +8,9 @@ from swin_b200 import ops
 dev = "cuda"
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
-cases = [(22272, 3, True), (22272, 3, False), (22272, 2, False), (22272, 1, False)]
+# stage 0 / 1 / 2 of the benchmark (B = 16, 800x1333: 29x48, 15x24, 8x12 windows per image) + Swin-B widths
+cases = [(22272, 3, True), (22272, 3, False), (5760, 6, True), (1536, 12, True), (22272, 4, True), (5760, 8, True)]
+GRID = {22272: (29, 48), 5760: (15, 24), 1536: (8, 12)}
 if len(sys.argv) > 2:
     cases = cases[:int(sys.argv[2])]
 
@@ -36,9 +38,9 @@ for B_, nH, masked in cases:
     canon = (0, 0)
     if masked:
         from oracle import swin_oracle as so
-        mask = torch.from_numpy(so.shift_mask_np(29 * 7, 48 * 7, 7, 3)).to(dev)     # 1392 windows (stage 0 of 800x1333)
+        canon = GRID[B_]
+        mask = torch.from_numpy(so.shift_mask_np(canon[0] * 7, canon[1] * 7, 7, 3)).to(dev)
         mnz = ops.mask_nonzero(mask)
-        canon = (29, 48)
     sc = 32 ** -0.5
     t_gemm = med(lambda: ops.gemm(xw, w, B_ * 49, 3 * C, C, bias=b))
     qkv = ops.gemm(xw, w, B_ * 49, 3 * C, C, bias=b).view(B_, 49, 3 * C)
