@@ -43,7 +43,6 @@ constexpr uint32_t kGroupBytes = 3 * 8192;      // Q, K, V operand tiles of one 
 constexpr uint32_t kXFull = 16384, kXTail = 8192;      // X k-blocks: 128 rows x 64 (SW128) / x 32 (SW64) bf16
 constexpr uint32_t kWFull = 12288, kWTail = 6144;      // W_h k-blocks: 96 rows x 64 (SW128) / x 32 (SW64) bf16
 constexpr int kMaxWSlots = 12;
-constexpr int kPenRows = 16;       // canonical-mask penalty rows: index = 8 R + 4 Cw + 2 ri + ci (see pen_index)
 
 struct AttnQkvParams {
   int B_, nH, nW, C, ntiles;
@@ -87,14 +86,27 @@ struct SpinGuard {
     if ((++spins & 4095) == 0 && clock64() - t0 > 4000000000LL) { atomicExch(&g_watchdog_flag, 1); __trap(); }
   }
 };
-// Canonical SW-MSA mask (REF:370-389), window 7 / shift 3, as ONE of 16 precomputed penalty rows.  Region ids differ only inside
-// the last window row (R) / column (Cw) of the grid, where tokens with row (column) index >= 4 belong to another region than
-// those < 4:  mask[i][j] = -100  <=>  (R and rowhi(j) != rowhi(i)) or (Cw and colhi(j) != colhi(i)).
-__device__ __forceinline__ int pen_index(int wi, int nwh, int nww, int i) {
-  const int wh = wi / nww, ww = wi - wh * nww;
+// Canonical SW-MSA mask (REF:370-389) in closed form, window 7 / shift 3 (see attn_tc.cu: canon_mask_pen): a key column's
+// (rowhi, colhi) is a compile-time class in the unrolled loops, a row needs four constants pen[rowhi][colhi] in {0, -100 log2 e},
+// and they fold into the "minus the row maximum" constant of the exponent -- the mask costs no per-element instruction.
+struct MaskPenQ { float c[2][2]; };
+__device__ __forceinline__ MaskPenQ canon_pen(bool active, int wi, int nwh, int nww, int i) {
+  MaskPenQ m;
+  bool R = false, Cw = false;
+  if (active) {
+    const int wh = wi / nww, ww = wi - wh * nww;
+    R = wh == nwh - 1; Cw = ww == nww - 1;
+  }
   const int ii = i < QN ? i : QN - 1;
-  return ((wh == nwh - 1) ? 8 : 0) | ((ww == nww - 1) ? 4 : 0) | ((ii / 7 >= 4) ? 2 : 0) | ((ii % 7 >= 4) ? 1 : 0);
+  const bool ri = ii / 7 >= 4, ci = ii % 7 >= 4;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) m.c[a][b] = ((R && ((a != 0) != ri)) || (Cw && ((b != 0) != ci))) ? -100.0f * kLog2eQ : 0.f;
+  return m;
 }
+#define QRH(j) (((j) / 7) >= 4 ? 1 : 0)
+#define QCH(j) (((j) % 7) >= 4 ? 1 : 0)
 
 __global__ void __launch_bounds__(kQThreads, 1)
 attn_qkv_fwd_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_constant__ CUtensorMap tmX64,
@@ -108,18 +120,12 @@ attn_qkv_fwd_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_con
   const uint32_t w_bytes = p.stream_w ? (uint32_t)p.wslots * kWFull : (uint32_t)p.nH * p.w_head_bytes;
   uint8_t* sX = sW + w_bytes;                                       // xslots x x_slot_bytes
   uint8_t* sG = sX + (uint32_t)p.xslots * p.x_slot_bytes;           // 2 groups x {Q, K, V tiles}
-  float* sPen = reinterpret_cast<float*>(sG + 2u * kGroupBytes);    // [16][52] canonical-mask penalties, pre-scaled by log2(e)
-  float* sBq = sPen + kPenRows * kRelLd;                            // 3C qkv bias (zeros if the Linear has none)
+  float* sBq = reinterpret_cast<float*>(sG + 2u * kGroupBytes);     // 3C qkv bias (zeros if the Linear has none)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
 
-  // ---- prologue: zero the X ring (its pad rows 49..63 are never written by TMA), stage the penalty rows and the qkv bias
+  // ---- prologue: zero the X ring (its pad rows 49..63 are never written by TMA), stage the qkv bias
   for (uint32_t o = tid * 16; o < (uint32_t)p.xslots * p.x_slot_bytes; o += kQThreads * 16) *reinterpret_cast<int4*>(sX + o) = make_int4(0, 0, 0, 0);
-  for (int e = tid; e < kPenRows * kRelLd; e += kQThreads) {
-    const int idx = e / kRelLd, j = e - idx * kRelLd;
-    const bool m = j < QN && (((idx & 8) && ((j / 7 >= 4) != ((idx & 2) != 0))) || ((idx & 4) && ((j % 7 >= 4) != ((idx & 1) != 0))));
-    sPen[e] = m ? -100.0f * kLog2eQ : 0.f;
-  }
   for (int e = tid; e < 3 * p.C; e += kQThreads) sBq[e] = p.bqkv != nullptr ? p.bqkv[e] : 0.f;
   if (tid == 0) {
     for (int i = 0; i < B_COUNT; ++i) {
@@ -345,7 +351,7 @@ attn_qkv_fwd_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_con
     QT_DECL
     int mask_k = -1;
     const float* mrow = nullptr;
-    const float* prow = nullptr;                     // canonical-mask penalty row of this thread (warp-uniform null / non-null)
+    MaskPenQ pen = canon_pen(false, 0, 1, 1, i);
     for (int n = g; n < nitems; n += 2) {
       const uint32_t ph = (uint32_t)(n >> 1) & 1;
       QT_ITEM
@@ -376,14 +382,13 @@ attn_qkv_fwd_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_con
       QT(2);
       // ---- (b) S -> P
       if (k != mask_k) {                              // the row's mask depends on the window only: once per tile, not per head
-        mask_k = k; mrow = nullptr; prow = nullptr;
-        if (p.mask != nullptr && win < p.B_) {
-          const int mw = win % p.nW;
-          if (p.canon_nwh > 0) {
-            const int idx = pen_index(mw, p.canon_nwh, p.canon_nww, i);
-            if (idx >= 4) prow = sPen + idx * kRelLd;
-          } else if (valid && (p.mask_nz == nullptr || p.mask_nz[mw])) mrow = p.mask + ((size_t)mw * QN + i) * QN;
+        mask_k = k; mrow = nullptr;
+        bool canon = false;
+        if (p.mask != nullptr && valid) {
+          if (p.canon_nwh > 0) canon = true;
+          else if (p.mask_nz == nullptr || p.mask_nz[win % p.nW]) mrow = p.mask + ((size_t)(win % p.nW) * QN + i) * QN;
         }
+        pen = canon_pen(canon, canon ? win % p.nW : 0, p.canon_nwh, p.canon_nww, i);
       }
       // this row's bias values: 52 coalesced loads (one line per key column across the warp), issued before the wait for S
       float bv[52];
@@ -405,15 +410,6 @@ attn_qkv_fwd_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_con
       f32x2 s2[26];
 #pragma unroll
       for (int c = 0; c < 26; ++c) s2[c] = fma2(pk2u(v[2 * c], v[2 * c + 1]), sc2, pk2(bv[2 * c], bv[2 * c + 1]));
-      if (prow != nullptr) {                          // warp-uniform: a warp's 32 rows belong to one window
-        const float4* p4 = reinterpret_cast<const float4*>(prow);
-#pragma unroll
-        for (int c = 0; c < 13; ++c) {
-          const float4 pp = p4[c];
-          s2[2 * c] = add2(s2[2 * c], pk2(pp.x, pp.y));
-          s2[2 * c + 1] = add2(s2[2 * c + 1], pk2(pp.z, pp.w));
-        }
-      }
       float sv[52];
 #pragma unroll
       for (int c = 0; c < 26; ++c) unpk2(s2[c], sv[2 * c], sv[2 * c + 1]);
@@ -421,22 +417,17 @@ attn_qkv_fwd_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_con
 #pragma unroll
         for (int jj = 0; jj < QN; ++jj) sv[jj] = fmaf(__ldg(mrow + jj), kLog2eQ, sv[jj]);
       }
-      // several independent chains for the row maximum and the row sum: with two softmax warps per scheduler there is little
-      // else to hide the dependent-issue latency of a 49-long serial chain behind
-      float m4[4] = {sv[0], sv[1], sv[2], sv[3]};
+      // row maximum of the MASKED logits from the four class maxima; exponent offset per class = penalty - maximum
+      float cm[2][2] = {{sv[0], sv[4]}, {sv[28], sv[32]}};
 #pragma unroll
-      for (int jj = 4; jj < 48; jj += 4) {
-        m4[0] = fmaxf(m4[0], sv[jj]); m4[1] = fmaxf(m4[1], sv[jj + 1]); m4[2] = fmaxf(m4[2], sv[jj + 2]); m4[3] = fmaxf(m4[3], sv[jj + 3]);
-      }
-      const float mx = fmaxf(fmaxf(fmaxf(m4[0], sv[48]), m4[1]), fmaxf(m4[2], m4[3]));
-      const f32x2 nmx = pk2(-mx, -mx);
+      for (int jj = 1; jj < QN; ++jj) cm[QRH(jj)][QCH(jj)] = fmaxf(cm[QRH(jj)][QCH(jj)], sv[jj]);
+      const float mx = fmaxf(fmaxf(cm[0][0] + pen.c[0][0], cm[0][1] + pen.c[0][1]), fmaxf(cm[1][0] + pen.c[1][0], cm[1][1] + pen.c[1][1]));
+      const float off[2][2] = {{pen.c[0][0] - mx, pen.c[0][1] - mx}, {pen.c[1][0] - mx, pen.c[1][1] - mx}};
       f32x2 acc2[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
       uint32_t pb[26];                                // P row as packed bf16 pairs
 #pragma unroll
       for (int c = 0; c < 26; ++c) {
-        float a, b;
-        unpk2(add2(pk2(sv[2 * c], sv[2 * c + 1]), nmx), a, b);
-        const float ea = ex2f(a), eb = ex2f(b);
+        const float ea = ex2f(sv[2 * c] + off[QRH(2 * c)][QCH(2 * c)]), eb = ex2f(sv[2 * c + 1] + off[QRH(2 * c + 1)][QCH(2 * c + 1)]);
         acc2[c & 1] = add2(acc2[c & 1], pk2(ea, eb));
         pb[c] = pack_bf16(ea, eb);
       }
@@ -510,7 +501,7 @@ QkvPlan attn_qkv_plan(int C, int nH) {
   pl.nfull = C / 64; pl.tail = (C % 64) ? 1 : 0;
   pl.x_slot = pl.nfull * kXFull + pl.tail * kXTail;
   pl.w_head = pl.nfull * kWFull + pl.tail * kWTail;
-  const size_t fixed = 2 * (size_t)kGroupBytes + (size_t)kPenRows * kRelLd * 4 + (size_t)3 * C * 4 + 1024;
+  const size_t fixed = 2 * (size_t)kGroupBytes + (size_t)3 * C * 4 + 1024;
   const size_t resident = fixed + (size_t)nH * pl.w_head + 2 * (size_t)pl.x_slot;
   if (resident <= kMaxDynSmem) {
     pl.ok = 1; pl.stream_w = 0; pl.wslots = 0; pl.xslots = 2; pl.smem = resident;

@@ -14,6 +14,7 @@
 // Backward recomputes S, forms dP = dO V^T, D = rowsum(P*dP), dS = P*(dP - D), and runs
 //     dV = P^T [dO_0|dO_1],  dK = dS^T [Q_0|Q_1],  dQ = dS [K_0|K_1]
 // with MN-major ("transposed") smem descriptors over the same compact P / dS tiles.
+#include <type_traits>
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tma_host.cuh"
@@ -49,19 +50,32 @@ __device__ __forceinline__ void store_row_bf16x8(uint8_t* dst, const float* v) {
 }
 
 
-// Canonical SW-MSA mask (REF:370-389) of one window row in closed form, window 7 / shift 3.  Region ids on the
-// padded grid differ only inside the last window row / column, where tokens with row (col) index >= ws - shift = 4
-// belong to another region than those < 4.  Returns a 49-bit set: bit j = 1 <=> mask[w][i][j] == -100.
-__device__ __forceinline__ unsigned long long canon_mask_bits(int wi, int nwh, int nww, int i) {
-  constexpr unsigned long long kRowHi = 0x1FFFFF0000000ULL;          // j/7 >= 4  <=> j >= 28   (bits 28..48)
-  constexpr unsigned long long kColHi = 0x1C3870E1C3870ULL;          // j%7 >= 4  (bits {4,5,6} + 7k, k = 0..6)
-  constexpr unsigned long long kAll = 0x1FFFFFFFFFFFFULL;
-  const int wh = wi / nww, ww = wi - wh * nww;
-  unsigned long long m = 0ULL;
-  if (wh == nwh - 1) m |= (i / 7 >= 4) ? (~kRowHi & kAll) : kRowHi;
-  if (ww == nww - 1) m |= (i % 7 >= 4) ? (~kColHi & kAll) : kColHi;
+// Canonical SW-MSA mask (REF:370-389) in closed form, window 7 / shift 3.  Region ids on the padded grid differ only inside
+// the last window row (R) / column (Cw) of the grid, where tokens with row (col) index >= ws - shift = 4 belong to another
+// region than those < 4:   mask[i][j] = -100  <=>  (R and rowhi(j) != rowhi(i)) or (Cw and colhi(j) != colhi(i)).
+// For an unrolled key column j, (rowhi(j), colhi(j)) is a compile-time CLASS (4 classes), so a row needs only four
+// constants pen[rowhi][colhi] in {0, -100 log2(e)} -- and since every use of the masked logit is "logit + constant"
+// (minus the row maximum / minus the saved LSE), the mask folds into that constant and costs no per-element instruction.
+struct MaskPen { float c[2][2]; };
+__device__ __forceinline__ MaskPen canon_mask_pen(bool active, int wi, int nwh, int nww, int i) {
+  MaskPen m;
+  const float kPen = -100.0f * 1.4426950408889634f;
+  bool R = false, Cw = false;
+  if (active) {
+    const int wh = wi / nww, ww = wi - wh * nww;
+    R = wh == nwh - 1; Cw = ww == nww - 1;
+  }
+  const int ii = i < AN ? i : AN - 1;
+  const bool ri = ii / 7 >= 4, ci = ii % 7 >= 4;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) m.c[a][b] = ((R && ((a != 0) != ri)) || (Cw && ((b != 0) != ci))) ? kPen : 0.f;
   return m;
 }
+// class of key column j (compile-time in the unrolled loops); pad columns (j >= 49) fall in class (1, *), their bias is kNegBig
+#define MASK_RH(j) (((j) / 7) >= 4 ? 1 : 0)
+#define MASK_CH(j) (((j) % 7) >= 4 ? 1 : 0)
 
 // Thread mapping of the backward kernel: 256 threads = 8 warps.  Warp w owns TMEM lane quarter q = w & 3 (rows
 // q*32..q*32+31 of the stacked tile) and column half hf = w >> 2 of the row's own 64-column window block, so two
@@ -72,7 +86,6 @@ constexpr int kBiasLd = 68;                      // sBias row pitch (floats): 64
                                                  // kNegBig so padded keys drop out of the softmax with no per-element predicate
 constexpr float kNegBig = -1.0e30f;
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-constexpr int kAttnThreads = 256;
 
 __device__ __forceinline__ void load_bias_tile(float* sBias, const float* __restrict__ bias, int h) {
   const float kLog2e = 1.4426950408889634f;
@@ -104,6 +117,7 @@ __device__ __forceinline__ void load_bias_tile(float* sBias, const float* __rest
 // item's softmax), <= 128 registers and 128 TMEM columns (O overlays columns [0,64) of S once P is in smem).
 constexpr uint32_t kFwdTiles = 3 * kTileBytes;     // Q,K,V
 constexpr int kFwdThreads = 128;
+constexpr int kFwdPrefetch = 0;                    // items prefetched into L2 beyond the one whose tiles are being loaded
 constexpr int kFwdBiasLd = 52;                     // bias row pitch of the forward kernel: 49 columns + 3 x kNegBig
 
 __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
@@ -161,12 +175,26 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
 #pragma unroll
     for (int w = 0; w < 2; ++w) tma_load_2d(aV + w * 4096, &tmQKV, bar_v, 2 * p.C + h * AHD, (2 * pair + w) * AN);
   };
+  // L2 prefetch of a later item's q, k, v boxes: the shared-memory tiles hold one item, so the HBM requests that keep the
+  // memory system busy (bandwidth = bytes in flight / latency; tools/probes/tma_probe.cu) are issued ahead of the ring
+  auto prefetch_item = [&](int pair) {
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const int row0 = (2 * pair + w) * AN;
+#pragma unroll
+      for (int part = 0; part < 3; ++part) tma_prefetch_2d(&tmQKV, part * p.C + h * AHD, row0);
+    }
+  };
   // Single-thread work (TMA / MMA issue) sits on the item's serial chain: warp 0 enters converged and ONE elected lane issues
   // (no per-active-lane retry loops in the SASS), with descriptors built as constant-hi : incremented-lo words.
   constexpr uint32_t kHi64 = umma_desc_hi(512, (uint32_t)kSw64), kHi128 = umma_desc_hi(1024, (uint32_t)kSw128);
   const uint32_t q_lo = umma_desc_lo(aQ, 16), k_lo = umma_desc_lo(aK, 16), p_lo = umma_desc_lo(aP, 16), v_lo = umma_desc_lo(aV, 4096);
   if (warp == 0) {
-    if (elect_one() && g < p.npairs) { issue_qk(g); issue_v(g); }
+    if (elect_one() && g < p.npairs) {
+      issue_qk(g); issue_v(g);
+      for (int d = 1; d <= kFwdPrefetch; ++d)
+        if (g + d * stride < p.npairs) prefetch_item(g + d * stride);
+    }
     __syncwarp();
   }
 
@@ -188,16 +216,19 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
     const int win = 2 * pair + wloc;
     const bool valid = (i < AN) && (win < p.B_);
     const float* mrow = nullptr;
-    unsigned long long mb = 0ULL;                // closed-form mask bits of this row (bit j: -100)
+    bool canon = false;
     if (p.mask != nullptr && valid) {
-      const int mw = win % p.nW;
-      if (p.canon_nwh > 0) mb = canon_mask_bits(mw, p.canon_nwh, p.canon_nww, i);
-      else if (p.mask_nz == nullptr || p.mask_nz[mw]) mrow = p.mask + ((size_t)mw * AN + i) * AN;
+      if (p.canon_nwh > 0) canon = true;
+      else if (p.mask_nz == nullptr || p.mask_nz[win % p.nW]) mrow = p.mask + ((size_t)(win % p.nW) * AN + i) * AN;
     }
+    const MaskPen pen = canon_mask_pen(canon, canon ? win % p.nW : 0, p.canon_nwh, p.canon_nww, i);
     mbar_wait(bar_s, ph);
     tc_fence_after();
     if (warp == 0) {                             // the Q, K tiles are free again
-      if (elect_one() && has_next) issue_qk(pair + stride);
+      if (elect_one()) {
+        if (has_next) issue_qk(pair + stride);
+        if (pair + (kFwdPrefetch + 1) * stride < p.npairs) prefetch_item(pair + (kFwdPrefetch + 1) * stride);
+      }
       __syncwarp();
     }
     // Rows >= 49 of a window (and a whole missing window) run the same math on harmless finite values: their P rows only
@@ -210,38 +241,33 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
     float sv[52];
     {
       const float4* b4 = reinterpret_cast<const float4*>(sBias + (i < AN ? i : AN - 1) * kFwdBiasLd);
+      const f32x2 sc = pk2(sc2, sc2);
 #pragma unroll
       for (int c = 0; c < 13; ++c) {
         const float4 bb = b4[c];
-        sv[4 * c + 0] = fmaf(__uint_as_float(v[4 * c + 0]), sc2, bb.x);
-        sv[4 * c + 1] = fmaf(__uint_as_float(v[4 * c + 1]), sc2, bb.y);
-        sv[4 * c + 2] = fmaf(__uint_as_float(v[4 * c + 2]), sc2, bb.z);
-        sv[4 * c + 3] = fmaf(__uint_as_float(v[4 * c + 3]), sc2, bb.w);
+        unpk2(fma2(pk2u(v[4 * c + 0], v[4 * c + 1]), sc, pk2(bb.x, bb.y)), sv[4 * c + 0], sv[4 * c + 1]);
+        unpk2(fma2(pk2u(v[4 * c + 2], v[4 * c + 3]), sc, pk2(bb.z, bb.w)), sv[4 * c + 2], sv[4 * c + 3]);
       }
     }
     if (mrow != nullptr) {
 #pragma unroll
       for (int jj = 0; jj < AN; ++jj) sv[jj] = fmaf(__ldg(mrow + jj), kLog2e, sv[jj]);
     }
-    if (mb != 0ULL) {
-      const uint32_t lo = (uint32_t)mb, hi = (uint32_t)(mb >> 32);
+    // row maximum of the MASKED logits from the four class maxima; exponent offset per class = penalty - maximum
+    float cm[2][2] = {{sv[0], sv[4]}, {sv[28], sv[32]}};
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj)
-        if ((lo >> jj) & 1u) sv[jj] -= 100.0f * kLog2e;
+    for (int jj = 1; jj < AN; ++jj) cm[MASK_RH(jj)][MASK_CH(jj)] = fmaxf(cm[MASK_RH(jj)][MASK_CH(jj)], sv[jj]);
+    const float mx = fmaxf(fmaxf(cm[0][0] + pen.c[0][0], cm[0][1] + pen.c[0][1]), fmaxf(cm[1][0] + pen.c[1][0], cm[1][1] + pen.c[1][1]));
+    const float off[2][2] = {{pen.c[0][0] - mx, pen.c[0][1] - mx}, {pen.c[1][0] - mx, pen.c[1][1] - mx}};
+    float sum = 0.f, sum1 = 0.f;
 #pragma unroll
-      for (int jj = 32; jj < AN; ++jj)
-        if ((hi >> (jj - 32)) & 1u) sv[jj] -= 100.0f * kLog2e;
+    for (int jj = 0; jj < 52; jj += 2) {
+      const float e0 = ex2_ftz(sv[jj] + off[MASK_RH(jj)][MASK_CH(jj)]);
+      const float e1 = ex2_ftz(sv[jj + 1] + off[MASK_RH(jj + 1)][MASK_CH(jj + 1)]);
+      sum += e0; sum1 += e1;
+      sv[jj] = e0; sv[jj + 1] = e1;
     }
-    float mx = sv[0];
-#pragma unroll
-    for (int jj = 1; jj < AN; ++jj) mx = fmaxf(mx, sv[jj]);
-    float sum = 0.f;
-#pragma unroll
-    for (int jj = 0; jj < 52; ++jj) {
-      const float e = ex2_ftz(sv[jj] - mx);
-      sum += e;
-      sv[jj] = e;
-    }
+    sum += sum1;
     // P row -> compact 128x64 bf16 tile (SW128): chunks 0..5 = columns 0..47, chunk 6 = columns 48..51 + zeros, chunk 7 = zeros
 #pragma unroll
     for (int c = 0; c < 6; ++c) store_row_bf16x8(sP + sw128_off(r, c), sv + 8 * c);
@@ -313,13 +339,23 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------ backward
+// 256-thread CTAs (two threads per row of the 128-row tile), two per SM, double-buffered operand tiles.  What shapes the loop:
+//   * dQ / dK / dV are staged IN PLACE over the item's own Q / K / V tiles (dead once its last MMAs have completed) and
+//     TMA-stored from there, so the P / dS tiles are free for the next item at once.  The wait for those stores to have read
+//     the buffer (cp.async.bulk.wait_group.read: ~1.5k cycles after the stores are issued) sits where it costs nothing --
+//     one barrier into the NEXT item, right before that buffer is refilled with the item after next.
+//   * dV = P^T dO is issued as soon as P is in shared memory and runs under the dS math.
+//   * the saved LSE (HBM) is fetched one item ahead; the canonical mask costs four constants per row (canon_mask_pen).
+//   (a TMA warp per CTA, or one 512/576-thread CTA per SM with two pipelines, were measured slower: registers are allocated
+//    per CTA in 4-warp granules, so 9 or 18 warps drop the kernel to 96 registers and it spills.)
 constexpr uint32_t kBwdTiles = 4 * kTileBytes;     // Q,K,V,dO per buffer
+constexpr int kBwdThreads = 256;
 
-__global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
-                                                                       const __grid_constant__ CUtensorMap tmDO,
-                                                                       const __grid_constant__ CUtensorMap tmDQKV, AttnTcParams p) {
+__global__ void __launch_bounds__(kBwdThreads, 2) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                                      const __grid_constant__ CUtensorMap tmDO,
+                                                                      const __grid_constant__ CUtensorMap tmDQKV, AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[4];
+  __shared__ __align__(8) uint64_t bars[4];               // load[2], s, o
   __shared__ uint32_t tmem_slot;
   __shared__ float sRed[2][128];                          // partial D per column half
   uint8_t* sbase = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -339,24 +375,29 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
     fence_barrier_init();
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQKV);
   }
   if (warp == 0) { tmem_alloc(smem_u32(&tmem_slot), 256); tmem_relinquish(); }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  const uint32_t aT = smem_u32(sT);
+  const int stride = p.ctas_per_head;
   const uint32_t tS = tmem_slot, tdP = tmem_slot + 128;
   const uint32_t tdV = tmem_slot, tdK = tmem_slot + 64, tdQ = tmem_slot + 128;   // reuse S / dP columns after the softmax pass
   const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-
   const int r = q * 32 + lane, wloc = r >> 6, i = r & 63;
   const int jbase = hf * 32;
   const uint32_t idesc_s = umma_idesc_bf16(128, false, false);
   const uint32_t idesc_tt = umma_idesc_bf16(64, true, true);     // A^T B, both MN-major
   const uint32_t idesc_nt = umma_idesc_bf16(64, false, true);
-  const uint32_t aT = smem_u32(sT), aP = smem_u32(sP), adS = smem_u32(sdS);
+  const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
   const float kLog2e = 1.4426950408889634f;
   const float sc2 = p.scale * kLog2e;
+  constexpr uint32_t kHi64 = umma_desc_hi(512, (uint32_t)kSw64), kHi128 = umma_desc_hi(1024, (uint32_t)kSw128);
+  const uint32_t ds_lo_k = umma_desc_lo(adS, 16);                                               // K-major view of dS
+  const uint32_t p_lo_mn = umma_desc_lo(aP, 8192), ds_lo_mn = umma_desc_lo(adS, 8192);          // MN-major (transposed) views
 
   auto issue_loads = [&](int pair, int buf) {
     const uint32_t bar = bar_load0 + 8 * buf, base = aT + buf * kBwdTiles;
@@ -370,53 +411,68 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
       tma_load_2d(base + 3 * kTileBytes + w * 4096, &tmDO, bar, h * AHD, row0);
     }
   };
-  constexpr uint32_t kHi64 = umma_desc_hi(512, (uint32_t)kSw64), kHi128 = umma_desc_hi(1024, (uint32_t)kSw128);
-  const uint32_t p_lo_k = umma_desc_lo(aP, 16), ds_lo_k = umma_desc_lo(adS, 16);              // K-major views of P / dS
-  const uint32_t p_lo_mn = umma_desc_lo(aP, 8192), ds_lo_mn = umma_desc_lo(adS, 8192);          // MN-major (transposed) views
-  (void)p_lo_k;
   if (warp == 0) {
-    if (elect_one() && g < p.npairs) issue_loads(g, 0);
+    if (elect_one()) {
+      if (g < p.npairs) issue_loads(g, 0);
+      if (g + stride < p.npairs) issue_loads(g + stride, 1);
+    }
     __syncwarp();
   }
 
-  float db[32];
+  // S = Q K^T and dP = dO V^T of the item in buffer `buf` (its `n`-th use)
+  auto issue_sdp = [&](uint32_t buf, uint32_t n) {
+    const uint32_t bQ = aT + buf * kBwdTiles;
+    const uint32_t q_lo = umma_desc_lo(bQ, 16), k_lo = umma_desc_lo(bQ + kTileBytes, 16), v_lo = umma_desc_lo(bQ + 2 * kTileBytes, 16),
+                   do_lo = umma_desc_lo(bQ + 3 * kTileBytes, 16);
+    mbar_wait(bar_load0 + 8 * buf, n & 1);
+    tc_fence_after();
 #pragma unroll
-  for (int j = 0; j < 32; ++j) db[j] = 0.f;
+    for (uint32_t k = 0; k < 2; ++k)
+      umma_bf16(tS, umma_desc_join(kHi64, q_lo + 2 * k), umma_desc_join(kHi64, k_lo + 2 * k), idesc_s, k);
+#pragma unroll
+    for (uint32_t k = 0; k < 2; ++k)
+      umma_bf16(tdP, umma_desc_join(kHi64, do_lo + 2 * k), umma_desc_join(kHi64, v_lo + 2 * k), idesc_s, k);
+    umma_commit(bar_s);
+  };
+
+  f32x2 db2[16];                                   // dBias partial sums of this thread's (row, 32 columns), packed pairs
+#pragma unroll
+  for (int j = 0; j < 16; ++j) db2[j] = pk2(0.f, 0.f);
   TDECL
+  // the saved LSE of a row comes from HBM: fetched one item ahead so that its latency never sits on the item's chain
+  auto load_lse = [&](int pair) -> float {
+    const int win = 2 * pair + wloc;
+    return ((i < AN) && (win < p.B_)) ? p.lse[((size_t)win * p.nH + h) * AN + i] * kLog2e : 0.f;
+  };
+  float lse_next = g < p.npairs ? load_lse(g) : 0.f;
+  const f32x2 sc2p = pk2(sc2, sc2), scalep = pk2(p.scale, p.scale);
+  const float4* brow = reinterpret_cast<const float4*>(sBias + (i < AN ? i : AN - 1) * kBiasLd + jbase);
 
   uint32_t it = 0;
-  for (int pair = g; pair < p.npairs; pair += p.ctas_per_head, ++it) {
-    const uint32_t ph = it & 1, buf = it & 1, lph = (it >> 1) & 1;
-    const uint32_t aQ = aT + buf * kBwdTiles, aK = aQ + kTileBytes, aV = aK + kTileBytes, adO = aV + kTileBytes;
+  for (int pair = g; pair < p.npairs; pair += stride, ++it) {
+    const uint32_t ph = it & 1, buf = it & 1;
+    const uint32_t aQ = aT + buf * kBwdTiles, aK = aQ + kTileBytes, adO = aQ + 3 * kTileBytes;
     TITEM
-    // operand tiles of this buffer as descriptor low words (K-major views: LBO 16; MN-major views of Q, K, dO: LBO 4096)
-    const uint32_t q_lo = umma_desc_lo(aQ, 16), k_lo = umma_desc_lo(aK, 16), v_lo = umma_desc_lo(aV, 16), do_lo = umma_desc_lo(adO, 16);
+    // MN-major views of this buffer's Q, K, dO tiles as descriptor low words (LBO 4096)
     const uint32_t q_lo_mn = umma_desc_lo(aQ, 4096), k_lo_mn = umma_desc_lo(aK, 4096), do_lo_mn = umma_desc_lo(adO, 4096);
-    if (warp == 0) {
-      if (elect_one()) {
-        mbar_wait(bar_load0 + 8 * buf, lph);
-        tc_fence_after();
-#pragma unroll
-        for (uint32_t k = 0; k < 2; ++k)
-          umma_bf16(tS, umma_desc_join(kHi64, q_lo + 2 * k), umma_desc_join(kHi64, k_lo + 2 * k), idesc_s, k);
-#pragma unroll
-        for (uint32_t k = 0; k < 2; ++k)
-          umma_bf16(tdP, umma_desc_join(kHi64, do_lo + 2 * k), umma_desc_join(kHi64, v_lo + 2 * k), idesc_s, k);
-        umma_commit(bar_s);
-        if (pair + p.ctas_per_head < p.npairs) issue_loads(pair + p.ctas_per_head, buf ^ 1);   // after the MMAs are in flight
-      }
+    const bool has_next = pair + stride < p.npairs;
+    if (it == 0 && warp == 0) {                    // (later items: issued at the end of the previous item, ahead of its stores)
+      if (elect_one()) issue_sdp(0, 0);
       __syncwarp();
     }
     const int win = 2 * pair + wloc;
     const bool valid = (i < AN) && (win < p.B_);
-    const float lse2 = valid ? p.lse[((size_t)win * p.nH + h) * AN + i] * kLog2e : 0.f;
+    const float lse2 = lse_next;
+    if (has_next) lse_next = load_lse(pair + stride);
     const float* mrow = nullptr;
-    uint32_t mb = 0u;
+    bool canon = false;
     if (p.mask != nullptr && valid) {
-      const int mw = win % p.nW;
-      if (p.canon_nwh > 0) mb = (uint32_t)(canon_mask_bits(mw, p.canon_nwh, p.canon_nww, i) >> jbase);
-      else if (p.mask_nz == nullptr || p.mask_nz[mw]) mrow = p.mask + ((size_t)mw * AN + i) * AN;
+      if (p.canon_nwh > 0) canon = true;
+      else if (p.mask_nz == nullptr || p.mask_nz[win % p.nW]) mrow = p.mask + ((size_t)(win % p.nW) * AN + i) * AN;
     }
+    // exponent offset per mask class: penalty - LSE (see canon_mask_pen)
+    MaskPen off = canon_mask_pen(canon, canon ? win % p.nW : 0, p.canon_nwh, p.canon_nww, i);
+    off.c[0][0] -= lse2; off.c[0][1] -= lse2; off.c[1][0] -= lse2; off.c[1][1] -= lse2;
     mbar_wait(bar_s, ph);
     tc_fence_after();
     TMARK(0);
@@ -430,54 +486,64 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
     // (rows >= 49 / a missing window run on harmless finite values: their dO and Q rows are zero, so they add nothing to
     //  dV / dK, their dQ rows are never stored and their bias gradients are never written; columns >= 49 carry kNegBig)
     float pr[32];
-    float delta = 0.f;
-    {
-      const float4* b4 = reinterpret_cast<const float4*>(sBias + (i < AN ? i : AN - 1) * kBiasLd + jbase);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 bb = b4[c];
-        pr[4 * c + 0] = fmaf(__uint_as_float(s[4 * c + 0]), sc2, bb.x);
-        pr[4 * c + 1] = fmaf(__uint_as_float(s[4 * c + 1]), sc2, bb.y);
-        pr[4 * c + 2] = fmaf(__uint_as_float(s[4 * c + 2]), sc2, bb.z);
-        pr[4 * c + 3] = fmaf(__uint_as_float(s[4 * c + 3]), sc2, bb.w);
-      }
+    for (int c = 0; c < 8; ++c) {
+      const float4 bb = brow[c];
+      unpk2(fma2(pk2u(s[4 * c + 0], s[4 * c + 1]), sc2p, pk2(bb.x, bb.y)), pr[4 * c + 0], pr[4 * c + 1]);
+      unpk2(fma2(pk2u(s[4 * c + 2], s[4 * c + 3]), sc2p, pk2(bb.z, bb.w)), pr[4 * c + 2], pr[4 * c + 3]);
     }
     if (mrow != nullptr) {
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj)
         if (jbase + jj < AN) pr[jj] = fmaf(__ldg(mrow + jbase + jj), kLog2e, pr[jj]);
     }
-    if (mb != 0u) {
+    float delta = 0.f, delta1 = 0.f;
+    // the mask class of column jbase + jj is a compile-time constant per column half
+    auto exp_half = [&](auto HF) {
+      constexpr int jb = decltype(HF)::value * 32;
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj)
-        if ((mb >> jj) & 1u) pr[jj] -= 100.0f * kLog2e;
-    }
-#pragma unroll
-    for (int jj = 0; jj < 32; ++jj) {
-      const float pv = ex2_ftz(pr[jj] - lse2);
-      delta = fmaf(pv, __uint_as_float(dp[jj]), delta);
-      pr[jj] = pv;
-    }
+      for (int jj = 0; jj < 32; jj += 2) {
+        const float p0 = ex2_ftz(pr[jj] + off.c[MASK_RH(jb + jj)][MASK_CH(jb + jj)]);
+        const float p1 = ex2_ftz(pr[jj + 1] + off.c[MASK_RH(jb + jj + 1)][MASK_CH(jb + jj + 1)]);
+        delta = fmaf(p0, __uint_as_float(dp[jj]), delta);
+        delta1 = fmaf(p1, __uint_as_float(dp[jj + 1]), delta1);
+        pr[jj] = p0; pr[jj + 1] = p1;
+      }
+    };
+    if (hf == 0) exp_half(std::integral_constant<int, 0>{}); else exp_half(std::integral_constant<int, 1>{});
+    delta += delta1;
     sRed[hf][r] = delta;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) store_row_bf16x8(sP + sw128_off(r, hf * 4 + c), pr + 8 * c);
     TMARK(2);
-    if (warp == 0) {                             // previous item's dQ/dK/dV tiles (staged in sP/sdS) drained
-      if (elect_one()) tma_store_wait_read<0>();
-      __syncwarp();
-    }
+    fence_proxy_async_smem();
+    tc_fence_before();
     __syncthreads();
     TMARK(3);
-    delta = sRed[0][r] + sRed[1][r];
-    float dsv[32];
+    if (warp == 0) {
+      if (elect_one()) {
+        tc_fence_after();
 #pragma unroll
-    for (int jj = 0; jj < 32; ++jj) {
-      const float ds = pr[jj] * (__uint_as_float(dp[jj]) - delta);
-      db[jj] += ds;
-      dsv[jj] = ds * p.scale;
+        for (uint32_t kk = 0; kk < 4; ++kk)   // dV[(w,j), (w',d)] = sum_i P_w[i][j] dO_w'[i][d]  -- runs under the dS math
+          umma_bf16(tdV, umma_desc_join(kHi128, p_lo_mn + 128 * kk), umma_desc_join(kHi64, do_lo_mn + 64 * kk), idesc_tt, kk);
+        // the PREVIOUS item's dQ / dK / dV (staged over its own tiles, stores issued ~2k cycles ago) have been read out: refill
+        // that buffer with the next item
+        if (it >= 1 && has_next) { tma_store_wait_read<0>(); issue_loads(pair + stride, buf ^ 1); }
+      }
+      __syncwarp();
     }
+    delta = sRed[0][r] + sRed[1][r];
+    {
+      const f32x2 nd = pk2(-delta, -delta);
+      float dsv[32];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      store_row_bf16x8(sP + sw128_off(r, hf * 4 + c), pr + 8 * c);
-      store_row_bf16x8(sdS + sw128_off(r, hf * 4 + c), dsv + 8 * c);
+      for (int c = 0; c < 16; ++c) {
+        const f32x2 ds = mul2(pk2(pr[2 * c], pr[2 * c + 1]), add2(pk2u(dp[2 * c], dp[2 * c + 1]), nd));
+        db2[c] = add2(db2[c], ds);
+        unpk2(mul2(ds, scalep), dsv[2 * c], dsv[2 * c + 1]);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) store_row_bf16x8(sdS + sw128_off(r, hf * 4 + c), dsv + 8 * c);
     }
     TMARK(4);
     fence_proxy_async_smem();
@@ -487,9 +553,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
     if (warp == 0) {
       if (elect_one()) {
         tc_fence_after();
-#pragma unroll
-        for (uint32_t kk = 0; kk < 4; ++kk)   // dV[(w,j), (w',d)] = sum_i P_w[i][j] dO_w'[i][d]
-          umma_bf16(tdV, umma_desc_join(kHi128, p_lo_mn + 128 * kk), umma_desc_join(kHi64, do_lo_mn + 64 * kk), idesc_tt, kk);
 #pragma unroll
         for (uint32_t kk = 0; kk < 4; ++kk)   // dK = (scale dS)^T Q
           umma_bf16(tdK, umma_desc_join(kHi128, ds_lo_mn + 128 * kk), umma_desc_join(kHi64, q_lo_mn + 64 * kk), idesc_tt, kk);
@@ -504,32 +567,44 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
     tc_fence_after();
     TMARK(6);
     {
-      // dQ / dK / dV rows -> three bf16 tiles (8 KB each, 64-byte swizzle) in the sP + sdS region, which is free now
-      // that the three MMAs have completed; then 49x32 TMA stores into the [q|k|v] column blocks of dqkv
+      // dQ / dK / dV rows -> bf16, staged IN PLACE over this item's Q / K / V tiles (64-byte swizzle, window w at +4096): every
+      // MMA that read them has completed.  Pad rows (i >= 49) are written as zeros so the tiles stay valid operand tiles when
+      // the refill rewrites rows 0..48 only.
       const uint32_t swz = (uint32_t)((r >> 1) & 3);
+      uint8_t* tbase = sT + buf * kBwdTiles + r * 64;
+      uint32_t o[48];
+      tmem_ld16(tdQ + lane_off + wloc * 32 + hf * 16, o);
+      tmem_ld16(tdK + lane_off + wloc * 32 + hf * 16, o + 16);
+      tmem_ld16(tdV + lane_off + wloc * 32 + hf * 16, o + 32);
+      tmem_ld_wait();
+      if (i >= AN) {
+#pragma unroll
+        for (int e = 0; e < 48; ++e) o[e] = 0u;
+      }
 #pragma unroll
       for (int part = 0; part < 3; ++part) {   // 0: dQ, 1: dK, 2: dV
-        uint32_t o[16];
-        tmem_ld16((part == 0 ? tdQ : part == 1 ? tdK : tdV) + lane_off + wloc * 32 + hf * 16, o);
-        tmem_ld_wait();
-        uint8_t* trow = sP + part * 8192 + r * 64;
-        store_row_bf16x8(trow + (((uint32_t)(hf * 2 + 0) ^ swz) << 4), reinterpret_cast<const float*>(o));
-        store_row_bf16x8(trow + (((uint32_t)(hf * 2 + 1) ^ swz) << 4), reinterpret_cast<const float*>(o + 8));
+        uint8_t* trow = tbase + part * kTileBytes;
+        store_row_bf16x8(trow + (((uint32_t)(hf * 2 + 0) ^ swz) << 4), reinterpret_cast<const float*>(o + 16 * part));
+        store_row_bf16x8(trow + (((uint32_t)(hf * 2 + 1) ^ swz) << 4), reinterpret_cast<const float*>(o + 16 * part + 8));
       }
     }
     TMARK(7);
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();                               // also: every warp has read dQ / dK / dV out of TMEM before the next item's S / dP MMAs
     TMARK(8);
     if (warp == 0) {
       if (elect_one()) {
+        // the next item's S / dP MMAs go first (its tiles landed long ago; every warp has read this item's outputs out of the
+        // TMEM columns they overwrite), then this item's stores: the MMA round trip is the longest wait of an item
+        if (has_next) issue_sdp(buf ^ 1, (it + 1) >> 1);
+        const uint32_t base = aT + buf * kBwdTiles;
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
           if (2 * pair + w >= p.B_) continue;
 #pragma unroll
           for (int part = 0; part < 3; ++part)
-            tma_store_2d(&tmDQKV, aP + part * 8192 + w * 4096, part * p.C + h * AHD, (2 * pair + w) * AN);
+            tma_store_2d(&tmDQKV, base + part * kTileBytes + w * 4096, part * p.C + h * AHD, (2 * pair + w) * AN);
         }
         tma_store_commit();
       }
@@ -541,12 +616,35 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_bwd_kernel(const __gr
     if (elect_one()) tma_store_wait_all<0>();
     __syncwarp();
   }
-  if (i < AN) {
-    float* dst = p.dbias + ((size_t)h * AN + i) * AN + jbase;
+  // dBias: the two windows of the tile hold the same (i, j) entries -- rows r and r + 64 are summed through shared memory
+  // (the P / dS tiles are dead: the last MMAs have completed) before the global atomics
+  if (g < p.npairs) {
+    float* mine = reinterpret_cast<float*>(sP) + ((hf * 64 + i) * 32);            // [2 column halves][64 rows][32] floats = 16 KB
+    if (wloc == 1) {
 #pragma unroll
-    for (int jj = 0; jj < 32; ++jj)
-      if (jbase + jj < AN) atomicAdd(dst + jj, db[jj]);
+      for (int c = 0; c < 8; ++c) {
+        float4 t;
+        unpk2(db2[2 * c], t.x, t.y); unpk2(db2[2 * c + 1], t.z, t.w);
+        reinterpret_cast<float4*>(mine)[c ^ (i & 7)] = t;
+      }
+    }
+    __syncthreads();
+    if (wloc == 0 && i < AN) {
+      float* dst = p.dbias + ((size_t)h * AN + i) * AN + jbase;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 t = reinterpret_cast<const float4*>(mine)[c ^ (i & 7)];
+        float a0, a1, a2, a3;
+        unpk2(db2[2 * c], a0, a1); unpk2(db2[2 * c + 1], a2, a3);
+        if (jbase + 4 * c + 0 < AN) atomicAdd(dst + 4 * c + 0, a0 + t.x);
+        if (jbase + 4 * c + 1 < AN) atomicAdd(dst + 4 * c + 1, a1 + t.y);
+        if (jbase + 4 * c + 2 < AN) atomicAdd(dst + 4 * c + 2, a2 + t.z);
+        if (jbase + 4 * c + 3 < AN) atomicAdd(dst + 4 * c + 3, a3 + t.w);
+      }
+    }
   }
+  tc_fence_before();
+  __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_slot, 256); }
 }
 
@@ -611,7 +709,7 @@ int attn_tc_bwd(const swin_attn_args* a, cudaStream_t st) {
   CUtensorMap tmdq;
   rc = make_tmap_bf16_2d(&tmdq, a->dqkv, (uint64_t)3 * p.C, (uint64_t)p.B_ * AN, (uint64_t)3 * p.C * 2, AHD, AN, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
-  attn_tc_bwd_kernel<<<p.nH * p.ctas_per_head, kAttnThreads, smem, st>>>(tm, tmdo, tmdq, p);
+  attn_tc_bwd_kernel<<<p.nH * p.ctas_per_head, kBwdThreads, smem, st>>>(tm, tmdo, tmdq, p);
   SWIN_LAUNCH_CHECK();
   return 0;
 }

@@ -484,8 +484,10 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
             const float x0 = __uint_as_float(v[4 * k + 0]) + b4[k].x, x1 = __uint_as_float(v[4 * k + 1]) + b4[k].y;
             const float x2 = __uint_as_float(v[4 * k + 2]) + b4[k].z, x3 = __uint_as_float(v[4 * k + 3]) + b4[k].w;
             if (gelu) {                                // pu <- gelu(u) (D), ph <- gelu'(u) (D2)
+              f32x2 ga, da, gb, db;
+              gelu_fast2(x0, x1, &ga, &da); gelu_fast2(x2, x3, &gb, &db);
               float g0, g1, g2, g3, d0, d1, d2, d3;
-              gelu_fast(x0, &g0, &d0); gelu_fast(x1, &g1, &d1); gelu_fast(x2, &g2, &d2); gelu_fast(x3, &g3, &d3);
+              unpk2(ga, g0, g1); unpk2(gb, g2, g3); unpk2(da, d0, d1); unpk2(db, d2, d3);
               pu[2 * k] = pack_bf16(g0, g1); pu[2 * k + 1] = pack_bf16(g2, g3);
               ph[2 * k] = pack_bf16(d0, d1); ph[2 * k + 1] = pack_bf16(d2, d3);
             } else {

@@ -104,6 +104,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
+// L2 prefetch of a 2-D box (no shared memory, no completion tracking): keeps HBM requests in flight beyond what the smem
+// ring can hold -- the later cp.async.bulk.tensor load of the same box then completes at L2 latency.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
+}
+
 // 2-D tiled store shared -> global (bulk async-group completion).  Issued by ONE thread after the smem tile has been
 // written by generic-proxy stores + fence.proxy.async + a warp/CTA barrier.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
@@ -225,6 +231,31 @@ __device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// GELU(u) = u Phi(u) and GELU'(u) = Phi(u) + u phi(u) for TWO elements with packed fp32x2 arithmetic (bf16 epilogues of the
+// tcgen05 GEMM; the fp32 parity mode uses erff).  Phi(u) - 1/2 is an odd degree-13 minimax polynomial on the clamped argument
+// |u| <= 3.72 (|err| <= 5.2e-5 incl. the clamp, two orders below bf16 rounding of the results) and phi comes from ONE
+// MUFU.EX2: 7 FMA-pipe + 2 ALU + 1 MUFU issue slots per element instead of 13 + 2 + 2 for the erfc form with its
+// MUFU.RCP -- at two MUFU per element the 16/clk/SM special-function unit, not the tensor pipe, paced the K = 384 fc1 tile.
+__device__ __forceinline__ void gelu_fast2(float u0, float u1, f32x2* g, f32x2* dg) {
+  const float kC = 3.72f;
+  const float c0 = fminf(fmaxf(u0, -kC), kC), c1 = fminf(fmaxf(u1, -kC), kC);
+  const f32x2 u = pk2(u0, u1), uc = pk2(c0, c1);
+  const f32x2 s = mul2(uc, uc);
+  f32x2 P = fma2(pk2(4.067643399e-08f, 4.067643399e-08f), s, pk2(-2.440210775e-06f, -2.440210775e-06f));
+  P = fma2(P, s, pk2(6.335137559e-05f, 6.335137559e-05f));
+  P = fma2(P, s, pk2(-9.516457104e-04f, -9.516457104e-04f));
+  P = fma2(P, s, pk2(9.389134269e-03f, 9.389134269e-03f));
+  P = fma2(P, s, pk2(-6.582961341e-02f, -6.582961341e-02f));
+  P = fma2(P, s, pk2(3.987229868e-01f, 3.987229868e-01f));
+  const f32x2 cdf = fma2(uc, P, pk2(0.5f, 0.5f));
+  float e0, e1;
+  unpk2(mul2(mul2(u, pk2(-0.72134752044448170368f, -0.72134752044448170368f)), u), e0, e1);
+  asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(e0));                     // exp(-u^2 / 2)
+  asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(e1));
+  *g = mul2(u, cdf);
+  *dg = fma2(mul2(u, pk2(0.39894228040143267794f, 0.39894228040143267794f)), pk2(e0, e1), cdf);
+}
 
 // TMEM -> registers: 32 lanes x 32 consecutive 32-bit columns (lane l of the warp reads TMEM lane base+l).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {

@@ -23,7 +23,7 @@ for B_, nH, masked in cases:
     dout = torch.randn(B_, 49, C, device=dev).bfloat16()
     tf, tb = [], []
     for _ in range(reps):
-        flush.zero_()
+        for _ in range(6): flush.zero_()      # L2 flush, long enough for the host to enqueue the timed launches behind it
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record()
         o, lse = ops.window_attn_fwd(qkv, bias, mask, B_, nH, 7, 32 ** -0.5, mask_nz)

@@ -18,7 +18,7 @@ if len(sys.argv) > 2:
 def med(fn):
     ts = []
     for _ in range(reps):
-        flush.zero_()
+        for _ in range(6): flush.zero_()      # L2 flush, long enough for the host to enqueue the timed launches behind it
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record()
         torch.cuda.synchronize()
