@@ -245,6 +245,45 @@ def run_reference(args, emit=print):
         "gpu_launches": 0}))
 
 
+
+def fused_attention_probe(dev, B, peak, hbm_peak):
+    """The fused QKV-projection + window-attention forward kernel (swin_window_attn_qkv_fwd: the inference path of the attention
+    branch; training keeps the GEMM + attention pair, which is as fast when q/k/v must be written for backward) on the window
+    rows of stages 0-2 of this benchmark's geometry: CUDA events, median of 5, L2 flushed between runs.  achieved = algorithmic
+    flops (2 T 3C C projection + 4 N^2 32 per (window, head) attention) / time."""
+    import swin_b200  # noqa: F401
+    from swin_b200 import ops
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    out = {}
+    for stage, (nH, gh, gw) in enumerate([(3, 29, 48), (6, 15, 24), (12, 8, 12)]):
+        C, B_ = nH * 32, B * gh * gw
+        if not ops.window_attn_qkv_supported(C, nH, 7):
+            continue
+        g = torch.Generator(device=dev).manual_seed(stage)
+        xw = torch.randn(B_ * 49, C, device=dev, generator=g).bfloat16()
+        w = (torch.randn(3 * C, C, device=dev, generator=g) / C ** 0.5).bfloat16()
+        bq = torch.randn(3 * C, device=dev, generator=g) * 0.1
+        bias = torch.randn(nH, 49, 49, device=dev, generator=g) * 0.3
+        mask = ops.shift_mask(gh * 7, gw * 7, 7, 3, dev)
+        mnz = ops.mask_nonzero(mask)
+        ts = []
+        for _ in range(5):
+            for _ in range(4):
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.window_attn_qkv_fwd(xw, w, bq, bias, mask, B_, nH, 7, 32 ** -0.5, mnz, (gh, gw), want_qkv=False, want_lse=False)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        t = sorted(ts)[2]
+        fl = 2.0 * B_ * 49 * C * 3 * C + 307328.0 * B_ * nH
+        by = 2.0 * B_ * 49 * C * 2
+        out[f"stage{stage}_C{C}"] = {"windows": B_, "us": t * 1e6, "achieved": fl / t / 1e12, "unit": "TFLOP/s", "frac": fl / t / 1e12 / peak,
+                                    "dram_gbs": by / t / 1e9, "dram_frac_of_hbm_peak": by / t / 1e9 / hbm_peak}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -465,6 +504,11 @@ def main():
             attn[pref if pref != "attn" else "all"] = {
                 "launches_per_step": n_a // max(K, 1), "ms_per_step": ms_a / max(K, 1), "achieved": tf, "unit": "TFLOP/s",
                 "frac": tf / peak, "dram_gbs": by_a / (ms_a / 1e3) / 1e9, "dram_frac_of_hbm_peak": by_a / (ms_a / 1e3) / 1e9 / hbm_peak}
+    if rank == 0 and world == 1 and args.compute_dtype == "bf16":
+        try:
+            attn["fused_qkv_fwd_probe"] = fused_attention_probe(dev, B, peak, hbm_peak)
+        except Exception as e:                      # the probe must never take the benchmark line down
+            attn["fused_qkv_fwd_probe"] = {"error": str(e)[:200]}
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all epilogues)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": gemm_bytes / max(n_launch, 1),

@@ -123,7 +123,7 @@ constexpr int kFwdBiasLd = 52;                     // bias row pitch of the forw
 __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                                       const __grid_constant__ CUtensorMap tmOut, AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[4];              // qk, v, s, o
+  __shared__ __align__(8) uint64_t bars[5];              // qk, v, s, o, free (the staged O tile of the previous item has been read)
   __shared__ uint32_t tmem_slot;
   uint8_t* sbase = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sT = sbase;                                   // {Q,K,V}
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
   float* sBias = reinterpret_cast<float*>(sP + kPBytes); // [49][52]
   const int tid = threadIdx.x, warp = tid >> 5;
   const int h = blockIdx.x % p.nH, g = blockIdx.x / p.nH;
-  const uint32_t bar_qk = smem_u32(&bars[0]), bar_v = smem_u32(&bars[1]), bar_s = smem_u32(&bars[2]), bar_o = smem_u32(&bars[3]);
+  const uint32_t bar_qk = smem_u32(&bars[0]), bar_v = smem_u32(&bars[1]), bar_s = smem_u32(&bars[2]), bar_o = smem_u32(&bars[3]), bar_free = smem_u32(&bars[4]);
 
   zero_smem(sT, kFwdTiles + kPBytes);
   {
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
     }
   }
   if (tid == 0) {
-    mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_free, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmQKV);
   }
@@ -189,6 +189,14 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
   // (no per-active-lane retry loops in the SASS), with descriptors built as constant-hi : incremented-lo words.
   constexpr uint32_t kHi64 = umma_desc_hi(512, (uint32_t)kSw64), kHi128 = umma_desc_hi(1024, (uint32_t)kSw128);
   const uint32_t q_lo = umma_desc_lo(aQ, 16), k_lo = umma_desc_lo(aK, 16), p_lo = umma_desc_lo(aP, 16), v_lo = umma_desc_lo(aV, 4096);
+  auto issue_s = [&](uint32_t phase) {           // S = Q K^T as soon as Q, K have landed
+    mbar_wait(bar_qk, phase);
+    tc_fence_after();
+#pragma unroll
+    for (uint32_t k = 0; k < 2; ++k)
+      umma_bf16(tS, umma_desc_join(kHi64, q_lo + 2 * k), umma_desc_join(kHi64, k_lo + 2 * k), idesc_s, k);
+    umma_commit(bar_s);
+  };
   if (warp == 0) {
     if (elect_one() && g < p.npairs) {
       issue_qk(g); issue_v(g);
@@ -202,15 +210,8 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
   for (int pair = g; pair < p.npairs; pair += stride, ++it) {
     const uint32_t ph = it & 1;
     const bool has_next = pair + stride < p.npairs;
-    if (warp == 0) {                             // S = Q K^T as soon as Q, K have landed
-      if (elect_one()) {
-        mbar_wait(bar_qk, ph);
-        tc_fence_after();
-#pragma unroll
-        for (uint32_t k = 0; k < 2; ++k)
-          umma_bf16(tS, umma_desc_join(kHi64, q_lo + 2 * k), umma_desc_join(kHi64, k_lo + 2 * k), idesc_s, k);
-        umma_commit(bar_s);
-      }
+    if (it == 0 && warp == 0) {                  // S = Q K^T of the first item (later items: issued at the end of the previous one)
+      if (elect_one()) issue_s(0);
       __syncwarp();
     }
     const int win = 2 * pair + wloc;
@@ -268,6 +269,13 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
       sv[jj] = e0; sv[jj + 1] = e1;
     }
     sum += sum1;
+    // the previous item's O tile is staged where P goes: its TMA store (issued a softmax ago) must have read it.  The wait
+    // belongs to the thread that issued the store; everybody else learns through bar_free.
+    if (warp == 0) {
+      if (elect_one()) { tma_store_wait_read<0>(); mbar_arrive(bar_free); }
+      __syncwarp();
+    }
+    mbar_wait(bar_free, ph);
     // P row -> compact 128x64 bf16 tile (SW128): chunks 0..5 = columns 0..47, chunk 6 = columns 48..51 + zeros, chunk 7 = zeros
 #pragma unroll
     for (int c = 0; c < 6; ++c) store_row_bf16x8(sP + sw128_off(r, c), sv + 8 * c);
@@ -319,13 +327,13 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
     __syncthreads();
     if (warp == 0) {
       if (elect_one()) {
+        // the next item's S MMA goes first (every thread has read this item's O out of the TMEM columns it overwrites): the
+        // MMA round trip, not the store, is on the next item's chain
+        if (has_next) issue_s(ph ^ 1);
 #pragma unroll
         for (int w = 0; w < 2; ++w)
           if (2 * pair + w < p.B_) tma_store_2d(&tmOut, aP + w * 4096, h * AHD, (2 * pair + w) * AN);
         tma_store_commit();
-        // sP is rewritten with the next item's P only after every thread has passed bar_s of the next item, which this
-        // thread commits after this wait: the staged O tile has been read out by then
-        tma_store_wait_read<0>();
       }
       __syncwarp();
     }

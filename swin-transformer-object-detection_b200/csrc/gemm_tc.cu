@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
     const int ew = warp - 2;                  // 0..7
     // per-epilogue-warp staging lives in dynamic smem right after the operand ring (4 KB per warp; 2 x 4 KB for class 2)
     float4* stage = reinterpret_cast<float4*>(smem_raw + (smem0 - smem_u32(smem_raw)) + (uint32_t)p.stages * stage_bytes + (uint32_t)ew * p.epi_bytes_per_warp);
+    uint32_t epi_sb = 0;                                   // class-1 epilogue: which of the warp's two staging buffers is next
     uint32_t u = 0;
     uint32_t aux_n = 0;                       // class 2: aux tiles requested so far by this warp (buffer = n & 1)
     PROF_DECL
@@ -462,8 +463,9 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
         const bool gelu = p.epi.epilogue == SWIN_EPI_GELU;
-        uint8_t* sbuf = reinterpret_cast<uint8_t*>(stage);
-        const uint32_t sbuf_a = smem_u32(sbuf);
+        // two staging buffers per warp, used alternately: a chunk's TMA store needs ~1k cycles before it has read its buffer
+        // (cp.async.bulk.wait_group.read), as long as the math of a chunk -- with one buffer every chunk waited for it
+        const uint32_t sb_bytes = gelu ? 4096u : 2048u;
         const uint32_t swz = (uint32_t)((lane >> 1) & 3);
         uint32_t v[32];
         int c = (int)(((uint32_t)(ew >> 2) + u) % kGroups) * 32;        // rotate the starting warp every tile
@@ -495,7 +497,10 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
             }
           }
           if (c + 32 * kGroups < p.block_n) tmem_ld32(taddr + c + 32 * kGroups, v);      // next chunk's TMEM read overlaps the stores below
-          if (lane == 0) tma_store_wait_read<0>();                   // previous chunk's TMA stores have drained the staging tile
+          uint8_t* sbuf = reinterpret_cast<uint8_t*>(stage) + epi_sb * sb_bytes;
+          const uint32_t sbuf_a = smem_u32(sbuf);
+          epi_sb ^= 1u;
+          if (lane == 0) tma_store_wait_read<1>();                   // the stores of the chunk before the previous one have drained this buffer
           __syncwarp();
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
@@ -719,7 +724,8 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
       p.tma_epi = 2;
     }
   }
-  p.epi_bytes_per_warp = p.tma_epi == 2 ? 8192u : 4096u;     // class 2: 2 x 4 KB (fp32) or 4 x 2 KB (bf16) aux ring per warp
+  // class 2: 2 x 4 KB (fp32) or 4 x 2 KB (bf16) aux ring per warp; class 1: two staging buffers of 2 KB (STORE) or 2 x 2 KB (GELU: D and D2)
+  p.epi_bytes_per_warp = (p.tma_epi == 2 || (p.tma_epi == 1 && a->epilogue == SWIN_EPI_GELU)) ? 8192u : 4096u;
   const uint32_t epi_bytes = p.epi_bytes_per_warp * (uint32_t)epi_warps(p.tma_epi);
   {
     const uint32_t ring_budget = 212 * 1024 - epi_bytes - 1024;     // dynamic smem: ring + epilogue staging + alignment slack

@@ -35,6 +35,45 @@ def _fuse_qkv(Cc: int, nH: int, ws: int) -> bool:
     return FUSE_QKV_ATTENTION and Cc <= FUSE_QKV_MAX_C and ops.window_attn_qkv_supported(Cc, nH, ws)
 
 
+# Backward: the four weight-gradient GEMMs of a block (split-K, atomics into pre-zeroed buffers) feed nothing downstream in the
+# block, so they can run on a side stream and fill the tail of the dX chain's persistent kernels (SWIN_DW_STREAM=1; joined before
+# backward returns, so autograd / the DDP hooks see ordinary main-stream tensors; under CUDA-graph capture the fork / join become
+# graph edges).
+DW_SIDE_STREAM = __import__("os").environ.get("SWIN_DW_STREAM", "0") == "1"
+_SIDE_STREAMS = {}
+
+
+class _SideLane:
+    """Runs callables on a per-device side stream, each after everything enqueued so far on the current stream."""
+
+    def __init__(self, device):
+        self.enabled = DW_SIDE_STREAM and device.type == "cuda"
+        if not self.enabled:
+            return
+        self.main = torch.cuda.current_stream(device)
+        key = (device.index, self.main.cuda_stream)
+        if key not in _SIDE_STREAMS:
+            _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+        self.side = _SIDE_STREAMS[key]
+        self.used = False
+
+    def run(self, fn):
+        if not self.enabled:
+            return fn()
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            fn()
+        self.used = True
+
+    def join(self):
+        if self.enabled and self.used:
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            self.main.wait_event(ev)
+
+
 def _w(param: torch.Tensor, dt: int) -> torch.Tensor:
     """Operand copy of a weight in the compute dtype.  bf16 shadow copies are cached per parameter OBJECT (weakly
     referenced, so an address reused by another model's parameter can never alias) and re-cast when the
@@ -150,6 +189,7 @@ class SwinBlockFn(torch.autograd.Function):
         dfc2w, dfc1w, dprojw, dqkvw, dfc1b, dqkvb_buf, dfc2b_buf, dgb2, dgb1, dbias_buf, dtable_buf = _zeros_flat(
             dx2.device, tuple(fc2w.shape), tuple(fc1w.shape), tuple(projw.shape), tuple(qkvw.shape), (hid,), (3 * Cc,),
             (Cc,), (3, Cc), (3, Cc), (nH, N, N), tuple(table.shape))
+        lane = _SideLane(dx2.device)
         got = ctx.recv.take(dx2) if ctx.recv is not None else None
         if got is not None:
             dy2, dfc2b = got                         # emitted by the next block's LN1 backward (BlockLink)
@@ -159,10 +199,10 @@ class SwinBlockFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         n_qkv, n_proj, n_fc1, n_fc2 = need[4] or need[5], need[6] or need[7], need[10] or need[11], need[12] or need[13]
         if n_fc2:
-            ops.gemm(dy2, h, Cc, hid, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc2w)
+            lane.run(lambda: ops.gemm(dy2, h, Cc, hid, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc2w))
         du = ops.gemm(dy2, _w(fc2w, dt), T, hid, Cc, b_trans=True, epilogue=L.EPI_DGELU, aux=u)
         if n_fc1:
-            ops.gemm(du, xn, hid, Cc, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc1w, colsum_a=dfc1b)
+            lane.run(lambda: ops.gemm(du, xn, hid, Cc, T, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dfc1w, colsum_a=dfc1b))
         dxn = ops.gemm(du, _w(fc1w, dt), T, Cc, hid, b_trans=True)
         # LN2 backward + residual-gradient add; the same kernel also emits dY of the proj Linear (drop-path scaled,
         # cast and partitioned into window slots) and its column sums (= d proj.bias)
@@ -170,15 +210,16 @@ class SwinBlockFn(torch.autograd.Function):
                                                   emit_windows=(ws, shift, s1), dgb=dgb2)
         # ---- attention branch
         if n_proj:
-            ops.gemm(dy1, o, Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dprojw)
+            lane.run(lambda: ops.gemm(dy1, o, Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dprojw))
         do = ops.gemm(dy1, _w(projw, dt), Tp, Cc, Cc, b_trans=True)
         dqkv, dbias = ops.window_attn_bwd(qkv.view(-1, N, 3 * Cc), o, do.view(-1, N, Cc), lse, bias, mask, Tp // N, nH, ws, scale, mask_nz, canon,
                                           dbias=dbias_buf)
         dtable = ops.rel_bias_reduce(dbias, ws, out=dtable_buf) if need[3] else None
         dqkvb = dqkvb_buf if has_qkvb else None
         if n_qkv:
-            ops.gemm(dqkv, xw, 3 * Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dqkvw, colsum_a=dqkvb)
+            lane.run(lambda: ops.gemm(dqkv, xw, 3 * Cc, Cc, Tp, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dqkvw, colsum_a=dqkvb))
         if not (need[0] or need[1] or need[2]):
+            lane.join()
             # first trainable block behind frozen stages: nothing upstream wants dx, norm1 is frozen too
             return (None, None, None, dtable, dqkvw if need[4] else None, dqkvb if need[5] else None, dprojw if need[6] else None,
                     dprojb if need[7] else None, dn2w, dn2b, dfc1w if need[10] else None, dfc1b if need[11] else None,
@@ -191,6 +232,7 @@ class SwinBlockFn(torch.autograd.Function):
             ctx.send.deposit(dx, dyp, csp)
         else:
             dx, dn1w, dn1b = ops.ln_bwd(1, dxw, x, n1w.detach(), mean1, rstd1, dx1, B, H, W, Cc, ws, shift, dgb=dgb1)
+        lane.join()
         return (dx, dn1w, dn1b, dtable, dqkvw if need[4] else None, dqkvb if need[5] else None, dprojw if need[6] else None,
                 dprojb if need[7] else None, dn2w, dn2b, dfc1w if need[10] else None, dfc1b if need[11] else None,
                 dfc2w if need[12] else None, dfc2b if need[13] else None) + (None,) * 16

@@ -53,9 +53,14 @@ def test_argument_validation_is_errno_style_and_does_not_need_a_gpu(lib):
     assert lib.swin_window_gather(16, 16, 1, 7, 7, 3, 7, 0, 2, None) == -22  # row bytes not a multiple of 16
     assert lib.swin_window_gather(16, 16, 1, 7, 7, 8, 7, 7, 2, None) == -22  # shift must be < ws
     assert lib.swin_shift_mask(16, 0, 7, 7, 3, None) == -22
-    at = L.AttnArgs(dtype=L.BF16, B_=4, nH=3, ws=12, qkv=16, bias=16, out=16, lse=16, scale=1.0)
+    at = L.AttnArgs(dtype=L.BF16, B_=5, nH=3, ws=7, nW=2, qkv=16, bias=16, mask=16, out=16, lse=16, scale=1.0)
     assert lib.swin_window_attn_fwd(ctypes.byref(at), None) == -22
+    assert b"multiple of nW" in lib.swin_last_error()
+    aq = L.AttnQkvArgs(B_=4, nH=3, ws=12, x=16, wqkv=16, bias=16, out=16, scale=1.0)
+    assert lib.swin_window_attn_qkv_fwd(ctypes.byref(aq), None) == -22
     assert b"window_size 7" in lib.swin_last_error()
+    assert lib.swin_window_attn_qkv_supported(384, 12, 7) == 1 and lib.swin_window_attn_qkv_supported(512, 16, 7) == 0
+    assert lib.swin_window_attn_qkv_workspace(96, 3, 7) == 3 * 52 * 64 * 4
     with pytest.raises(RuntimeError):
         L.check(-22, "demo")
 
