@@ -528,6 +528,22 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
         epi_rowscale[ew][lane] = scale;
       }
       __syncwarp();
+      // Residual epilogues read their aux rows (fp32 x, scattered by the window-reverse map) with plain loads right before use:
+      // with 8 float4 per lane in flight the read stream is latency-bound (bytes in flight / latency).  The NEXT unit's rows
+      // are therefore pulled into L2 now, a whole unit ahead: lane = one row, one prefetch per 128-byte line of this warp's chunks.
+      if (p.epi.epilogue == SWIN_EPI_SCATTER_RESIDUAL || p.epi.epilogue == SWIN_EPI_RESIDUAL) {
+        WorkIter wn = w;
+        if (wn.next()) {
+          const int nrow = (wn.tile / p.n_tiles) * TM + (int)cta_rank * TBM + q * 32 + lane;
+          const int nn0 = (wn.tile % p.n_tiles) * p.block_n;
+          long long drow = 0; float scale = 1.f;
+          if (epi_row_setup(p.epi, nrow, &drow, &scale)) {
+            const float* src = reinterpret_cast<const float*>(p.epi.aux) + drow * p.epi.ldd + nn0;
+            for (int cc = ((ew >> 2) ^ (int)((u + 1) & 1)) * 32; cc < p.block_n && nn0 + cc < p.epi.N; cc += 64)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(src + cc));
+          }
+        }
+      }
       PROF_WAIT(prof_w0, mbar_wait(tfull_bar(acc), acc_ph));
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
