@@ -271,9 +271,13 @@ def backbone_forward(img: torch.Tensor, p: Dict[str, torch.Tensor], embed_dim: i
                      window_size: int = 7, patch_size: int = 4, patch_norm: bool = True,
                      out_indices: Sequence[int] = (0, 1, 2, 3), qk_scale: Optional[float] = None,
                      drop_scales: Optional[List[Tuple[torch.Tensor, torch.Tensor]]] = None) -> Tuple[torch.Tensor, ...]:
-    """SwinTransformer.forward (REF:600-625), ape=False, dropout 0.  ``drop_scales`` optionally
-    gives the host-drawn DropPath multipliers per block in execution order."""
+    """SwinTransformer.forward (REF:600-625), dropout 0.  ``drop_scales`` optionally gives the host-drawn DropPath
+    multipliers per block in execution order.  ape=True (REF:604-607) is selected by the presence of
+    ``absolute_pos_embed`` (1, C, Hpre, Wpre) in ``p``: bicubic-interpolated to the token grid and added before the first block."""
     x, H, W = patch_embed(img, p, patch_size, patch_norm)
+    if "absolute_pos_embed" in p:
+        pos = torch.nn.functional.interpolate(p["absolute_pos_embed"], size=(H, W), mode="bicubic")      # REF:606
+        x = x + pos.flatten(2).transpose(1, 2)
     outs = []
     blk_no = 0
     for s, depth in enumerate(depths):

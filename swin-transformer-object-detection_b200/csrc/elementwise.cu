@@ -116,25 +116,24 @@ __global__ void rel_bias_expand_kernel(const float* __restrict__ table, float* _
     bias[e] = table[rel_index(i, j, ws) * nH + h];
   }
 }
-// one thread per table entry: deterministic gather-sum of every (i,j) that maps to it
+// one WARP per table entry: deterministic gather-sum of every (i,j) that maps to it -- the (rj, cj) pairs of an entry are spread
+// over the lanes (fixed assignment, fixed shuffle tree), so the result does not depend on scheduling
 __global__ void rel_bias_reduce_kernel(const float* __restrict__ dbias, float* __restrict__ dtable, int nH, int ws) {
-  int R = 2 * ws - 1;
-  int total = R * R * nH;
-  int N = ws * ws;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    int h = e % nH, r = e / nH;
-    int dr = r / R - (ws - 1), dc = r % R - (ws - 1);   // ri - rj, ci - cj
+  const int R = 2 * ws - 1;
+  const int total = R * R * nH;
+  const int N = ws * ws;
+  const int lane = threadIdx.x & 31;
+  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total; e += (gridDim.x * blockDim.x) >> 5) {
+    const int h = e % nH, r = e / nH;
+    const int dr = r / R - (ws - 1), dc = r % R - (ws - 1);   // ri - rj, ci - cj
     float s = 0.f;
-    for (int rj = 0; rj < ws; ++rj) {
-      int ri = rj + dr;
-      if (ri < 0 || ri >= ws) continue;
-      for (int cj = 0; cj < ws; ++cj) {
-        int ci = cj + dc;
-        if (ci < 0 || ci >= ws) continue;
-        s += dbias[((size_t)h * N + (ri * ws + ci)) * N + (rj * ws + cj)];
-      }
+    for (int t = lane; t < N; t += 32) {
+      const int rj = t / ws, cj = t - rj * ws;
+      const int ri = rj + dr, ci = cj + dc;
+      if (ri >= 0 && ri < ws && ci >= 0 && ci < ws) s += dbias[((size_t)h * N + (ri * ws + ci)) * N + t];
     }
-    dtable[e] += s;
+    s = warp_sum(s);
+    if (lane == 0) dtable[e] += s;
   }
 }
 
@@ -959,7 +958,7 @@ extern "C" int swin_rel_bias_expand(const float* table, float* bias, int nH, int
 extern "C" int swin_rel_bias_reduce(const float* dbias, float* dtable, int nH, int ws, void* stream) {
   SWIN_REQUIRE(nH > 0 && ws > 0, "rel_bias_reduce: bad shape");
   int total = (2 * ws - 1) * (2 * ws - 1) * nH;
-  rel_bias_reduce_kernel<<<ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(dbias, dtable, nH, ws);
+  rel_bias_reduce_kernel<<<ceil_div(total, 8), 256, 0, (cudaStream_t)stream>>>(dbias, dtable, nH, ws);
   SWIN_LAUNCH_CHECK();
   return 0;
 }

@@ -38,6 +38,32 @@ __global__ void __launch_bounds__(256) patch_unfold_kernel(float* __restrict__ i
   }
 }
 
+// Forward gather for 4x4 patches and bf16 columns (the benchmark's PatchEmbed): one thread = one (token, channel): four 16-byte
+// image-row reads (consecutive threads = consecutive patches of one image row: coalesced) and ONE whole 32-byte sector written
+// ([c][i][j] = 16 bf16).  The generic kernel above writes 8-byte pieces 96 bytes apart (2.1 TB/s); this one is a plain stream.
+__global__ void __launch_bounds__(256) patch_unfold4_bf16_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ cols, int Cin,
+                                                                 int Hi, int Wi, int Hh, int Ww) {
+  const int bp = blockIdx.y;                         // b * Hh + ph
+  const int b = bp / Hh, ph = bp - b * Hh;
+  const int K = Cin * 16;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < Cin * Ww; t += gridDim.x * blockDim.x) {
+    const int c = t / Ww, pw = t - c * Ww;
+    const float* src = img + (((long long)b * Cin + c) * Hi + ph * 4) * Wi + pw * 4;
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v[4];
+      const bool rowin = ph * 4 + i < Hi;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (rowin && pw * 4 + j < Wi) ? __ldg(src + (long long)i * Wi + j) : 0.f;
+      o[2 * i] = pack_bf16(v[0], v[1]); o[2 * i + 1] = pack_bf16(v[2], v[3]);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(cols + ((long long)bp * Ww + pw) * K + c * 16);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ LN + NCHW store
 // A block owns a tile of 32 consecutive tokens.  Each token is normalised by a group of G lanes holding VPL float4
 // (like the LN kernels in elementwise.cu), so 8 warps x 32/G tokens are in flight per round; the tile is then
@@ -253,6 +279,12 @@ extern "C" int swin_patch_gather(const float* img, void* cols, int B, int Cin, i
   const int Hh = ceil_div(Hi, patch), Ww = ceil_div(Wi, patch);
   long long total = (long long)B * Cin * Hh * patch * Ww;
   int grid = (int)(ceil_div64(total, 256) < (long long)kNumSMs * 16 ? ceil_div64(total, 256) : (long long)kNumSMs * 16);
+  if (dtype == SWIN_BF16 && patch == 4 && aligned16(cols)) {
+    dim3 g4((unsigned)ceil_div(Cin * Ww, 256), (unsigned)(B * Hh));
+    patch_unfold4_bf16_kernel<<<g4, 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)cols, Cin, Hi, Wi, Hh, Ww);
+    SWIN_LAUNCH_CHECK();
+    return 0;
+  }
   if (dtype == SWIN_F32) patch_unfold_kernel<float, false><<<grid, 256, 0, (cudaStream_t)stream>>>(const_cast<float*>(img), (float*)cols, B, Cin, Hi, Wi, patch, Hh, Ww);
   else if (dtype == SWIN_BF16) patch_unfold_kernel<__nv_bfloat16, false><<<grid, 256, 0, (cudaStream_t)stream>>>(const_cast<float*>(img), (__nv_bfloat16*)cols, B, Cin, Hi, Wi, patch, Hh, Ww);
   else { set_error("patch_gather: bad dtype"); return -EINVAL; }

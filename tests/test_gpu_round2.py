@@ -253,3 +253,64 @@ def test_no_grad_forward_uses_fused_kernel_and_matches_training_forward():
     assert n_fused == 2 and n_fused_g == 0          # the two stage-0 blocks (C = 96, resident weights); C = 192 keeps the two-kernel chain
     for a, b in zip(outs_ng, outs_g):
         assert so.rel_l2(a, b) < 5e-3
+
+
+def test_window12_model_runs_in_bf16_mode_and_matches_fp32_mode():
+    """Window 12 (the 384-pixel Swin-B/L configs): bf16 mode keeps every GEMM on tcgen05 and runs the attention core on the
+    fp32-arithmetic kernels with bf16 storage; outputs and gradients agree with the fp32 mode (itself oracle-checked for window 12 at
+    kernel level) within the bf16 tolerance.  Seeded noisy weights and random cotangents (with gamma = 1 and a plain sum as the
+    loss, the gradient through the output LayerNorm is identically zero and every comparison would be noise against noise)."""
+    import swin_b200
+    cfg = dict(embed_dim=64, depths=[2, 2], num_heads=[2, 4], window_size=12, out_indices=(0, 1))
+    shapes = so.param_shapes(cfg["embed_dim"], cfg["depths"], cfg["num_heads"], cfg["window_size"], out_indices=cfg["out_indices"])
+    params = so.seeded_params(shapes, seed=21)
+    nets = {}
+    for mode in ("fp32", "bf16"):
+        net = swin_b200.SwinTransformer(drop_path_rate=0.0, compute_dtype=mode, **cfg)
+        sd = net.state_dict()
+        for k in sd:
+            if not k.endswith("relative_position_index"):
+                sd[k] = params[k]
+        net.load_state_dict(sd)
+        nets[mode] = net.to(DEV).train()
+    g = torch.Generator(device=DEV).manual_seed(4)
+    x = torch.randn(2, 3, 150, 200, device=DEV, generator=g)
+    outs_r = nets["fp32"](x)
+    cots = [torch.randn(o.shape, device=DEV, generator=g) for o in outs_r]
+    torch.autograd.backward(outs_r, cots)
+    outs = nets["bf16"](x)
+    torch.autograd.backward(outs, cots)
+    torch.cuda.synchronize()
+    for a, b in zip(outs, outs_r):
+        assert so.rel_l2(a, b) < 2e-2
+    errs = sorted(((so.rel_l2(p.grad, q.grad), k) for (k, p), (_, q) in zip(nets["bf16"].named_parameters(), nets["fp32"].named_parameters())), reverse=True)
+    assert errs[0][0] < 4e-2, errs[:5]
+
+
+def test_absolute_position_embedding_path_vs_oracle():
+    """ape=True (REF:513-517, :604-607): the bicubic-interpolated absolute position embedding is added to the patch tokens before
+    the first block; fp32 mode against the oracle (pinned to the live reference for this path by
+    tests/test_oracle_vs_reference.py), outputs and every gradient incl. absolute_pos_embed."""
+    import swin_b200
+    cfg = dict(embed_dim=32, depths=[2, 2], num_heads=[1, 2], window_size=7, out_indices=(0, 1))
+    shapes = so.param_shapes(cfg["embed_dim"], cfg["depths"], cfg["num_heads"], cfg["window_size"], out_indices=cfg["out_indices"])
+    shapes["absolute_pos_embed"] = (1, 32, 14, 14)
+    params = so.seeded_params(shapes, seed=11)
+    img = torch.from_numpy(np.random.default_rng(2).standard_normal((2, 3, 60, 84)).astype(np.float32))
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    outs_r = so.backbone_forward(img, p, **cfg)
+    sum(o.sum() for o in outs_r).backward()
+    net = swin_b200.SwinTransformer(drop_path_rate=0.0, compute_dtype="fp32", ape=True, pretrain_img_size=56, **cfg)
+    sd = net.state_dict()
+    for k in sd:
+        if not k.endswith("relative_position_index"):
+            sd[k] = params[k]
+    net.load_state_dict(sd)
+    net = net.to(DEV).train()
+    outs = net(img.to(DEV))
+    sum(o.sum() for o in outs).backward()
+    torch.cuda.synchronize()
+    for a, b in zip(outs, outs_r):
+        assert so.rel_l2(a, b) < 1e-4
+    for k, v in net.named_parameters():
+        assert so.rel_l2(v.grad, p[k].grad) < 1e-4, k

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="/root/refere
 
 def _load_ref(cfg, params):
     ref = ref_loader.load()
-    net = ref.SwinTransformer(drop_path_rate=0.0, **cfg)
+    net = ref.SwinTransformer(drop_path_rate=0.0, ape="absolute_pos_embed" in params, pretrain_img_size=56, **cfg)
     sd = net.state_dict()
     for k in sd:
         if k.endswith("relative_position_index") or k.endswith("attn_mask"):
@@ -28,10 +28,15 @@ def _load_ref(cfg, params):
     (dict(embed_dim=32, depths=[2, 2], num_heads=[1, 2], window_size=7, out_indices=(0, 1)), 2, (50, 70)),
     (dict(embed_dim=96, depths=[2, 2, 2, 2], num_heads=[3, 6, 12, 24], window_size=7, out_indices=(0, 1, 2, 3)), 1, (224, 300)),
     (dict(embed_dim=32, depths=[2], num_heads=[1], window_size=12, out_indices=(0,)), 1, (90, 100)),
+    (dict(embed_dim=32, depths=[2, 2], num_heads=[1, 2], window_size=7, out_indices=(0, 1), _ape=True), 2, (60, 84)),
 ])
 def test_oracle_matches_live_reference_forward_and_backward(cfg, B, HW):
     torch.manual_seed(0)
+    cfg = dict(cfg)
+    ape = cfg.pop("_ape", False)
     shapes = so.param_shapes(cfg["embed_dim"], cfg["depths"], cfg["num_heads"], cfg["window_size"], out_indices=cfg["out_indices"])
+    if ape:                                              # REF:513-517: (1, C, pretrain/patch, pretrain/patch)
+        shapes["absolute_pos_embed"] = (1, cfg["embed_dim"], 14, 14)
     params = so.seeded_params(shapes, seed=3)
     img = torch.from_numpy(np.random.default_rng(1).standard_normal((B, 3) + HW).astype(np.float32))
     net = _load_ref(cfg, params)
