@@ -87,13 +87,28 @@ constexpr int kBiasLd = 68;                      // sBias row pitch (floats): 64
 constexpr float kNegBig = -1.0e30f;
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-__device__ __forceinline__ void load_bias_tile(float* sBias, const float* __restrict__ bias, int h) {
+// bias tile of head h -> shared memory, row pitch LD, pre-scaled by log2(e), pad columns kNegBig.  The global loads of a batch of
+// four elements per thread are issued before any of them is used: as a plain load-then-store loop the prologue of a CTA was
+// 13-20 dependent L2 round trips (~5 us of a 45-65 us launch at the stage-2/3 shapes).
+template <int LD>
+__device__ __forceinline__ void load_bias_tile_ld(float* sBias, const float* __restrict__ bias, int h) {
   const float kLog2e = 1.4426950408889634f;
-  for (int e = threadIdx.x; e < AN * kBiasLd; e += blockDim.x) {
-    const int i = e / kBiasLd, j = e - i * kBiasLd;
-    sBias[e] = j < AN ? bias[((size_t)h * AN + i) * AN + j] * kLog2e : kNegBig;
+  const float* src = bias + (size_t)h * AN * AN;
+  const int n = AN * LD, step = blockDim.x;
+  for (int e0 = threadIdx.x; e0 < n; e0 += 4 * step) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * step;
+      const int i = e / LD, j = e - i * LD;
+      v[u] = (e < n && j < AN) ? __ldg(src + i * AN + j) * kLog2e : kNegBig;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (e0 + u * step < n) sBias[e0 + u * step] = v[u];
   }
 }
+__device__ __forceinline__ void load_bias_tile(float* sBias, const float* __restrict__ bias, int h) { load_bias_tile_ld<kBiasLd>(sBias, bias, h); }
 
 // Development aid: -DSWIN_ATTN_TIMING accumulates per-phase clock64() deltas of one softmax thread of CTA 0 and
 // prints them at kernel exit (never enabled in the shipped library).
@@ -134,13 +149,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
   const uint32_t bar_qk = smem_u32(&bars[0]), bar_v = smem_u32(&bars[1]), bar_s = smem_u32(&bars[2]), bar_o = smem_u32(&bars[3]), bar_free = smem_u32(&bars[4]);
 
   zero_smem(sT, kFwdTiles + kPBytes);
-  {
-    const float kLog2e = 1.4426950408889634f;
-    for (int e = tid; e < AN * kFwdBiasLd; e += blockDim.x) {
-      const int bi = e / kFwdBiasLd, bj = e - bi * kFwdBiasLd;
-      sBias[e] = bj < AN ? p.bias[((size_t)h * AN + bi) * AN + bj] * kLog2e : kNegBig;
-    }
-  }
+  load_bias_tile_ld<kFwdBiasLd>(sBias, p.bias, h);
   if (tid == 0) {
     mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_free, 1);
     fence_barrier_init();
