@@ -407,7 +407,9 @@ class OutNormMergeFn(torch.autograd.Function):
     residual gradient (``dres``) it already knows how to add, so x's gradient is written once."""
 
     @staticmethod
-    def forward(ctx, x, onw, onb, mnw, mnb, redw, H, W, dt, eps_out, eps_merge):
+    def forward(ctx, x, onw, onb, mnw, mnb, redw, H, W, dt, eps_out, eps_merge, recv=None):
+        """``recv``: BlockLink to the FIRST block of the next stage, whose LN1 backward holds this node's incoming dy in registers
+        and emits its compute-dtype copy (what ``scale_cast`` would produce here with a pass of its own)."""
         B, Lx, Cc = x.shape
         x = _f32c(x)
         out, omean, orstd = ops.ln_nchw_fwd(x, onw.detach(), onb.detach(), H, W, eps_out)
@@ -416,6 +418,7 @@ class OutNormMergeFn(torch.autograd.Function):
         y = ops.gemm(g.view(T2, 4 * Cc), _w(redw, dt), T2, 2 * Cc, 4 * Cc, out_dtype=L.F32)
         ctx.save_for_backward(x, onw, omean, orstd, mnw, redw, g, mean, rstd)
         ctx.cfg = (B, H, W, Cc, dt, T2)
+        ctx.recv = recv
         return out, y.view(B, g.shape[1], 2 * Cc)
 
     @staticmethod
@@ -423,11 +426,18 @@ class OutNormMergeFn(torch.autograd.Function):
         x, onw, omean, orstd, mnw, redw, g, mean, rstd = ctx.saved_tensors
         B, H, W, Cc, dt, T2 = ctx.cfg
         dx_out, dog, dob = ops.ln_nchw_bwd(_f32c(dout), x, onw.detach(), omean, orstd)
-        dyf = _f32c(dy).view(T2, 2 * Cc)
-        dy1 = dyf if dt == L.F32 else ops.scale_cast(dyf, None, 0, 1, T2, 1, 2 * Cc, 1, 0, dt)
+        dyc = _f32c(dy)
+        dyf = dyc.view(T2, 2 * Cc)
+        got = ctx.recv.take(dyc) if ctx.recv is not None else None
+        if dt == L.F32:
+            dy1 = dyf
+        elif got is not None:
+            dy1 = got[0].view(T2, 2 * Cc)          # emitted by the next stage's first LN1 backward (BlockLink)
+        else:
+            dy1 = ops.scale_cast(dyf, None, 0, 1, T2, 1, 2 * Cc, 1, 0, dt)
         dredw = torch.zeros_like(redw, dtype=torch.float32)
         ops.gemm(dy1, g.view(T2, 4 * Cc), 2 * Cc, 4 * Cc, T2, a_trans=True, b_trans=True, epilogue=L.EPI_ATOMIC_ADD, out=dredw)
         dg = ops.gemm(dy1, _w(redw, dt), T2, 4 * Cc, 2 * Cc, b_trans=True)
         dx, dnw, dnb = ops.ln_bwd(2, dg, x, mnw.detach(), mean, rstd, dx_out, B, H, W, Cc, 1, 0)
-        return dx, dog, dob, dnw, dnb, dredw, None, None, None, None, None
+        return dx, dog, dob, dnw, dnb, dredw, None, None, None, None, None, None
 

@@ -24,6 +24,8 @@ from . import ops
 from .functional import BlockLink, MlpFn, OutNormFn, OutNormMergeFn, PatchEmbedFn, PatchMergingFn, SwinBlockFn, WindowAttentionFn
 from .registry import register_backbone
 
+_STAGE_LINK = os.environ.get("SWIN_STAGE_LINK", "1") != "0"      # A/B knob: 0 = the PatchMerging dY cast runs as its own scale_cast pass
+
 
 def _dt_code(compute_dtype: Optional[str]) -> int:
     v = (compute_dtype or os.environ.get("SWIN_B200_DTYPE", "bf16")).lower()
@@ -297,16 +299,19 @@ class BasicLayer(nn.Module):
             self._mask_cache[key] = m
         return m
 
-    def forward(self, x, H, W, out_norm=None):
+    def forward(self, x, H, W, out_norm=None, stage_send=None):
         """Reference signature ``forward(x, H, W) -> (x, H, W, x_down, Wh, Ww)`` (REF:362, :397-402).  With ``out_norm`` (the
         backbone's norm{i} module; SwinTransformer.forward passes it) the first element is already norm{i}(x) in NCHW:
-        the output norm and the downsample then form one autograd node (functional.OutNormMergeFn)."""
+        the output norm and the downsample then form one autograd node (functional.OutNormMergeFn).  ``stage_send``: the
+        previous stage's link (its OutNormMergeFn takes the compute-dtype copy of its incoming gradient from this stage's first
+        LN1 backward); this stage's own link is left in ``self.stage_link`` for the next one."""
         _need_cuda(x, "BasicLayer")
         mask = self.attn_mask(H, W, x.device)
         # backward hand-over between consecutive blocks (functional.BlockLink); not under activation checkpointing, whose
         # recomputation would run the blocks' forwards out of order
         link = torch.is_grad_enabled() and not self.use_checkpoint
-        send = None
+        send = stage_send if link else None
+        self.stage_link = None
         for bi, blk in enumerate(self.blocks):
             blk.H, blk.W = H, W
             if self.use_checkpoint:
@@ -318,8 +323,11 @@ class BasicLayer(nn.Module):
         if self.downsample is not None:
             if out_norm is not None:
                 ds = self.downsample
+                if link and ds._dt == L.BF16 and _STAGE_LINK:
+                    self.stage_link = BlockLink()
                 out, x_down = OutNormMergeFn.apply(x, out_norm.weight, out_norm.bias, ds.norm.weight, ds.norm.bias,
-                                                   ds.reduction.weight, H, W, ds._dt, float(out_norm.eps), float(ds.norm.eps))
+                                                   ds.reduction.weight, H, W, ds._dt, float(out_norm.eps), float(ds.norm.eps),
+                                                   self.stage_link)
                 return out, H, W, x_down, (H + 1) // 2, (W + 1) // 2
             x_down = self.downsample(x, H, W)
             return x, H, W, x_down, (H + 1) // 2, (W + 1) // 2
@@ -465,7 +473,8 @@ class SwinTransformer(nn.Module):
         outs = []
         for i, layer in enumerate(self.layers):
             n = getattr(self, f"norm{i}") if (apply_out_norm and i in self.out_indices) else None
-            x_out, H, W, x, Wh, Ww = layer(x, Wh, Ww) if n is None else layer(x, Wh, Ww, out_norm=n)
+            prev_link = getattr(self.layers[i - 1], "stage_link", None) if i > 0 else None
+            x_out, H, W, x, Wh, Ww = layer(x, Wh, Ww, stage_send=prev_link) if n is None else layer(x, Wh, Ww, out_norm=n, stage_send=prev_link)
             if i in self.out_indices:
                 outs.append((i, x_out, H, W))
         return outs
