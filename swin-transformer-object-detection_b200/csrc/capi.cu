@@ -88,14 +88,14 @@ extern "C" int swin_gemm_plan(const swin_gemm_args* a, int* out6) { return gemm_
 extern "C" int swin_window_attn_fwd(const swin_attn_args* a, void* stream) {
   if (!a) { set_error("attn: null args"); return -EINVAL; }
   if (a->dtype == SWIN_F32) return attn_simt_fwd(a, (cudaStream_t)stream);
-  if (a->dtype == SWIN_BF16) return a->ws == 7 ? attn_tc_fwd(a, (cudaStream_t)stream) : attn_simt_fwd(a, (cudaStream_t)stream);
+  if (a->dtype == SWIN_BF16) return a->ws == 7 ? attn_tc_fwd(a, (cudaStream_t)stream) : (a->ws == 12 ? attn_mma_fwd(a, (cudaStream_t)stream) : attn_simt_fwd(a, (cudaStream_t)stream));
   set_error("attn: bad dtype %d", a->dtype);
   return -EINVAL;
 }
 extern "C" int swin_window_attn_bwd(const swin_attn_args* a, void* stream) {
   if (!a) { set_error("attn: null args"); return -EINVAL; }
   if (a->dtype == SWIN_F32) return attn_simt_bwd(a, (cudaStream_t)stream);
-  if (a->dtype == SWIN_BF16) return a->ws == 7 ? attn_tc_bwd(a, (cudaStream_t)stream) : attn_simt_bwd(a, (cudaStream_t)stream);
+  if (a->dtype == SWIN_BF16) return a->ws == 7 ? attn_tc_bwd(a, (cudaStream_t)stream) : (a->ws == 12 ? attn_mma_bwd(a, (cudaStream_t)stream) : attn_simt_bwd(a, (cudaStream_t)stream));
   set_error("attn: bad dtype %d", a->dtype);
   return -EINVAL;
 }

@@ -157,6 +157,8 @@ int set_pair_mode(int mode);
 int gemm_tc_plan(const swin_gemm_args* a, int* out6);
 int attn_simt_fwd(const swin_attn_args* a, cudaStream_t st);
 int attn_simt_bwd(const swin_attn_args* a, cudaStream_t st);
+int attn_mma_fwd(const swin_attn_args* a, cudaStream_t st);
+int attn_mma_bwd(const swin_attn_args* a, cudaStream_t st);
 int attn_tc_fwd(const swin_attn_args* a, cudaStream_t st);
 int attn_tc_bwd(const swin_attn_args* a, cudaStream_t st);
 int attn_qkv_fwd(const swin_attn_qkv_args* a, cudaStream_t st);
