@@ -38,9 +38,17 @@ class BucketedGradAllReduce:
         self.params = params
         if self.world > 1 and broadcast_params:
             with torch.no_grad():
-                for p in params:                  # DDP-constructor behaviour: rank 0's weights win.  Broadcasting into the
-                    dist.broadcast(p, src=0, group=process_group)   # parameter itself (not .data) bumps its version counter,
-                                                                    # so cached bf16 operand copies (functional._W16) are re-cast
+                for p in params:                  # DDP-constructor behaviour: rank 0's weights win
+                    dist.broadcast(p, src=0, group=process_group)
+            # a c10d collective writes the parameter without bumping its version counter, so bf16 operand copies cached by an
+            # earlier forward (functional._W16, keyed by parameter version) would survive on the ranks whose weights were just
+            # replaced: drop them (tests/ddp_nccl_worker.py starts rank 1 from other weights and runs a forward first)
+            try:
+                from . import functional as _F
+                for p in params:
+                    _F._W16.pop(id(p), None)
+            except ImportError:                   # gloo / CPU unit tests drive this class with plain torch modules
+                pass
         self._cap = int(bucket_mb * 1024 * 1024 / 4)
         self._tail = int(tail_kb * 1024 / 4)
         self._cuda = params[0].is_cuda if params else False
