@@ -149,13 +149,15 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
   const uint32_t bar_qk = smem_u32(&bars[0]), bar_v = smem_u32(&bars[1]), bar_s = smem_u32(&bars[2]), bar_o = smem_u32(&bars[3]), bar_free = smem_u32(&bars[4]);
 
   zero_smem(sT, kFwdTiles + kPBytes);
-  load_bias_tile_ld<kFwdBiasLd>(sBias, p.bias, h);
   if (tid == 0) {
     mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_free, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmQKV);
   }
   if (warp == 0) { tmem_alloc(smem_u32(&tmem_slot), 128); tmem_relinquish(); }
+  pdl_wait();                                    // (PDL) the above overlapped the previous kernel's tail; from here on global memory
+  pdl_trigger();
+  load_bias_tile_ld<kFwdBiasLd>(sBias, p.bias, h);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -386,7 +388,6 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_tc_bwd_kernel(const __gri
   const uint32_t bar_load0 = smem_u32(&bars[0]), bar_s = smem_u32(&bars[2]), bar_o = smem_u32(&bars[3]);
 
   zero_smem(sT, 2 * kBwdTiles + 2 * kPBytes);
-  load_bias_tile(sBias, p.bias, h);
   if (tid == 0) {
     mbar_init(bar_load0, 1); mbar_init(bar_load0 + 8, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
     fence_barrier_init();
@@ -395,6 +396,9 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_tc_bwd_kernel(const __gri
     tma_prefetch_desc(&tmDQKV);
   }
   if (warp == 0) { tmem_alloc(smem_u32(&tmem_slot), 256); tmem_relinquish(); }
+  pdl_wait();                                    // (PDL) the above overlapped the previous kernel's tail; from here on global memory
+  pdl_trigger();
+  load_bias_tile(sBias, p.bias, h);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -705,7 +709,14 @@ int attn_tc_fwd(const swin_attn_args* a, cudaStream_t st) {
   CUtensorMap tmo;
   rc = make_tmap_bf16_2d(&tmo, a->out, (uint64_t)p.C, (uint64_t)p.B_ * AN, (uint64_t)p.C * 2, AHD, AN, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
-  attn_tc_fwd_kernel<<<p.nH * p.ctas_per_head, kFwdThreads, smem, st>>>(tm, tmo, p);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(p.nH * p.ctas_per_head)); cfg.blockDim = dim3(kFwdThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute lattr[1];
+    cfg.attrs = lattr; cfg.numAttrs = pdl_attr(&lattr[0]);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, attn_tc_fwd_kernel, tm, tmo, p);
+    if (le != cudaSuccess) { set_error("attn_tc_fwd launch: %s", cudaGetErrorString(le)); return (int)le; }
+  }
   SWIN_LAUNCH_CHECK();
   return 0;
 }
@@ -726,7 +737,14 @@ int attn_tc_bwd(const swin_attn_args* a, cudaStream_t st) {
   CUtensorMap tmdq;
   rc = make_tmap_bf16_2d(&tmdq, a->dqkv, (uint64_t)3 * p.C, (uint64_t)p.B_ * AN, (uint64_t)3 * p.C * 2, AHD, AN, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
-  attn_tc_bwd_kernel<<<p.nH * p.ctas_per_head, kBwdThreads, smem, st>>>(tm, tmdo, tmdq, p);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(p.nH * p.ctas_per_head)); cfg.blockDim = dim3(kBwdThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute lattr[1];
+    cfg.attrs = lattr; cfg.numAttrs = pdl_attr(&lattr[0]);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, attn_tc_bwd_kernel, tm, tmdo, tmdq, p);
+    if (le != cudaSuccess) { set_error("attn_tc_bwd launch: %s", cudaGetErrorString(le)); return (int)le; }
+  }
   SWIN_LAUNCH_CHECK();
   return 0;
 }

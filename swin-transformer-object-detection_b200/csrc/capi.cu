@@ -7,6 +7,7 @@
 #include <set>
 #include <utility>
 
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace swin {
@@ -38,6 +39,10 @@ int persistent_sms() {
 
 static std::mutex g_attr_mu;
 static std::set<std::pair<const void*, int>> g_attr_done;
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("SWIN_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 int ensure_dyn_smem(const void* func, int bytes) {
   int dev = 0;
   cudaGetDevice(&dev);

@@ -150,6 +150,24 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the attribute may begin while its predecessor in the stream is still
+// running; everything it does before pdl_wait() (barrier init, TMEM allocation, shared-memory zeroing: no global access) overlaps
+// the predecessor's tail.  pdl_wait() returns once every prerequisite grid has completed and its writes are visible; pdl_trigger()
+// (issued right after it, so completion stays transitive along the stream) lets the NEXT kernel's CTAs be scheduled as SMs free up.
+// Under stream capture the attribute becomes a programmatic edge of the CUDA graph.  SWIN_PDL=0 launches everything plainly.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+// fills `attr` with the programmatic-serialization attribute; returns 1 if PDL is on (number of attributes written)
+inline int pdl_attr(cudaLaunchAttribute* attr) {
+  if (!pdl_enabled()) return 0;
+  attr->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr->val.programmaticStreamSerializationAllowed = 1;
+  return 1;
+}
+
 // internal entry points implemented per translation unit
 int gemm_simt(const swin_gemm_args* a, cudaStream_t st);
 int gemm_tc(const swin_gemm_args* a, cudaStream_t st);

@@ -206,6 +206,9 @@ __global__ void __launch_bounds__(gemm_threads(EPI_CLASS), 1) gemm_tc_kernel(con
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  // everything above touched only shared memory / TMEM and overlapped the previous kernel's tail (PDL); from here on global memory
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -758,10 +761,15 @@ int gemm_tc(const swin_gemm_args* a, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};                                                                                  \
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)gemm_threads(TE));                          \
     cfg.dynamicSmemBytes = smem; cfg.stream = st;                                                                 \
-    cudaLaunchAttribute lattr[1];                                                                                 \
-    lattr[0].id = cudaLaunchAttributeClusterDimension;                                                            \
-    lattr[0].val.clusterDim.x = CT; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = 1;                 \
-    cfg.attrs = lattr; cfg.numAttrs = CT > 1 ? 1 : 0;                                                             \
+    cudaLaunchAttribute lattr[2];                                                                                 \
+    int nattr = 0;                                                                                                \
+    if (CT > 1) {                                                                                                 \
+      lattr[0].id = cudaLaunchAttributeClusterDimension;                                                          \
+      lattr[0].val.clusterDim.x = CT; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = 1;               \
+      nattr = 1;                                                                                                  \
+    }                                                                                                             \
+    nattr += pdl_attr(&lattr[nattr]);                                                                             \
+    cfg.attrs = lattr; cfg.numAttrs = nattr;                                                                      \
     cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<AM, BM, TE, CT>, tmA, tmB, tmD, tmD2, p);            \
     if (le != cudaSuccess) { set_error("gemm_tc launch: %s", cudaGetErrorString(le)); return (int)le; }           \
   } while (0)
