@@ -104,8 +104,10 @@ __device__ __forceinline__ void store_rows(const float (&o)[4][4], float s0, flo
 
 // ------------------------------------------------------------------------------------------ forward
 template <int NP>
-__global__ void __launch_bounds__(NP * 2, 1) attn_mma_fwd_kernel(AttnMmaParams p) {
-  constexpr int NT = NP / 8, NK = NP / 16;
+__global__ void __launch_bounds__(NP * 2, 2) attn_mma_fwd_kernel(AttnMmaParams p) {
+  constexpr int NT = NP / 8;
+  constexpr int CHF = 6;                                 // n-tiles (8 keys) per softmax chunk: 48 keys
+  static_assert(NT % CHF == 0, "NP must be a multiple of 48");
   constexpr int kTile = NP * kPitch;
   extern __shared__ __align__(16) uint8_t sm[];          // 2 stages x {Q, K, V}
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -121,14 +123,6 @@ __global__ void __launch_bounds__(NP * 2, 1) attn_mma_fwd_kernel(AttnMmaParams p
     load_tile<NP>(s + 2 * kTile, base + 2 * p.C, ld3);
     cp_async_commit();
   };
-  // the CTA stays on head h: its bias tile (NP x NP fp32, pre-scaled by log2 e) is staged in shared memory once -- read from L2
-  // per item it was ~1k cycles of exposed latency in a chain that one CTA per SM cannot hide
-  float* sBias = reinterpret_cast<float*>(sm + 2 * 3 * kTile);
-  for (int e = threadIdx.x; e < NP * NP / 4; e += blockDim.x) {
-    float4 v = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)h * NP * NP) + e);
-    v.x *= kL2e; v.y *= kL2e; v.z *= kL2e; v.w *= kL2e;
-    reinterpret_cast<float4*>(sBias)[e] = v;
-  }
   if (cta < p.B_) issue(cta, 0);
   int it = 0;
   for (int win = cta; win < p.B_; win += p.per_head, ++it) {
@@ -141,52 +135,63 @@ __global__ void __launch_bounds__(NP * 2, 1) attn_mma_fwd_kernel(AttnMmaParams p
     const uint8_t* sV = sQ + 2 * kTile;
     uint32_t aq[2][4];
     load_a_frags(aq, sQ, i0, lane);
-    float s[NT][4];
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
-#pragma unroll
-    for (int nt2 = 0; nt2 < NK; ++nt2) mma_nk(s[2 * nt2], s[2 * nt2 + 1], aq, sK, nt2, lane);
-    // logits in the log2 domain: scale * s + bias (+ mask); rows r0 = i0 + g and r1 = r0 + 8, columns 8 nt + 2 t + {0, 1}
+    // online softmax over chunks of 48 keys (FlashAttention-2): 24 logit registers at a time instead of 72, so two CTAs fit an SM
     const int r0 = i0 + g, r1 = r0 + 8;
-    const float* b0 = sBias + r0 * NP + 2 * t;
-    const float* b1 = b0 + 8 * NP;
+    const float* b0 = p.bias + ((size_t)h * NP + r0) * NP + 2 * t;
     const float* m0 = nullptr;
     if (p.mask != nullptr) {
       const int mw = win % p.nW;
       if (p.mask_nz == nullptr || p.mask_nz[mw]) m0 = p.mask + ((size_t)mw * NP + r0) * NP + 2 * t;
     }
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      float2 ba = *reinterpret_cast<const float2*>(b0 + nt * 8), bb = *reinterpret_cast<const float2*>(b1 + nt * 8);
-      if (m0 != nullptr) {
-        const float2 ma = __ldg(reinterpret_cast<const float2*>(m0 + nt * 8)), mb = __ldg(reinterpret_cast<const float2*>(m0 + 8 * NP + nt * 8));
-        ba.x = fmaf(ma.x, kL2e, ba.x); ba.y = fmaf(ma.y, kL2e, ba.y); bb.x = fmaf(mb.x, kL2e, bb.x); bb.y = fmaf(mb.y, kL2e, bb.y);
-      }
-      s[nt][0] = fmaf(s[nt][0], sc2, ba.x); s[nt][1] = fmaf(s[nt][1], sc2, ba.y);
-      s[nt][2] = fmaf(s[nt][2], sc2, bb.x); s[nt][3] = fmaf(s[nt][3], sc2, bb.y);
-      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1])); mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      s[nt][0] = ex2a(s[nt][0] - mx0); s[nt][1] = ex2a(s[nt][1] - mx0);
-      s[nt][2] = ex2a(s[nt][2] - mx1); s[nt][3] = ex2a(s[nt][3] - mx1);
-      sum0 += s[nt][0] + s[nt][1]; sum1 += s[nt][2] + s[nt][3];
-    }
-    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    float mx0 = -INFINITY, mx1 = -INFINITY, sum0 = 0.f, sum1 = 0.f;
     float o[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
 #pragma unroll
-    for (int kj = 0; kj < NK; ++kj) {
-      uint32_t a[4] = {pack_bf16(s[2 * kj][0], s[2 * kj][1]), pack_bf16(s[2 * kj][2], s[2 * kj][3]),
-                       pack_bf16(s[2 * kj + 1][0], s[2 * kj + 1][1]), pack_bf16(s[2 * kj + 1][2], s[2 * kj + 1][3])};
-      mma_kn(o, a, sV, kj, lane);
+    for (int c = 0; c < NT / CHF; ++c) {
+      float s[CHF][4];
+#pragma unroll
+      for (int k = 0; k < CHF; ++k) { s[k][0] = s[k][1] = s[k][2] = s[k][3] = 0.f; }
+#pragma unroll
+      for (int k2 = 0; k2 < CHF / 2; ++k2) mma_nk(s[2 * k2], s[2 * k2 + 1], aq, sK, c * (CHF / 2) + k2, lane);
+      // logits in the log2 domain: scale * s + bias (+ mask); rows r0 and r1 = r0 + 8, columns 8 nt + 2 t + {0, 1}
+      float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < CHF; ++k) {
+        const int nt = c * CHF + k;
+        float2 ba = __ldg(reinterpret_cast<const float2*>(b0 + nt * 8)), bb = __ldg(reinterpret_cast<const float2*>(b0 + 8 * NP + nt * 8));
+        if (m0 != nullptr) {
+          const float2 ma = __ldg(reinterpret_cast<const float2*>(m0 + nt * 8)), mb = __ldg(reinterpret_cast<const float2*>(m0 + 8 * NP + nt * 8));
+          ba.x += ma.x; ba.y += ma.y; bb.x += mb.x; bb.y += mb.y;
+        }
+        s[k][0] = fmaf(s[k][0], sc2, ba.x * kL2e); s[k][1] = fmaf(s[k][1], sc2, ba.y * kL2e);
+        s[k][2] = fmaf(s[k][2], sc2, bb.x * kL2e); s[k][3] = fmaf(s[k][3], sc2, bb.y * kL2e);
+        cm0 = fmaxf(cm0, fmaxf(s[k][0], s[k][1])); cm1 = fmaxf(cm1, fmaxf(s[k][2], s[k][3]));
+      }
+      cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1)); cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+      cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1)); cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+      const float n0 = fmaxf(mx0, cm0), n1 = fmaxf(mx1, cm1);
+      const float f0 = ex2a(mx0 - n0), f1 = ex2a(mx1 - n1);          // rescale of what has been accumulated so far (0 on the first chunk)
+      mx0 = n0; mx1 = n1;
+      float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < CHF; ++k) {
+        s[k][0] = ex2a(s[k][0] - n0); s[k][1] = ex2a(s[k][1] - n0);
+        s[k][2] = ex2a(s[k][2] - n1); s[k][3] = ex2a(s[k][3] - n1);
+        ps0 += s[k][0] + s[k][1]; ps1 += s[k][2] + s[k][3];
+      }
+      sum0 = fmaf(sum0, f0, ps0); sum1 = fmaf(sum1, f1, ps1);           // per-thread partial sums; the quad adds up after the loop
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) { o[nt][0] *= f0; o[nt][1] *= f0; o[nt][2] *= f1; o[nt][3] *= f1; }
+#pragma unroll
+      for (int k2 = 0; k2 < CHF / 2; ++k2) {
+        uint32_t a[4] = {pack_bf16(s[2 * k2][0], s[2 * k2][1]), pack_bf16(s[2 * k2][2], s[2 * k2][3]),
+                         pack_bf16(s[2 * k2 + 1][0], s[2 * k2 + 1][1]), pack_bf16(s[2 * k2 + 1][2], s[2 * k2 + 1][3])};
+        mma_kn(o, a, sV, c * (CHF / 2) + k2, lane);
+      }
     }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
     if (t == 0) {
       float* l = p.lse + ((size_t)win * p.nH + h) * NP;
       l[r0] = (mx0 + log2f(sum0)) * 0.6931471805599453f;
@@ -368,11 +373,11 @@ int attn_mma_supported(int ws) { return ws == 12; }
 
 int attn_mma_fwd(const swin_attn_args* a, cudaStream_t st) {
   AttnMmaParams p;
-  int rc = mma_common(a, &p, false, 2);
+  int rc = mma_common(a, &p, false, 2);      // two CTAs per SM
   if (rc) return rc;
   if (p.B_ == 0) return 0;
   constexpr int NP = 144;
-  const size_t smem = 2 * 3 * NP * kPitch + (size_t)NP * NP * 4;
+  const size_t smem = 2 * 3 * NP * kPitch;
   rc = ensure_dyn_smem((const void*)attn_mma_fwd_kernel<NP>, (int)smem);
   if (rc) return rc;
   attn_mma_fwd_kernel<NP><<<p.nH * p.per_head, NP * 2, smem, st>>>(p);
