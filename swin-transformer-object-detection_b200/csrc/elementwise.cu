@@ -651,6 +651,95 @@ static int ln_geom(const swin_ln_args* a, bool bwd, LnGeom* out) {
 }
 
 // lanes per row: the smallest of 8/16/32 that keeps <= 4 float4 per lane (else 32 with more per lane)
+
+// LayerNorm backward for WIDE merged rows (PatchMerging, mode 2, 4C = 768 .. 2048): the whole 256-thread block owns one row at a
+// time (thread = one or two float4 columns), so the per-thread state is a handful of registers instead of the 250+ (with
+// spills) the lane-group kernel needs at 12-16 float4 per lane -- that one launch ran at 0.6-2.1 TB/s.  Row statistics go
+// through a block reduction; dgamma / dbeta partials stay in registers (a thread keeps its columns) until the end.
+template <typename YT>
+__global__ void __launch_bounds__(256) ln_bwd_block_kernel(const YT* __restrict__ dy, const float* __restrict__ x,
+                                                           const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, const float* __restrict__ dres,
+                                                           float* __restrict__ dx, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, LnGeom lg) {
+  __shared__ float sred2[2][8];
+  constexpr int KV = 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int vps = lg.C >> 2;
+  const int vrow = vps * lg.nseg;
+  const float inv_n = 1.0f / (float)(vrow * 4);
+  float4 ag[KV], ab[KV], gm[KV];
+#pragma unroll
+  for (int k = 0; k < KV; ++k) {
+    ag[k] = make_float4(0.f, 0.f, 0.f, 0.f); ab[k] = ag[k];
+    const int v = tid + 256 * k;
+    gm[k] = v < vrow ? __ldg(reinterpret_cast<const float4*>(gamma) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float* rsrc = dres != nullptr ? dres : x;
+  const float rflag = dres != nullptr ? 1.0f : 0.0f;
+  for (int row = blockIdx.x; row < lg.rows; row += gridDim.x) {
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[KV], gd[KV], rr[KV];
+    long long idx[KV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < KV; ++k) {
+      const int v = tid + 256 * k;
+      const bool on = v < vrow;
+      idx[k] = -1;
+      xh[k] = gd[k] = rr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (on) {
+        const int q = fdiv(v, lg.dvps), off = v - q * vps;
+        const int srow = lg.mode == 2 ? merge_src(lg, row, q) : row;
+        const float4 d = Vec4IO<YT>::cvt(Vec4IO<YT>::ldraw(dy, (long long)row * vrow + v));
+        if (srow >= 0) {
+          idx[k] = (long long)srow * vps + (lg.mode == 2 ? off : v);
+          const float4 xv = Vec4IO<float>::ld(x, idx[k]);
+          const float4 r4 = Vec4IO<float>::ld(rsrc, idx[k]);
+          rr[k] = make_float4(r4.x * rflag, r4.y * rflag, r4.z * rflag, r4.w * rflag);
+          xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        } else {
+          xh[k] = make_float4(-mu * rs, -mu * rs, -mu * rs, -mu * rs);          // zero-padded segment of the merged row: xhat = (0 - mu) * rs
+        }
+        gd[k] = make_float4(d.x * gm[k].x, d.y * gm[k].y, d.z * gm[k].z, d.w * gm[k].w);
+        s1 += gd[k].x + gd[k].y + gd[k].z + gd[k].w;
+        s2 += gd[k].x * xh[k].x + gd[k].y * xh[k].y + gd[k].z * xh[k].z + gd[k].w * xh[k].w;
+        ag[k].x += d.x * xh[k].x; ag[k].y += d.y * xh[k].y; ag[k].z += d.z * xh[k].z; ag[k].w += d.w * xh[k].w;
+        ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
+      }
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) { sred2[0][warp] = s1; sred2[1][warp] = s2; }
+    __syncthreads();
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { m1 += sred2[0][w]; m2 += sred2[1][w]; }
+    m1 *= inv_n; m2 *= inv_n;
+    __syncthreads();                                   // sred2 is rewritten by the next row
+#pragma unroll
+    for (int k = 0; k < KV; ++k) {
+      if (idx[k] >= 0) {
+        float4 o;
+        o.x = rs * (gd[k].x - m1 - xh[k].x * m2) + rr[k].x;
+        o.y = rs * (gd[k].y - m1 - xh[k].y * m2) + rr[k].y;
+        o.z = rs * (gd[k].z - m1 - xh[k].z * m2) + rr[k].z;
+        o.w = rs * (gd[k].w - m1 - xh[k].w * m2) + rr[k].w;
+        Vec4IO<float>::st(dx, idx[k], o);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KV; ++k) {
+    const int v = tid + 256 * k;
+    if (v < vrow) {
+      atomicAdd(dgamma + v * 4 + 0, ag[k].x); atomicAdd(dgamma + v * 4 + 1, ag[k].y);
+      atomicAdd(dgamma + v * 4 + 2, ag[k].z); atomicAdd(dgamma + v * 4 + 3, ag[k].w);
+      atomicAdd(dbeta + v * 4 + 0, ab[k].x); atomicAdd(dbeta + v * 4 + 1, ab[k].y);
+      atomicAdd(dbeta + v * 4 + 2, ab[k].z); atomicAdd(dbeta + v * 4 + 3, ab[k].w);
+    }
+  }
+}
+
 static void ln_shape(int vrow, int* G, int* vpl) {
   int g = 8;
   while (g < 32 && vrow > g * 4) g *= 2;
@@ -693,6 +782,12 @@ static int ln_bwd_dispatch(const swin_ln_args* a, const LnGeom& lg, cudaStream_t
   int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
   if (grid < 1) grid = 1;
   size_t smem = (size_t)2 * vrow * 4 * sizeof(float);
+  if (lg.mode == 2 && vrow >= 256 && vrow <= 512 && a->dy2 == nullptr) {      // wide PatchMerging rows: one block per row
+    const int gridb = lg.rows < 3 * kNumSMs ? lg.rows : 3 * kNumSMs;
+    ln_bwd_block_kernel<YT><<<gridb, 256, 0, st>>>((const YT*)a->dy, a->x, a->gamma, a->mean, a->rstd, a->dres, a->dx, a->dgamma, a->dbeta, lg);
+    SWIN_LAUNCH_CHECK();
+    return 0;
+  }
   static const bool use_pf = getenv("SWIN_LN_BWD_NO_PREFETCH") == nullptr;
 #define LN_BWD_PF_CASE(V, GG)                                                                                      \
   if (use_pf && G == GG && vpl <= V) {                                                                             \
