@@ -792,14 +792,14 @@ static int ln_bwd_dispatch(const swin_ln_args* a, const LnGeom& lg, cudaStream_t
 #define LN_BWD_PF_CASE(V, GG)                                                                                      \
   if (use_pf && G == GG && vpl <= V) {                                                                             \
     const size_t smem_pf = ((smem + 15) & ~(size_t)15) + (size_t)8 * 2 * LnBwdStage<V, YT>::kBytes;                \
-    { const int ar = ensure_dyn_smem((const void*)ln_bwd_pf_kernel<V, GG, YT>, 160 * 1024); if (ar) return ar; }      \
+    { const int ar = ensure_dyn_smem((const void*)ln_bwd_pf_kernel<V, GG, YT>, 210 * 1024); if (ar) return ar; }      \
     ln_bwd_pf_kernel<V, GG, YT><<<grid, 256, smem_pf, st>>>((const YT*)a->dy, a->x, a->gamma, a->mean, a->rstd, a->dres, \
                                                            a->dx, a->dgamma, a->dbeta, lg);                        \
     SWIN_LAUNCH_CHECK();                                                                                           \
     return 0;                                                                                                      \
   }
   LN_BWD_PF_CASE(3, 8) LN_BWD_PF_CASE(4, 8) LN_BWD_PF_CASE(3, 16) LN_BWD_PF_CASE(4, 16) LN_BWD_PF_CASE(3, 32) LN_BWD_PF_CASE(4, 32)
-  LN_BWD_PF_CASE(6, 32)          // 768-wide rows (stage-3 LayerNorms, the stage-1 PatchMerging): 123 KB of staging, one block per SM either way
+  LN_BWD_PF_CASE(6, 32) LN_BWD_PF_CASE(8, 32)   // 768- / 1024-wide rows (stage-3 LayerNorms): 123-197 KB of staging, one block per SM either way
 #undef LN_BWD_PF_CASE
 #define LN_BWD_CASE(V, GG)                                                                                         \
   if (G == GG && vpl <= V) {                                                                                       \
