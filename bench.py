@@ -117,6 +117,15 @@ class KernelTimer:
         sel = [r for r in self.recs if r[0].startswith(prefix)]
         return len(sel), sum(r[3].elapsed_time(r[4]) for r in sel), sum(r[1] for r in sel), sum(r[2] for r in sel)
 
+    def own_roofline(self, prefix, peak_tflops, peak_gbs):
+        """(sum over launches of max(flops/peak, bytes/peak) in ms, measured ms) for the kinds starting with ``prefix``: each
+        launch is held against the bound that applies to IT (the K = 96 GEMMs of stage 0 are HBM kernels, the stage-2 ones
+        tensor kernels), which one class-wide TFLOP/s figure cannot express."""
+        torch.cuda.synchronize()
+        sel = [r for r in self.recs if r[0].startswith(prefix)]
+        roof = sum(max(r[1] / (peak_tflops * 1e12), r[2] / (peak_gbs * 1e9)) for r in sel) * 1e3
+        return roof, sum(r[3].elapsed_time(r[4]) for r in sel)
+
     def table(self, steps, peak_tflops, peak_gbs):
         """Per kernel kind: launches/step, ms/step, roofline ms/step = max(flops/peak, bytes/peak), achieved rates."""
         torch.cuda.synchronize()
@@ -530,6 +539,10 @@ def main():
                 "launches_per_step": n_launch // max(K, 1), "ms_per_step_in_kernel": gemm_ms / max(K, 1),
                 "whole_step_frac_of_tensor_roofline": (GFLOP_PER_IMG * 1e9 * B / (ms_step / 1e3)) / (peak * 1e12),
                 "attention": attn}
+    # every launch against its own bound (max of the tensor time and the HBM time of its algorithmic flops / bytes)
+    for key, pref in (("own_roofline_frac", "gemm_tc"), ("own_roofline_frac_all_kernels", "")):
+        r_ms, t_ms = timer.own_roofline(pref, peak, hbm_peak)
+        roofline[key] = (r_ms / t_ms) if t_ms > 0 else None
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

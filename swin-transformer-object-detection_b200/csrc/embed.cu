@@ -129,16 +129,21 @@ __global__ void __launch_bounds__(256) ln_nchw_fwd_kernel(const float* __restric
     for (int c = warp; c < C; c += 8) out[((long long)b * C + c) * L + t] = tile[c * 33 + lane];
 }
 
-template <int VPL, int G>
+template <int VPL, int G, int TOK, bool SX>
 __global__ void __launch_bounds__(256, (VPL <= 3 ? 3 : (VPL <= 6 ? 2 : 1))) ln_nchw_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x,
                                                           const float* __restrict__ gamma, const float* __restrict__ mean,
                                                           const float* __restrict__ rstd, float* __restrict__ dx,
                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int L, int C,
                                                           int tiles_per_block, int nbuf) {
-  // dout arrives channel-major (NCHW): a [C][32-token] tile is transposed through smem.  With nbuf == 2 the NEXT tile's
-  // dout AND x rows are fetched with cp.async while the current one is processed.
-  extern __shared__ __align__(16) float tile_all[];        // nbuf x ([C][33] dout tile + [32][C] x rows) + [2][C] partials
-  const size_t buf_floats = (size_t)C * 33 + (nbuf == 2 ? (size_t)kTokTile * C + 2 * kTokTile : 0) + 4;      // +4 keeps the x rows 16-byte aligned
+  constexpr int tok = TOK;
+  constexpr bool stage_x = SX;
+  // dout arrives channel-major (NCHW): a [C][tok-token] tile (tok = 32, or 16 for wide rows) is transposed through smem.
+  // With two buffers the NEXT tile's dout (and, with stage_x, its x rows and statistics) is fetched with cp.async while the
+  // current one is processed.  Without stage_x the rows of x are read straight from global memory (float4 per lane, all
+  // VPL loads of a token issued together).
+  extern __shared__ __align__(16) float tile_all[];        // nbuf x ([C][tok+1] dout tile (+ [tok][C] x rows + 2 x tok stats)) + [2][C] partials
+  constexpr int pitch = tok + 1;
+  const size_t buf_floats = (size_t)C * pitch + (stage_x ? (size_t)tok * C + 2 * tok : 0) + 4;      // +4 keeps the x rows 16-byte aligned
   float* sred = tile_all + (size_t)nbuf * buf_floats;
   constexpr int R = 32 / G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G, gi = lane / G;
@@ -149,77 +154,81 @@ __global__ void __launch_bounds__(256, (VPL <= 3 ? 3 : (VPL <= 6 ? 2 : 1))) ln_n
   float4 ag[VPL], ab[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) { ag[k] = make_float4(0.f, 0.f, 0.f, 0.f); ab[k] = ag[k]; }
-  const size_t xoff = ((size_t)C * 33 + 3) & ~(size_t)3;
+  const size_t xoff = ((size_t)C * pitch + 3) & ~(size_t)3;
+  constexpr int cper = 32 / tok;
+  const int tl = lane & (tok - 1), cl = lane / tok;      // a warp covers cper channels x tok tokens per load
   auto fetch_tile = [&](int tb, int buf) {
-    const int t0 = (blockIdx.x * tiles_per_block + tb) * kTokTile;
+    const int t0 = (blockIdx.x * tiles_per_block + tb) * tok;
     if (tb >= tiles_per_block || t0 >= L) return;
     float* base = tile_all + (size_t)buf * buf_floats;
-    if (nbuf == 2) {
-      const int t = t0 + lane;
+    {
+      const int t = t0 + tl;
       const uint32_t nbytes = t < L ? 4u : 0u;           // src-size 0: zero fill
       const float* src = dout + (long long)b * C * L + (t < L ? t : 0);
-      for (int c = warp; c < C; c += 8)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(base + c * 33 + lane)),
+      for (int c = warp * cper + cl; c < C; c += 8 * cper)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(base + c * pitch + tl)),
                      "l"(src + (long long)c * L), "r"(nbytes) : "memory");
-    } else {                                             // wide rows: single buffer, plain loads (no room for a second tile)
-      const int t = t0 + lane;
-      for (int c = warp; c < C; c += 8) base[c * 33 + lane] = (t < L) ? __ldg(dout + ((long long)b * C + c) * L + t) : 0.f;
     }
-    if (nbuf == 2) {
-      // x rows of the tile: 32 tokens x C floats, contiguous in global memory (token-major)
-      const int nvec = kTokTile * vrow;
-      const int live = min(kTokTile, L - t0) * vrow;       // vectors of real tokens (the tile's rows are contiguous)
+    if (stage_x) {
+      // x rows of the tile: tok tokens x C floats, contiguous in global memory (token-major)
+      const int nvec = tok * vrow;
+      const int live = min(tok, L - t0) * vrow;            // vectors of real tokens (the tile's rows are contiguous)
       const long long row0 = (long long)b * L + t0;
       for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
         const uint32_t nbytes = v < live ? 16u : 0u;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(base + xoff + (size_t)v * 4)),
                      "l"(reinterpret_cast<const float4*>(x + row0 * C) + (v < live ? v : 0)), "r"(nbytes) : "memory");
       }
-      // per-token statistics of the tile (mean | rstd), 2 x 32 floats after the x rows
-      if (threadIdx.x < 2 * kTokTile) {
-        const int tt = threadIdx.x & (kTokTile - 1);
-        const float* sp = (threadIdx.x < kTokTile ? mean : rstd) + row0 + (t0 + tt < L ? tt : 0);
+      // per-token statistics of the tile (mean | rstd), 2 x tok floats after the x rows
+      if ((int)threadIdx.x < 2 * tok) {
+        const int tt = threadIdx.x & (tok - 1);
+        const float* sp = ((int)threadIdx.x < tok ? mean : rstd) + row0 + (t0 + tt < L ? tt : 0);
         const uint32_t nb = t0 + tt < L ? 4u : 0u;
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(base + xoff + (size_t)nvec * 4 + threadIdx.x)),
                      "l"(sp), "r"(nb) : "memory");
       }
     }
   };
-  if (nbuf == 2) fetch_tile(0, 0);
+  fetch_tile(0, 0);
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int tb = 0; tb < tiles_per_block; ++tb) {
-    const int t0 = (blockIdx.x * tiles_per_block + tb) * kTokTile;
+    const int t0 = (blockIdx.x * tiles_per_block + tb) * tok;
     if (t0 >= L) break;
     if (nbuf == 2) {
       fetch_tile(tb + 1, (tb + 1) & 1);
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
-      fetch_tile(tb, 0);
-      asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     const float* tile = tile_all + (size_t)(nbuf == 2 ? (tb & 1) : 0) * buf_floats;
     const float4* xs = reinterpret_cast<const float4*>(tile + xoff);
 #pragma unroll 1
-    for (int tt = warp * R + gi; tt < kTokTile; tt += 8 * R) {
+    for (int tt = warp * R + gi; tt < tok; tt += 8 * R) {
       const int t = t0 + tt;
       const bool act = t < L;
       const long long rowi = (long long)b * L + (act ? t : 0);
-      const float* stat = tile + xoff + (size_t)kTokTile * vrow * 4;
-      const float mu = nbuf == 2 ? stat[tt] : mean[rowi], rs = nbuf == 2 ? stat[kTokTile + tt] : rstd[rowi];
-      const float4* xrow = nbuf == 2 ? xs + (size_t)tt * vrow : reinterpret_cast<const float4*>(x + rowi * C);
+      const float* stat = tile + xoff + (size_t)tok * vrow * 4;
+      const float mu = stage_x ? stat[tt] : __ldg(mean + rowi), rs = stage_x ? stat[tok + tt] : __ldg(rstd + rowi);
+      const float4* xrow = stage_x ? xs + (size_t)tt * vrow : reinterpret_cast<const float4*>(x + rowi * C);
       float4 xh[VPL], gd[VPL];
+      if (!stage_x) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {           // the token's x vectors: every load in flight before the first use
+          const int v = gl + G * k;
+          xh[k] = (act && v < vrow) ? __ldg(xrow + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
         const int v = gl + G * k;
+        const float4 xv = stage_x ? ((act && v < vrow) ? xrow[v] : make_float4(0.f, 0.f, 0.f, 0.f)) : xh[k];
         xh[k] = make_float4(0.f, 0.f, 0.f, 0.f); gd[k] = xh[k];
         if (act && v < vrow) {
           const int c = 4 * v;
-          const float4 d = make_float4(tile[(c + 0) * 33 + tt], tile[(c + 1) * 33 + tt], tile[(c + 2) * 33 + tt], tile[(c + 3) * 33 + tt]);
-          const float4 xv = nbuf == 2 ? xrow[v] : __ldg(xrow + v);
+          const float4 d = make_float4(tile[(c + 0) * pitch + tt], tile[(c + 1) * pitch + tt], tile[(c + 2) * pitch + tt], tile[(c + 3) * pitch + tt]);
           const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + v);
           xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
           gd[k] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
@@ -239,6 +248,10 @@ __global__ void __launch_bounds__(256, (VPL <= 3 ? 3 : (VPL <= 6 ? 2 : 1))) ln_n
       }
     }
     __syncthreads();                          // every warp is done with this tile before its buffer is refilled
+    if (nbuf == 1) {                          // single buffer (one or two tiles per block, overlap comes from the co-resident blocks)
+      fetch_tile(tb + 1, 0);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
@@ -315,8 +328,7 @@ extern "C" int swin_ln_nchw_fwd(const float* x, const float* gamma, const float*
   dim3 grid(ceil_div(L, kTokTile), B);
 #define NCHW_FWD(V, GG)                                                                                                   \
   if (G == GG && vpl <= V) {                                                                                              \
-    static bool attr = false;                                                                                             \
-    if (!attr) { cudaFuncSetAttribute(ln_nchw_fwd_kernel<V, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; } \
+    { const int ar = ensure_dyn_smem((const void*)ln_nchw_fwd_kernel<V, GG>, 160 * 1024); if (ar) return ar; }            \
     ln_nchw_fwd_kernel<V, GG><<<grid, 256, smem, (cudaStream_t)stream>>>(x, gamma, beta, out, mean, rstd, L, C, eps);      \
     SWIN_LAUNCH_CHECK();                                                                                                  \
     return 0;                                                                                                             \
@@ -331,9 +343,17 @@ extern "C" int swin_ln_nchw_bwd(const float* dout, const float* x, const float* 
   SWIN_REQUIRE(B > 0 && L > 0 && C > 0 && C % 4 == 0 && C <= 1024, "ln_nchw: bad shape (C %% 4 == 0, C <= 1024)");
   SWIN_REQUIRE(dout && x && gamma && mean && rstd && dx && dgamma && dbeta, "ln_nchw_bwd: null pointer");
   SWIN_REQUIRE(aligned16(x) && aligned16(dx) && aligned16(gamma), "ln_nchw_bwd: alignment");
-  const int nbuf = C <= 192 ? 2 : 1;
-  size_t smem = ((size_t)nbuf * ((size_t)C * 33 + (nbuf == 2 ? (size_t)kTokTile * C + 2 * kTokTile : 0) + 4) + 2 * C) * sizeof(float);
-  int tiles = ceil_div(L, kTokTile);
+  // Measured on the Swin-T / Swin-B stage shapes (profiles/r02/ln_nchw_bwd_sweep.txt): C <= 128 (long token axis) runs best with 32-token
+  // tiles, two buffers and the next tile's dout + x rows + statistics in flight while this one is processed.  Wider rows come
+  // with few tokens per image; there shared memory is better spent on residency than on staging x: 16-token dout tiles (64-byte
+  // row segments), x read from global memory, two buffers -- except the 768-wide rows (128 registers, two blocks per SM),
+  // where one buffer per block measured faster (2.26 vs 1.91 TB/s).
+  const int stage_x = C <= 128 ? 1 : 0;
+  const int tok = C <= 128 ? kTokTile : kTokTile / 2;
+  const int nbuf = (C > 512 && C <= 768) ? 1 : 2;
+  size_t smem = ((size_t)nbuf * ((size_t)C * (tok + 1) + (stage_x ? (size_t)tok * C + 2 * tok : 0) + 4) + 2 * C) * sizeof(float);
+  SWIN_REQUIRE(smem <= 212 * 1024, "ln_nchw_bwd: tile does not fit shared memory");
+  int tiles = ceil_div(L, tok);
   // tiles per block: ~8-24 so the dgamma/dbeta atomics amortise, chosen so that the grid fills the resident-block capacity
   // (<= 3 blocks per SM by registers, fewer when the tile buffers are large) in whole waves — 5.05 waves ran as 6
   int bps = (int)((227 * 1024) / (smem + 1024));
@@ -352,16 +372,22 @@ extern "C" int swin_ln_nchw_bwd(const float* dout, const float* x, const float* 
   dim3 grid(ceil_div(tiles, tpb), B);
   int G, vpl;
   nchw_shape(C / 4, &G, &vpl);
+#define NCHW_BWD_LAUNCH(V, GG, TK, SXV, cond)                                                                             \
+  if (cond) {                                                                                                             \
+    const int ar = ensure_dyn_smem((const void*)ln_nchw_bwd_kernel<V, GG, TK, SXV>, 212 * 1024);                          \
+    if (ar) return ar;                                                                                                    \
+    ln_nchw_bwd_kernel<V, GG, TK, SXV><<<grid, 256, smem, (cudaStream_t)stream>>>(dout, x, gamma, mean, rstd, dx, dgamma, dbeta, L, C, tpb, nbuf); \
+  }
 #define NCHW_BWD(V, GG)                                                                                                   \
   if (G == GG && vpl <= V) {                                                                                              \
-    static bool attr = false;                                                                                             \
-    if (!attr) { cudaFuncSetAttribute(ln_nchw_bwd_kernel<V, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024); attr = true; } \
-    ln_nchw_bwd_kernel<V, GG><<<grid, 256, smem, (cudaStream_t)stream>>>(dout, x, gamma, mean, rstd, dx, dgamma, dbeta, L, C, tpb, nbuf); \
+    NCHW_BWD_LAUNCH(V, GG, kTokTile, true, stage_x)                                                                       \
+    NCHW_BWD_LAUNCH(V, GG, kTokTile / 2, false, !stage_x)                                                                 \
     SWIN_LAUNCH_CHECK();                                                                                                  \
     return 0;                                                                                                             \
   }
   NCHW_CASES(NCHW_BWD)
 #undef NCHW_BWD
+#undef NCHW_BWD_LAUNCH
   set_error("ln_nchw: unsupported C %d", C);
   return -EINVAL;
 }

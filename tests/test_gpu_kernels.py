@@ -181,7 +181,9 @@ def test_scale_cast_grad_gather():
     assert torch.equal(bucket, want)
 
 
-@pytest.mark.parametrize("C,H,W", [(96, 9, 13), (768, 5, 7), (32, 40, 33)])
+# C <= 192: 32-token tiles with staged x rows; 192 < C <= 384: 32-token tiles, x from global memory; wider: 16-token tiles
+@pytest.mark.parametrize("C,H,W", [(96, 9, 13), (768, 5, 7), (32, 40, 33), (192, 11, 9), (256, 6, 11), (384, 9, 13), (512, 7, 9),
+                                   (1024, 5, 7), (384, 50, 84)])
 def test_ln_nchw_fwd_bwd(C, H, W):
     ops, _ = _ops()
     B = 2
