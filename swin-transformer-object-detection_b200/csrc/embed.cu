@@ -77,18 +77,19 @@ __device__ __forceinline__ float group_sum_e(float v) {
   return v;
 }
 
-template <int VPL, int G>
+template <int VPL, int G, int TOK>
 __global__ void __launch_bounds__(256) ln_nchw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float* __restrict__ out,
                                                           float* __restrict__ mean, float* __restrict__ rstd, int L, int C, float eps) {
-  extern __shared__ float tile[];            // [C][33]
+  extern __shared__ float tile[];            // [C][TOK + 1]
+  constexpr int pitch = TOK + 1;
   constexpr int R = 32 / G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G, gi = lane / G;
-  const int b = blockIdx.y, t0 = blockIdx.x * kTokTile;
+  const int b = blockIdx.y, t0 = blockIdx.x * TOK;
   const int vrow = C >> 2;
   const float inv_n = 1.0f / (float)C;
 #pragma unroll 1
-  for (int tt = warp * R + gi; tt < kTokTile; tt += 8 * R) {
+  for (int tt = warp * R + gi; tt < TOK; tt += 8 * R) {
     const int t = t0 + tt;
     const bool act = t < L;
     const float4* row = reinterpret_cast<const float4*>(x + ((long long)b * L + (act ? t : 0)) * C);
@@ -116,17 +117,18 @@ __global__ void __launch_bounds__(256) ln_nchw_fwd_kernel(const float* __restric
       if (act && v < vrow) {
         const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + v), bt = __ldg(reinterpret_cast<const float4*>(beta) + v);
         const int c = 4 * v;
-        tile[(c + 0) * 33 + tt] = (r[k].x - mu) * rs * gm.x + bt.x;
-        tile[(c + 1) * 33 + tt] = (r[k].y - mu) * rs * gm.y + bt.y;
-        tile[(c + 2) * 33 + tt] = (r[k].z - mu) * rs * gm.z + bt.z;
-        tile[(c + 3) * 33 + tt] = (r[k].w - mu) * rs * gm.w + bt.w;
+        tile[(c + 0) * pitch + tt] = (r[k].x - mu) * rs * gm.x + bt.x;
+        tile[(c + 1) * pitch + tt] = (r[k].y - mu) * rs * gm.y + bt.y;
+        tile[(c + 2) * pitch + tt] = (r[k].z - mu) * rs * gm.z + bt.z;
+        tile[(c + 3) * pitch + tt] = (r[k].w - mu) * rs * gm.w + bt.w;
       }
     }
   }
   __syncthreads();
-  const int t = t0 + lane;
+  constexpr int cper = 32 / TOK;             // a warp stores cper channels x TOK tokens per instruction
+  const int t = t0 + (lane & (TOK - 1)), cl = lane / TOK;
   if (t < L)
-    for (int c = warp; c < C; c += 8) out[((long long)b * C + c) * L + t] = tile[c * 33 + lane];
+    for (int c = warp * cper + cl; c < C; c += 8 * cper) out[((long long)b * C + c) * L + t] = tile[c * pitch + (lane & (TOK - 1))];
 }
 
 template <int VPL, int G, int TOK, bool SX>
@@ -322,19 +324,28 @@ extern "C" int swin_ln_nchw_fwd(const float* x, const float* gamma, const float*
   SWIN_REQUIRE(B > 0 && L > 0 && C > 0 && C % 4 == 0 && C <= 1024, "ln_nchw: bad shape (C %% 4 == 0, C <= 1024)");
   SWIN_REQUIRE(x && gamma && beta && out && mean && rstd, "ln_nchw: null pointer");
   SWIN_REQUIRE(aligned16(x) && aligned16(gamma) && aligned16(beta), "ln_nchw: alignment");
-  size_t smem = (size_t)C * 33 * sizeof(float);
+  // 32-token tiles (128-byte NCHW row segments) up to C = 256; wider rows come with short token axes, where 8-token tiles
+  // (one 32-byte sector per channel row, a quarter of the shared memory, more blocks per SM) measured 8-35 % faster
+  const int tok = C <= 256 ? kTokTile : kTokTile / 4;
+  size_t smem = (size_t)C * (tok + 1) * sizeof(float);
   int G, vpl;
   nchw_shape(C / 4, &G, &vpl);
-  dim3 grid(ceil_div(L, kTokTile), B);
+  dim3 grid(ceil_div(L, tok), B);
+#define NCHW_FWD_LAUNCH(V, GG, TK)                                                                                        \
+  if (tok == TK) {                                                                                                        \
+    const int ar = ensure_dyn_smem((const void*)ln_nchw_fwd_kernel<V, GG, TK>, 160 * 1024);                               \
+    if (ar) return ar;                                                                                                    \
+    ln_nchw_fwd_kernel<V, GG, TK><<<grid, 256, smem, (cudaStream_t)stream>>>(x, gamma, beta, out, mean, rstd, L, C, eps); \
+  }
 #define NCHW_FWD(V, GG)                                                                                                   \
   if (G == GG && vpl <= V) {                                                                                              \
-    { const int ar = ensure_dyn_smem((const void*)ln_nchw_fwd_kernel<V, GG>, 160 * 1024); if (ar) return ar; }            \
-    ln_nchw_fwd_kernel<V, GG><<<grid, 256, smem, (cudaStream_t)stream>>>(x, gamma, beta, out, mean, rstd, L, C, eps);      \
+    NCHW_FWD_LAUNCH(V, GG, kTokTile) NCHW_FWD_LAUNCH(V, GG, kTokTile / 4)                                                 \
     SWIN_LAUNCH_CHECK();                                                                                                  \
     return 0;                                                                                                             \
   }
   NCHW_CASES(NCHW_FWD)
 #undef NCHW_FWD
+#undef NCHW_FWD_LAUNCH
   set_error("ln_nchw: unsupported C %d", C);
   return -EINVAL;
 }
