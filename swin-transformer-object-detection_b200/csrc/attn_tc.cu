@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_tc_bwd_kernel(const __gri
                                                                       const __grid_constant__ CUtensorMap tmDO,
                                                                       const __grid_constant__ CUtensorMap tmDQKV, AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[4];               // load[2], s, o
+  __shared__ __align__(8) uint64_t bars[5];               // load[2], s, o, v
   __shared__ uint32_t tmem_slot;
   __shared__ float sRed[2][128];                          // partial D per column half
   uint8_t* sbase = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -385,11 +385,11 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_tc_bwd_kernel(const __gri
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, hf = warp >> 2;
   const int h = blockIdx.x % p.nH, g = blockIdx.x / p.nH;
-  const uint32_t bar_load0 = smem_u32(&bars[0]), bar_s = smem_u32(&bars[2]), bar_o = smem_u32(&bars[3]);
+  const uint32_t bar_load0 = smem_u32(&bars[0]), bar_s = smem_u32(&bars[2]), bar_o = smem_u32(&bars[3]), bar_v = smem_u32(&bars[4]);
 
   zero_smem(sT, 2 * kBwdTiles + 2 * kPBytes);
   if (tid == 0) {
-    mbar_init(bar_load0, 1); mbar_init(bar_load0 + 8, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    mbar_init(bar_load0, 1); mbar_init(bar_load0 + 8, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_v, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_tc_bwd_kernel(const __gri
   // the saved LSE of a row comes from HBM: fetched one item ahead so that its latency never sits on the item's chain
   auto load_lse = [&](int pair) -> float {
     const int win = 2 * pair + wloc;
-    return ((i < AN) && (win < p.B_)) ? p.lse[((size_t)win * p.nH + h) * AN + i] * kLog2e : 0.f;
+    return ((i < AN) && (win < p.B_)) ? p.lse[((size_t)win * p.nH + h) * AN + i] : 0.f;      // raw: see the use below
   };
   float lse_next = g < p.npairs ? load_lse(g) : 0.f;
   const f32x2 sc2p = pk2(sc2, sc2), scalep = pk2(p.scale, p.scale);
@@ -483,7 +483,9 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_tc_bwd_kernel(const __gri
     }
     const int win = 2 * pair + wloc;
     const bool valid = (i < AN) && (win < p.B_);
-    const float lse2 = lse_next;
+    // the value fetched during the PREVIOUS item is scaled only here: a multiply placed next to the load made every warp wait
+    // for the HBM round trip on the spot (13.6 % of the kernel's stall samples, profiles/r02/r02_attn_bwd_s0.hot.txt)
+    const float lse2 = lse_next * kLog2e;
     if (has_next) lse_next = load_lse(pair + stride);
     const float* mrow = nullptr;
     bool canon = false;
@@ -547,6 +549,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_tc_bwd_kernel(const __gri
 #pragma unroll
         for (uint32_t kk = 0; kk < 4; ++kk)   // dV[(w,j), (w',d)] = sum_i P_w[i][j] dO_w'[i][d]  -- runs under the dS math
           umma_bf16(tdV, umma_desc_join(kHi128, p_lo_mn + 128 * kk), umma_desc_join(kHi64, do_lo_mn + 64 * kk), idesc_tt, kk);
+        umma_commit(bar_v);                     // dV has its own barrier: it is staged while the dK / dQ MMAs are still running
         // the PREVIOUS item's dQ / dK / dV (staged over its own tiles, stores issued ~2k cycles ago) have been read out: refill
         // that buffer with the next item
         if (it >= 1 && has_next) { tma_store_wait_read<0>(); issue_loads(pair + stride, buf ^ 1); }
@@ -584,30 +587,36 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_tc_bwd_kernel(const __gri
       }
       __syncwarp();
     }
-    mbar_wait(bar_o, ph);
-    tc_fence_after();
-    TMARK(6);
     {
-      // dQ / dK / dV rows -> bf16, staged IN PLACE over this item's Q / K / V tiles (64-byte swizzle, window w at +4096): every
-      // MMA that read them has completed.  Pad rows (i >= 49) are written as zeros so the tiles stay valid operand tiles when
-      // the refill rewrites rows 0..48 only.
+      // dQ / dK / dV rows -> bf16, staged IN PLACE over this item's Q / K / V tiles (64-byte swizzle, window w at +4096) once every
+      // MMA that read the tile has completed.  Pad rows (i >= 49) are written as zeros so the tiles stay valid operand tiles when
+      // the refill rewrites rows 0..48 only.  dV goes first: its MMAs finished under the dS math and the V tile was last read by
+      // the dP MMA, so this third of the epilogue runs while the dK / dQ MMAs (which still read Q and K) are in flight.
       const uint32_t swz = (uint32_t)((r >> 1) & 3);
       uint8_t* tbase = sT + buf * kBwdTiles + r * 64;
-      uint32_t o[48];
+      auto put = [&](uint32_t* o, int part) {
+        if (i >= AN) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[e] = 0u;
+        }
+        uint8_t* trow = tbase + part * kTileBytes;
+        store_row_bf16x8(trow + (((uint32_t)(hf * 2 + 0) ^ swz) << 4), reinterpret_cast<const float*>(o));
+        store_row_bf16x8(trow + (((uint32_t)(hf * 2 + 1) ^ swz) << 4), reinterpret_cast<const float*>(o + 8));
+      };
+      uint32_t o[32];
+      mbar_wait(bar_v, ph);
+      tc_fence_after();
+      tmem_ld16(tdV + lane_off + wloc * 32 + hf * 16, o);
+      tmem_ld_wait();
+      put(o, 2);
+      mbar_wait(bar_o, ph);
+      tc_fence_after();
+      TMARK(6);
       tmem_ld16(tdQ + lane_off + wloc * 32 + hf * 16, o);
       tmem_ld16(tdK + lane_off + wloc * 32 + hf * 16, o + 16);
-      tmem_ld16(tdV + lane_off + wloc * 32 + hf * 16, o + 32);
       tmem_ld_wait();
-      if (i >= AN) {
-#pragma unroll
-        for (int e = 0; e < 48; ++e) o[e] = 0u;
-      }
-#pragma unroll
-      for (int part = 0; part < 3; ++part) {   // 0: dQ, 1: dK, 2: dV
-        uint8_t* trow = tbase + part * kTileBytes;
-        store_row_bf16x8(trow + (((uint32_t)(hf * 2 + 0) ^ swz) << 4), reinterpret_cast<const float*>(o + 16 * part));
-        store_row_bf16x8(trow + (((uint32_t)(hf * 2 + 1) ^ swz) << 4), reinterpret_cast<const float*>(o + 16 * part + 8));
-      }
+      put(o, 0);
+      put(o + 16, 1);
     }
     TMARK(7);
     fence_proxy_async_smem();

@@ -960,14 +960,34 @@ __global__ void __launch_bounds__(256) adamw_kernel(const __grid_constant__ Adam
     float* __restrict__ vv = t.v[e] + base;
     __nv_bfloat16* __restrict__ ww = t.w16[e] ? t.w16[e] + base : nullptr;
     const float decay = t.decay[e];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const float g = gg[i] * t.grad_scale;
-      float pv = pp[i] * decay;
-      float m = mm[i], v = vv[i];
+    auto update = [&](float g, float& pv, float& m, float& v) {
+      g *= t.grad_scale;
+      pv *= decay;
       m = m + (g - m) * t.omb1;                  // exp_avg.lerp_(grad, 1 - beta1)
       v = v * t.beta2 + t.omb2 * g * g;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
       const float denom = sqrtf(v) * t.inv_sqrt_bc2 + t.eps;
       pv = pv - t.step_size * (m / denom);
+    };
+    // 128-bit accesses (the chunk base is a multiple of 4 elements; torch's allocations are 512-byte aligned, so only views at
+    // odd offsets take the scalar path); four independent 16-byte loads per thread are in flight before the first use
+    const bool vec = ((reinterpret_cast<uintptr_t>(pp) | reinterpret_cast<uintptr_t>(gg) | reinterpret_cast<uintptr_t>(mm) |
+                       reinterpret_cast<uintptr_t>(vv)) & 15) == 0 && (reinterpret_cast<uintptr_t>(ww) & 7) == 0;
+    const int n4 = vec ? n >> 2 : 0;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(gg) + i);
+      float4 p4 = reinterpret_cast<float4*>(pp)[i], m4 = reinterpret_cast<float4*>(mm)[i], v4 = reinterpret_cast<float4*>(vv)[i];
+      update(g4.x, p4.x, m4.x, v4.x); update(g4.y, p4.y, m4.y, v4.y); update(g4.z, p4.z, m4.z, v4.z); update(g4.w, p4.w, m4.w, v4.w);
+      reinterpret_cast<float4*>(pp)[i] = p4; reinterpret_cast<float4*>(mm)[i] = m4; reinterpret_cast<float4*>(vv)[i] = v4;
+      if (ww) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(p4.x, p4.y), hi = __floats2bfloat162_rn(p4.z, p4.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(ww)[i] = pk;
+      }
+    }
+    for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) {
+      float pv = pp[i], m = mm[i], v = vv[i];
+      update(gg[i], pv, m, v);
       pp[i] = pv; mm[i] = m; vv[i] = v;
       if (ww) ww[i] = __float2bfloat16(pv);
     }

@@ -112,15 +112,31 @@ def main():
     for _ in range(2):
         step()
     ms = timed(step, K)
-    # the optimizer alone (same launches, outside any graph), to show its share of the step
-    ms_opt = timed(opt.step, K)
+    ms_fb = timed(graphed.replay, K)                 # forward + backward (+ all-reduce) alone, same process, same box
+    # the optimizer alone: host time to enqueue one step, and the GPU time of its launches (CUDA events around each one)
+    import time
+    from bench import KernelTimer
+    torch.cuda.synchronize()
+    h0 = time.perf_counter()
+    for _ in range(K):
+        opt.step()
+    host_opt = (time.perf_counter() - h0) * 1e3 / K
+    torch.cuda.synchronize()
+    timer = KernelTimer()
+    ops.set_kernel_timer(timer)
+    for _ in range(K):
+        opt.step()
+    ops.set_kernel_timer(None)
+    n_opt, ms_opt, _, by_opt = timer.summary("adamw_step")
     loss = float(step().item())
     assert np.isfinite(loss), "non-finite loss"
     nparam = sum(p.numel() for p in model.parameters())
     if rank == 0:
         print(json.dumps({
             "metric": f"{args.model}_backbone_fpn_laterals_adamw_train_step_images_per_sec_800x1333", "value": world * B * K / (ms / 1e3),
-            "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "adamw_ms_per_step": ms_opt / K,
+            "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "fwd_bwd_ms_per_step": ms_fb / K,
+            "adamw": {"gpu_ms_per_step": ms_opt / K, "launches_per_step": n_opt // K, "host_enqueue_ms_per_step": host_opt,
+                      "gb_per_s": by_opt / (ms_opt / 1e3) / 1e9 if ms_opt > 0 else None},
             "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic", "gpu_launches": launches_per_step * K,
             "config": {"workload": "configs[2] restricted to the rows in scope: backbone fwd+bwd + norm{i}/FPN lateral 1x1 convs (f2) + "
                                    "gradient all-reduce + fused AdamW step (f3); detector heads out of scope",
