@@ -233,10 +233,20 @@ __global__ void __launch_bounds__(NP * 2, 1) attn_mma_bwd_kernel(AttnMmaParams p
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) { db[nt][0] = db[nt][1] = db[nt][2] = db[nt][3] = 0.f; }
   if (cta < p.B_) issue(cta, 0);
+  // the saved LSE of this thread's two rows comes from HBM: fetched one item ahead (raw -- it is scaled where it is used, so no
+  // instruction waits for the load next to it)
+  const int lr0 = warp * 16 + g, lr1 = lr0 + 8;
+  float lse0_n = 0.f, lse1_n = 0.f;
+  if (cta < p.B_) { const float* l = p.lse + ((size_t)cta * p.nH + h) * NP; lse0_n = l[lr0]; lse1_n = l[lr1]; }
   int it = 0;
   for (int win = cta; win < p.B_; win += p.per_head, ++it) {
     const int st = it & 1;
     const bool more = win + p.per_head < p.B_;
+    const float lse0 = lse0_n, lse1 = lse1_n;
+    if (more) {
+      const float* l = p.lse + ((size_t)(win + p.per_head) * p.nH + h) * NP;
+      lse0_n = l[lr0]; lse1_n = l[lr1];
+    }
     if (more) { issue(win + p.per_head, st ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
     __syncthreads();
     uint8_t* sQ = sm + st * 5 * kTile;
@@ -264,8 +274,7 @@ __global__ void __launch_bounds__(NP * 2, 1) attn_mma_bwd_kernel(AttnMmaParams p
       d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
       d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
     }
-    const float* lrow = p.lse + ((size_t)win * p.nH + h) * NP;
-    const float l0 = lrow[r0] * kL2e, l1 = lrow[r1] * kL2e;
+    const float l0 = lse0 * kL2e, l1 = lse1 * kL2e;
     const float* b0 = p.bias + ((size_t)h * NP + r0) * NP + 2 * t;
     const float* m0 = nullptr;
     if (p.mask != nullptr) {
