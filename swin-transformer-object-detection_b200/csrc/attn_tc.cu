@@ -432,7 +432,11 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_tc_bwd_kernel(const __gri
       tma_load_2d(base + 3 * kTileBytes + w * 4096, &tmDO, bar, h * AHD, row0);
     }
   };
-  if (warp == 0) {
+  // Issue duties are split over two warps so that neither falls far behind the other seven between two block barriers: warp 0
+  // issues every MMA, warp kTmaWarp every TMA load and store (bulk-group waits belong to the issuing thread, so loads and
+  // stores stay together).
+  constexpr int kTmaWarp = 4;
+  if (warp == kTmaWarp) {
     if (elect_one()) {
       if (g < p.npairs) issue_loads(g, 0);
       if (g + stride < p.npairs) issue_loads(g + stride, 1);
@@ -550,10 +554,13 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_tc_bwd_kernel(const __gri
         for (uint32_t kk = 0; kk < 4; ++kk)   // dV[(w,j), (w',d)] = sum_i P_w[i][j] dO_w'[i][d]  -- runs under the dS math
           umma_bf16(tdV, umma_desc_join(kHi128, p_lo_mn + 128 * kk), umma_desc_join(kHi64, do_lo_mn + 64 * kk), idesc_tt, kk);
         umma_commit(bar_v);                     // dV has its own barrier: it is staged while the dK / dQ MMAs are still running
-        // the PREVIOUS item's dQ / dK / dV (staged over its own tiles, stores issued ~2k cycles ago) have been read out: refill
-        // that buffer with the next item
-        if (it >= 1 && has_next) { tma_store_wait_read<0>(); issue_loads(pair + stride, buf ^ 1); }
       }
+      __syncwarp();
+    }
+    if (warp == kTmaWarp && it >= 1 && has_next) {
+      // the PREVIOUS item's dQ / dK / dV (staged over its own tiles, stores issued ~2k cycles ago) have been read out: refill
+      // that buffer with the next item
+      if (elect_one()) { tma_store_wait_read<0>(); issue_loads(pair + stride, buf ^ 1); }
       __syncwarp();
     }
     delta = sRed[0][r] + sRed[1][r];
@@ -623,11 +630,14 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_tc_bwd_kernel(const __gri
     tc_fence_before();
     __syncthreads();                               // also: every warp has read dQ / dK / dV out of TMEM before the next item's S / dP MMAs
     TMARK(8);
-    if (warp == 0) {
+    if (warp == 0 && has_next) {
+      // the next item's S / dP MMAs (its tiles landed long ago; every warp has read this item's outputs out of the TMEM columns
+      // they overwrite): the MMA round trip is the longest wait of an item
+      if (elect_one()) issue_sdp(buf ^ 1, (it + 1) >> 1);
+      __syncwarp();
+    }
+    if (warp == kTmaWarp) {
       if (elect_one()) {
-        // the next item's S / dP MMAs go first (its tiles landed long ago; every warp has read this item's outputs out of the
-        // TMEM columns they overwrite), then this item's stores: the MMA round trip is the longest wait of an item
-        if (has_next) issue_sdp(buf ^ 1, (it + 1) >> 1);
         const uint32_t base = aT + buf * kBwdTiles;
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
@@ -642,7 +652,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_tc_bwd_kernel(const __gri
     }
   }
   TPRINT("attn_bwd");
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     if (elect_one()) tma_store_wait_all<0>();
     __syncwarp();
   }
