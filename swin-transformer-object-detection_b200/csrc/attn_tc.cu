@@ -208,7 +208,10 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
       umma_bf16(tS, umma_desc_join(kHi64, q_lo + 2 * k), umma_desc_join(kHi64, k_lo + 2 * k), idesc_s, k);
     umma_commit(bar_s);
   };
-  if (warp == 0) {
+  // issue duties on two warps (as in the backward kernel): warp 0 every MMA, warp kTmaWarp every TMA load / store and the
+  // bulk-group wait that belongs to the storing thread
+  constexpr int kTmaWarp = 2;
+  if (warp == kTmaWarp) {
     if (elect_one() && g < p.npairs) {
       issue_qk(g); issue_v(g);
       for (int d = 1; d <= kFwdPrefetch; ++d)
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
     const MaskPen pen = canon_mask_pen(canon, canon ? win % p.nW : 0, p.canon_nwh, p.canon_nww, i);
     mbar_wait(bar_s, ph);
     tc_fence_after();
-    if (warp == 0) {                             // the Q, K tiles are free again
+    if (warp == kTmaWarp) {                      // the Q, K tiles are free again
       if (elect_one()) {
         if (has_next) issue_qk(pair + stride);
         if (pair + (kFwdPrefetch + 1) * stride < p.npairs) prefetch_item(pair + (kFwdPrefetch + 1) * stride);
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
     sum += sum1;
     // the previous item's O tile is staged where P goes: its TMA store (issued a softmax ago) must have read it.  The wait
     // belongs to the thread that issued the store; everybody else learns through bar_free.
-    if (warp == 0) {
+    if (warp == kTmaWarp) {
       if (elect_one()) { tma_store_wait_read<0>(); mbar_arrive(bar_free); }
       __syncwarp();
     }
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
     }
     mbar_wait(bar_o, ph);
     tc_fence_after();
-    if (warp == 0) {                             // the V tile is free again
+    if (warp == kTmaWarp) {                      // the V tile is free again
       if (elect_one() && has_next) issue_v(pair + stride);
       __syncwarp();
     }
@@ -336,11 +339,14 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 0 && has_next) {
+      // the next item's S MMA (every thread has read this item's O out of the TMEM columns it overwrites): the MMA round trip
+      // is on the next item's chain
+      if (elect_one()) issue_s(ph ^ 1);
+      __syncwarp();
+    }
+    if (warp == kTmaWarp) {
       if (elect_one()) {
-        // the next item's S MMA goes first (every thread has read this item's O out of the TMEM columns it overwrites): the
-        // MMA round trip, not the store, is on the next item's chain
-        if (has_next) issue_s(ph ^ 1);
 #pragma unroll
         for (int w = 0; w < 2; ++w)
           if (2 * pair + w < p.B_) tma_store_2d(&tmOut, aP + w * 4096, h * AHD, (2 * pair + w) * AN);
@@ -349,7 +355,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) attn_tc_fwd_kernel(const __gri
       __syncwarp();
     }
   }
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     if (elect_one()) tma_store_wait_all<0>();
     __syncwarp();
   }
