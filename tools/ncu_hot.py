@@ -5,7 +5,8 @@ path = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 rows = list(csv.reader(open(path)))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[2:] if len(r) == len(hdr)]
+# a report with several kernels repeats the header row per kernel: keep the instruction rows only (first kernel's columns)
+data = [r for r in rows[2:] if len(r) == len(hdr) and r != hdr and (r[ix["# Samples"]] or "0").isdigit()]
 tot = sum(int(r[ix["# Samples"]] or 0) for r in data)
 print("total samples", tot, "instructions", len(data))
 stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
