@@ -51,6 +51,9 @@ def test_fused_adamw_matches_torch():
     g = torch.Generator().manual_seed(3)
     sizes = [1, 7, 96, 169 * 3, 4096, 4097, 288 * 96] + [int(x) for x in torch.randint(1, 3000, (70,), generator=g)]
     params = [torch.randn(n, generator=g).to(dev) for n in sizes]
+    # a view at an odd element offset: its pointers are not 16-byte aligned, so the kernel's scalar path updates it
+    sizes.append(1001)
+    params.append(torch.randn(1004, generator=g).to(dev)[1:1002])
     wds = [0.05 if i % 3 else 0.0 for i in range(len(sizes))]
     ref_params = [torch.nn.Parameter(p.clone()) for p in params]
     ref = torch.optim.AdamW([{"params": [rp], "weight_decay": wd} for rp, wd in zip(ref_params, wds)], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)

@@ -34,6 +34,10 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--model", default="swin_t", choices=sorted(MODELS))
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line (as bench.py): libraries that write to fd 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch.distributed as dist
     import swin_b200
     from swin_b200 import ops
@@ -132,6 +136,8 @@ def main():
     assert np.isfinite(loss), "non-finite loss"
     nparam = sum(p.numel() for p in model.parameters())
     if rank == 0:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps({
             "metric": f"{args.model}_backbone_fpn_laterals_adamw_train_step_images_per_sec_800x1333", "value": world * B * K / (ms / 1e3),
             "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "fwd_bwd_ms_per_step": ms_fb / K,
